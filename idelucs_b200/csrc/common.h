@@ -1,0 +1,17 @@
+// idelucs_b200 — internal helpers shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/idelucs_b200.h"
+
+namespace idl {
+// records the thread-local error text returned by idl_last_error(); returns `code`
+int set_error(int code, const char* fmt, const char* a = "", long long b = 0);
+}  // namespace idl
+
+#define IDL_CUDA_CHECK(expr)                                                                             \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return ::idl::set_error(IDL_ECUDA, "%s (cuda error %lld)", cudaGetErrorString(_e), (long long)_e); \
+    } while (0)

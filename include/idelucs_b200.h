@@ -1,0 +1,157 @@
+/* idelucs_b200 — C ABI of the B200-native iDeLUCS featurisation / mimic / IIC-loss hot path.
+ *
+ * The reference (Kari-Genomics-Lab/iDeLUCS) has no FFI: its boundary for this path is a set
+ * of Python callables.  Each entry point below names the reference interface it replaces
+ * (file:line into the upstream repository); the Python shims in idelucs_b200/ keep the
+ * reference names and signatures and bind these symbols through ctypes.
+ *
+ * Conventions
+ *  - plain C, no C++ / torch types; every pointer whose name starts with d_ is a DEVICE
+ *    pointer owned by the caller (e.g. the PyTorch caching allocator); the library never
+ *    allocates or frees persistent device memory and never synchronises the stream;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *  - return value 0 = ok, otherwise an IDL_E* code; idl_last_error() gives the text
+ *    (thread-local).  No exceptions, no exit();
+ *  - packed sequence set ("seqset"):
+ *      d_codes     uint32, 2 bits/base, 16 bases/word, big-endian inside the word
+ *                  (A=0 C=1 G=2 T=3 — idelucs/kmers.pyx:19-34 numbering)
+ *      d_nmask     uint32, 1 bit/base (bit 31-j of a word = base j): 1 = window reset
+ *      d_chunk_off int64[n+1]: first 64-base chunk of every sequence (4 code words,
+ *                  2 mask words per chunk); chunk_off[n] = number of chunks in use; the
+ *                  buffers hold chunk_off[n]+1 chunks (one slack chunk)
+ *      d_len       int32[n]: bases per sequence
+ */
+#ifndef IDELUCS_B200_H
+#define IDELUCS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDL_ABI_VERSION 1
+
+enum {
+    IDL_OK = 0,
+    IDL_EINVAL = 1,      /* bad argument */
+    IDL_ECUDA = 2,       /* CUDA runtime error (text in idl_last_error) */
+    IDL_EUNSUPPORTED = 3 /* valid request this build cannot serve (e.g. k > 6) */
+};
+
+/* variant kinds: the transforms of idelucs/utils.py:54-135 */
+enum {
+    IDL_KIND_CLEAN = 0,        /* no mutation (kmersFasta(transform=None), utils.py:401) */
+    IDL_KIND_TRANSITION = 1,   /* transition(p1), utils.py:54-76 */
+    IDL_KIND_TRANSVERSION = 2, /* transversion(p2), utils.py:98-118 */
+    IDL_KIND_BOTH = 3,         /* transition_transversion(p1, p2), utils.py:120-135 */
+    IDL_KIND_RANDOM_N = 4,     /* Random_N(n_bp), utils.py:78-95 */
+    IDL_KIND_EXPLICIT = 5      /* caller-supplied edit list (parity with the reference's own RNG) */
+};
+
+/* output kinds of idl_profiles */
+enum {
+    IDL_OUT_COUNTS_I32 = 0, /* raw window counts, no pseudocount (kmers.pyx:2-50) */
+    IDL_OUT_FREQ_F32 = 1,   /* float32((count+pc)/sum)  (utils.py:242-250 then :353 astype) */
+    IDL_OUT_STD_F32 = 2,    /* (freq32 - mean32) / scale32  (utils.py:358-366 via sklearn) */
+    IDL_OUT_FREQ_F64 = 3    /* float64 (count+pc)/sum  (utils.py:250) */
+};
+
+/* One mimic variant.  rng_id is the variant's identity in the counter-based RNG, so the
+ * same (seed, sequence id, rng_id) always regenerates the same mimic, in any batch, on any
+ * rank.  explicit_idx selects the edit list block for IDL_KIND_EXPLICIT. */
+typedef struct idl_variant {
+    int32_t kind;
+    int32_t rng_id;
+    int32_t n_bp;         /* Random_N */
+    int32_t explicit_idx; /* EXPLICIT: lists are d_edit_off[explicit_idx * n_seqs_total + seq] */
+    double p1;            /* transition probability */
+    double p2;            /* transversion probability */
+} idl_variant;
+
+int idl_abi_version(void);
+const char* idl_last_error(void);
+
+/* T[g-1] = floor((1-(1-p)^g) * 2^32), g = 1..128: the geometric gap table the rng mode
+ * uses for an iid Bernoulli(p) process (host function; exported for the parity tests). */
+int idl_geometric_table(double p, uint32_t* out128);
+
+/* K1 — replaces check_sequence (idelucs/utils.py:26-51) + the byte LUT of kmer_counts
+ * (idelucs/kmers.pyx:19-34).  d_ascii: concatenated sequence bytes; d_byte_off int64[n+1].
+ * alphabet 0 = check_sequence mapping (acgtu -> ACGTT, IUPAC/'-' -> N, invalid bytes are
+ * reported), 1 = strict kmers.pyx LUT (only 'A','C','G','T' are bases, nothing is invalid).
+ * d_bad uint64[n] must be preset to 0xFF..FF by the caller; after the call an entry is
+ * (pos << 3 | cls) of the first offending byte (cls 5 = whitespace that check_sequence
+ * deletes, 6 = invalid byte) or still all-ones.  max_len = longest sequence (host hint). */
+int idl_pack(const uint8_t* d_ascii, const int64_t* d_byte_off, int64_t n, int alphabet, int64_t max_len,
+             const int64_t* d_chunk_off, uint32_t* d_codes, uint32_t* d_nmask, int32_t* d_len,
+             unsigned long long* d_bad, void* stream);
+
+/* workspace (bytes) idl_profiles needs in d_workspace */
+size_t idl_profiles_workspace_bytes(void);
+
+/* K2 + K3 — replaces kmer_counts (idelucs/kmers.pyx:2-50), the per-record body of
+ * kmersFasta (idelucs/utils.py:239-250) and the mimic passes of AugmentFasta
+ * (idelucs/utils.py:330-351).
+ *
+ * Work items: n_items; item w processes sequence d_sidx[w] (or w when d_sidx is NULL) and,
+ * for s in [0, S): variant slot d_sel[w*S+s] (or s when d_sel is NULL; then S must equal
+ * n_variants).  Row (s, w) of the output is written at element offset
+ * out_off[s] + w*out_stride of d_out (elements of the out_kind's type; multiples of 4).
+ * The RNG sequence id of an item is seq_id0 + its sequence index.
+ * d_edit_off / d_edits: CSR edit lists for IDL_KIND_EXPLICIT variants (entry = pos<<3 | val,
+ * val 0..3 = set A/C/G/T, 4 = set N; position-sorted and unique per list), n_seqs_total =
+ * number of sequences the CSR is indexed over.  d_mean/d_scale: float32[4^k] for
+ * IDL_OUT_STD_F32.  accumulate != 0 (COUNTS only) adds into d_out like kmers.pyx does.
+ * d_status int32[n_items] (optional): bit 0 set when an item's edit list overflowed the
+ * on-chip list (the item's outputs for that variant are then unmutated). */
+int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
+                 const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
+                 int64_t seq_id0, int k, const idl_variant* variants, int n_variants, const int32_t* d_sel,
+                 int S, uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits, int out_kind,
+                 void* d_out, const int64_t* out_off, int64_t out_stride, int pseudocount, int accumulate,
+                 const float* d_mean, const float* d_scale, int32_t* d_status, void* d_workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* Convenience form of the above for kmer_counts (idelucs/kmers.pyx:2-50): raw int32 counts
+ * of every sequence into d_counts[n, 4^k] (accumulating when accumulate != 0). */
+int idl_kmer_counts(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
+                    const int32_t* d_len, int64_t n, int k, int32_t* d_counts, int accumulate,
+                    void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* K4 — replaces sklearn StandardScaler.fit as called at idelucs/utils.py:358-359 (float32
+ * t_norm profiles) and :404-405 (float64 clean profiles).
+ * idl_colstats: per-column (count, mean, M2) partials of a row-major [n, F] matrix
+ * (is_f64: 0 = float32, 1 = float64) into d_partials double[n_parts][2][F] and
+ * d_part_n double[n_parts]; n_parts = idl_colstats_parts(n).
+ * idl_scaler_finalize: Chan-merges n_parts partials in index order (deterministic) and
+ * emits float64 mean/var/scale with sklearn's near-constant rule (scale 1) plus float32
+ * copies.  Multi-GPU: all-gather the partials of every rank and finalize over all of them. */
+int idl_colstats_parts(int64_t n);
+int idl_colstats(const void* d_x, int is_f64, int64_t n, int F, double* d_partials, double* d_part_n,
+                 void* stream);
+int idl_scaler_finalize(const double* d_partials, const double* d_part_n, int n_parts, int F, double* d_mean64,
+                        double* d_var64, double* d_scale64, float* d_mean32, float* d_scale32, void* stream);
+
+/* replaces StandardScaler.transform at idelucs/utils.py:361-363 (float32, in place or out of
+ * place: (x - mean32) / scale32 with IEEE float32 rounding) and :405 (float64:
+ * (x - mean64) / scale64, optionally also written as float32 like models.py:163 casts it). */
+int idl_standardize_f32(const float* d_x, float* d_out, int64_t n, int F, const float* d_mean32,
+                        const float* d_scale32, void* stream);
+int idl_standardize_f64(const double* d_x, double* d_out64, float* d_out32, int64_t n, int F,
+                        const double* d_mean64, const double* d_scale64, void* stream);
+
+/* K5 — replaces IID_loss / compute_joint (idelucs/LossFunctions.py:20-62), forward and
+ * backward in one launch.  d_z1, d_z2: float32 [B, C] row-major.  Outputs (each optional,
+ * NULL to skip): d_loss float32[1]; d_joint float32[C, C] (symmetrised, normalised,
+ * unclamped — compute_joint's return value); d_dz1, d_dz2 float32 [B, C] = dLoss/dz.
+ * C <= idl_iid_loss_max_clusters(). */
+int idl_iid_loss_max_clusters(void);
+int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float* d_loss,
+                 float* d_joint, float* d_dz1, float* d_dz2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDELUCS_B200_H */
