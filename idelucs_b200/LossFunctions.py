@@ -1,0 +1,80 @@
+"""Loss functions with the reference's names and signatures (idelucs/LossFunctions.py).
+
+``IID_loss`` / ``compute_joint`` run the fused sm_100a kernel K5 (forward + backward in one
+cooperative launch) through the C ABI.  ``info_nce_loss`` is a dense 2B x 2B contraction
+and stays PyTorch/cuBLAS, as the scope contract says."""
+import sys
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def _ws(device, C):
+    from .featurise import _workspace
+    return _workspace(device, _lib.load().idl_iid_loss_workspace_bytes(C), "loss%d" % C)
+
+
+class _IIDLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_out, x_tf_out, lamb, EPS):
+        lib = _lib.load()
+        if not x_out.is_cuda:
+            raise _lib.IdelucsB200Error("IID_loss: tensors must be on a CUDA device (no CPU fallback)")
+        z1 = x_out.detach().contiguous().float()
+        z2 = x_tf_out.detach().contiguous().float()
+        B, C = z1.shape
+        assert z2.shape == (B, C)
+        loss = torch.empty((), dtype=torch.float32, device=z1.device)
+        need_grad = x_out.requires_grad or x_tf_out.requires_grad
+        dz1 = torch.empty_like(z1) if need_grad else None
+        dz2 = torch.empty_like(z2) if need_grad else None
+        with torch.cuda.device(z1.device):
+            ws = _ws(z1.device, C)
+            _lib.check(lib.idl_iid_loss(_lib.ptr(z1), _lib.ptr(z2), B, C, float(lamb), float(EPS), _lib.ptr(loss), None,
+                                        _lib.ptr(dz1), _lib.ptr(dz2), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        if need_grad:
+            ctx.save_for_backward(dz1, dz2)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dz1, dz2 = ctx.saved_tensors
+        return grad_out * dz1, grad_out * dz2, None, None
+
+
+def IID_loss(x_out, x_tf_out, lamb=1.0, EPS=sys.float_info.epsilon):
+    """idelucs/LossFunctions.py:20-46 — same arguments, returns a 0-d tensor with autograd."""
+    return _IIDLoss.apply(x_out, x_tf_out, lamb, EPS)
+
+
+def compute_joint(x_out, x_tf_out):
+    """idelucs/LossFunctions.py:49-62 — symmetrised, normalised joint [C, C] (no autograd)."""
+    lib = _lib.load()
+    z1 = x_out.detach().contiguous().float()
+    z2 = x_tf_out.detach().contiguous().float()
+    B, C = z1.shape
+    joint = torch.empty((C, C), dtype=torch.float32, device=z1.device)
+    with torch.cuda.device(z1.device):
+        ws = _ws(z1.device, C)
+        _lib.check(lib.idl_iid_loss(_lib.ptr(z1), _lib.ptr(z2), B, C, 1.0, float(sys.float_info.epsilon), None,
+                                    _lib.ptr(joint), None, None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return joint
+
+
+def info_nce_loss(z1, z2, temperature):
+    """SimCLR NT-Xent (idelucs/LossFunctions.py:65-98), PyTorch ops; written for the device
+    the inputs live on (the reference builds its masks on the CPU and moves them)."""
+    n = z1.shape[0]
+    feats = F.normalize(torch.cat((z1, z2), 0).float(), dim=1)
+    sim = feats @ feats.T
+    idx = torch.arange(2 * n, device=sim.device)
+    pos = sim[idx, (idx + n) % (2 * n)].unsqueeze(1)                   # the other view of the same sample
+    neg_mask = torch.ones_like(sim, dtype=torch.bool)
+    neg_mask[idx, idx] = False
+    neg_mask[idx, (idx + n) % (2 * n)] = False
+    neg = sim[neg_mask].view(2 * n, -1)
+    logits = torch.cat([pos, neg], dim=1) / temperature
+    labels = torch.zeros(2 * n, dtype=torch.long, device=sim.device)
+    return F.cross_entropy(logits, labels)

@@ -1,0 +1,89 @@
+"""ctypes binding of libidelucs_b200.so (the C ABI declared in include/idelucs_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libidelucs_b200.so")
+
+IDL_OK = 0
+KIND_CLEAN, KIND_TRANSITION, KIND_TRANSVERSION, KIND_BOTH, KIND_RANDOM_N, KIND_EXPLICIT = range(6)
+OUT_COUNTS_I32, OUT_FREQ_F32, OUT_STD_F32, OUT_FREQ_F64 = range(4)
+
+c_void_p, c_int, c_i64, c_u64, c_size_t, c_double, c_float = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_double, ctypes.c_float)
+
+
+class Variant(ctypes.Structure):
+    """struct idl_variant"""
+    _fields_ = [("kind", ctypes.c_int32), ("rng_id", ctypes.c_int32), ("n_bp", ctypes.c_int32),
+                ("explicit_idx", ctypes.c_int32), ("p1", c_double), ("p2", c_double)]
+
+
+# every symbol include/idelucs_b200.h declares: name -> (restype, argtypes)
+PROTOTYPES = {
+    "idl_abi_version": (c_int, []),
+    "idl_last_error": (ctypes.c_char_p, []),
+    "idl_geometric_table": (c_int, [c_double, c_void_p]),
+    "idl_pack": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "idl_profiles_workspace_bytes": (c_size_t, []),
+    "idl_profiles": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int,
+                             ctypes.POINTER(Variant), c_int, c_void_p, c_int, c_u64, c_void_p, c_void_p, c_int,
+                             c_void_p, ctypes.POINTER(c_i64), c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_size_t, c_void_p]),
+    "idl_kmer_counts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "idl_colstats_parts": (c_int, [c_i64]),
+    "idl_colstats": (c_int, [c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
+    "idl_scaler_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "idl_standardize_f32": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
+    "idl_standardize_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
+    "idl_iid_loss_max_clusters": (c_int, []),
+    "idl_iid_loss_workspace_bytes": (c_size_t, [c_int]),
+    "idl_iid_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+class IdelucsB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and bind every prototype.  Raises if it is missing —
+    the product path has no CPU or PyTorch fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IdelucsB200Error(
+            "libidelucs_b200.so not found at %s — build it with `python __graft_entry__.py` "
+            "(nvcc, sm_100a). idelucs_b200 has no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.idl_abi_version() != 1:
+        raise IdelucsB200Error("ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != IDL_OK:
+        msg = load().idl_last_error().decode(errors="replace")
+        raise IdelucsB200Error("idelucs_b200 call failed (code %d): %s" % (rc, msg))
+
+
+def ptr(t):
+    """device (or host) pointer of a torch tensor / None"""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

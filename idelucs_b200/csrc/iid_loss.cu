@@ -1,0 +1,267 @@
+// idelucs_b200 — K5: IIC mutual-information loss, forward + backward in ONE cooperative launch.
+//
+// Replaces idelucs/LossFunctions.py:20-62 (IID_loss -> compute_joint) and its autograd
+// backward.  The reference materialises a [B, C, C] broadcast product (82 MB at C=200) and
+// runs ~20 small kernels; here the C x C joint is tiled 16 x 16 over CTAs, each CTA owning a
+// tile and its transpose (the joint is symmetrised, LossFunctions.py:59), and the phases
+// are separated by grid-wide barriers:
+//   1. S = z1^T z2 tile (+ transposed tile); Ssym = (S + S^T)/2; partial total and marginals
+//   2. P = Ssym / T, clamp at EPS (:36-38), entropy terms (:40-44), loss partial, dL/dP pieces
+//   3. dS = (G - <G,P>) / T for the tile -> global
+//   4. dz1 = z2 dS^T, dz2 = z1 dS  (the closed-form backward)
+// All cross-CTA reductions go through fixed-order partial arrays (no float atomics), so the
+// result is bit-reproducible run to run.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace cg = cooperative_groups;
+
+namespace idl {
+
+constexpr int LT = 16;          // joint tile edge
+constexpr int LNT = 256;        // threads per CTA (LT * LT)
+constexpr int LBC = 64;         // batch rows staged per step
+constexpr int LMAXC = 256;      // max clusters of the fused kernel
+constexpr int LMAXT = LMAXC / LT;
+
+struct LossParams {
+    const float* z1;
+    const float* z2;
+    int B, C, nt, npairs;
+    float lamb, eps;
+    float* loss;
+    float* joint;
+    float* dz1;
+    float* dz2;
+    // workspace
+    float* partT;     // [npairs]
+    float* partLoss;  // [npairs]
+    float* partAP;    // [npairs]
+    float* marg;      // [nt][LMAXC]  marg[t][i] = sum_{j in tile t} Ssym[i][j]
+    float* corr;      // [nt][LMAXC]  corr[t][i] = sum_{j in tile t, P_ij < eps} (eps - P_ij)
+    float* dS;        // [C][C]
+};
+
+// deterministic block sum (fixed shuffle tree + fixed warp order); result valid in all threads
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < LNT / 32; ++w) t += scratch[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(LNT) iid_loss_kernel(const LossParams p) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float sA[4][LBC][LT];       // phase 1: z1[:,I] z2[:,J] z1[:,J] z2[:,I]; phase 4: z chunk / dS chunk
+    __shared__ float sRed[LNT / 32];
+    __shared__ float sRow[LT][LT + 1];
+    __shared__ float sVec[2][LMAXC];       // pic (clamped marginal), g (marginal gradient term)
+    const int tid = threadIdx.x;
+    const int ti = tid / LT, tj = tid % LT;
+    const int B = p.B, C = p.C;
+
+    // tile pair of this CTA: (I, J) with I <= J, enumerated row by row
+    int I = 0, rem = blockIdx.x;
+    while (rem >= p.nt - I) { rem -= p.nt - I; ++I; }
+    const int J = I + rem;
+    const int I0 = I * LT, J0 = J * LT;
+    const int gi = I0 + ti, gj = J0 + tj;
+    const bool valid = gi < C && gj < C;
+    const float wgt = (I == J) ? 1.f : 2.f;
+
+    // ---- phase 1: S tile and its transpose ------------------------------------------------
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    for (int r0 = 0; r0 < B; r0 += LBC) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < (LBC * LT) / LNT; ++q) {
+            const int idx = tid + q * LNT;
+            const int row = idx / LT, col = idx % LT;
+            const int b = r0 + row;
+            const bool rb = b < B;
+            const bool ci = rb && (I0 + col) < C, cj = rb && (J0 + col) < C;
+            sA[0][row][col] = ci ? p.z1[(size_t)b * C + I0 + col] : 0.f;
+            sA[3][row][col] = ci ? p.z2[(size_t)b * C + I0 + col] : 0.f;
+            sA[1][row][col] = cj ? p.z2[(size_t)b * C + J0 + col] : 0.f;
+            sA[2][row][col] = cj ? p.z1[(size_t)b * C + J0 + col] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < LBC; r += 2) {
+            a0 = fmaf(sA[0][r][ti], sA[1][r][tj], a0);
+            b0 = fmaf(sA[2][r][tj], sA[3][r][ti], b0);
+            a1 = fmaf(sA[0][r + 1][ti], sA[1][r + 1][tj], a1);
+            b1 = fmaf(sA[2][r + 1][tj], sA[3][r + 1][ti], b1);
+        }
+    }
+    const float ssym = valid ? ((a0 + a1) + (b0 + b1)) / 2.f : 0.f;  // (S_ij + S_ji) / 2, LossFunctions.py:59
+    {
+        const float t = block_sum(ssym * wgt, sRed);
+        if (tid == 0) p.partT[blockIdx.x] = t;
+        // marginal partials: row sums over this tile's columns, column sums for the mirrored tile
+        sRow[ti][tj] = ssym;
+        __syncthreads();
+        if (tid < LT) {
+            float rs = 0.f, cs = 0.f;
+#pragma unroll
+            for (int q = 0; q < LT; ++q) { rs += sRow[tid][q]; cs += sRow[q][tid]; }
+            if (I0 + tid < C) p.marg[J * LMAXC + I0 + tid] = rs;
+            if (I != J && J0 + tid < C) p.marg[I * LMAXC + J0 + tid] = cs;
+        }
+    }
+    grid.sync();
+
+    // ---- phase 2: normalise, clamp, entropy terms ------------------------------------------
+    float T = 0.f;
+    for (int q = 0; q < p.npairs; ++q) T += p.partT[q];   // same order in every CTA
+    const float invT = 1.0f / T;
+    // marginals p_i (== p_j by symmetry) for all clusters, clamped copy in sVec[0]
+    for (int i = tid; i < C; i += LNT) {
+        float m = 0.f;
+        for (int t = 0; t < p.nt; ++t) m += p.marg[t * LMAXC + i];
+        sVec[1][i] = m / T;  // raw marginal (temporarily)
+    }
+    __syncthreads();
+    const float P = ssym / T;                                  // LossFunctions.py:60
+    const float pi_raw = valid ? sVec[1][gi] : 1.f, pj_raw = valid ? sVec[1][gj] : 1.f;
+    const bool cl = P < p.eps;
+    const float Pc = cl ? p.eps : P;                           // :36
+    const float pic = pi_raw < p.eps ? p.eps : pi_raw;         // :38
+    const float pjc = pj_raw < p.eps ? p.eps : pj_raw;         // :37
+    const float inner = logf(Pc) - p.lamb * logf(pjc) - p.lamb * logf(pic);
+    const float term = valid ? -Pc * inner : 0.f;              // :40-42
+    const float Aij = (valid && !cl) ? (-inner - 1.f) : 0.f;   // d term / d P_ij through the unclamped entry
+    {
+        const float l = block_sum(term * wgt, sRed);
+        const float ap = block_sum(Aij * P * wgt, sRed);
+        if (tid == 0) { p.partLoss[blockIdx.x] = l; p.partAP[blockIdx.x] = ap; }
+        // clamp corrections of the row sums of Pc (enter d term / d p_i)
+        __syncthreads();
+        sRow[ti][tj] = (valid && cl) ? (p.eps - P) : 0.f;
+        __syncthreads();
+        if (tid < LT) {
+            float rs = 0.f, cs = 0.f;
+#pragma unroll
+            for (int q = 0; q < LT; ++q) { rs += sRow[tid][q]; cs += sRow[q][tid]; }
+            if (I0 + tid < C) p.corr[J * LMAXC + I0 + tid] = rs;
+            if (I != J && J0 + tid < C) p.corr[I * LMAXC + J0 + tid] = cs;
+        }
+        if (p.joint && valid) {                                // compute_joint's return value
+            p.joint[(size_t)gi * C + gj] = P;
+            p.joint[(size_t)gj * C + gi] = P;
+        }
+    }
+    (void)invT;
+    grid.sync();
+
+    // ---- phase 3: loss, dL/dS tile -------------------------------------------------------------
+    if (blockIdx.x == 0 && tid == 0 && p.loss) {
+        float l = 0.f;
+        for (int q = 0; q < p.npairs; ++q) l += p.partLoss[q];
+        *p.loss = l;                                           // :44
+    }
+    if (!p.dz1 && !p.dz2) return;                              // uniform over the grid
+    // g_i = lamb * (sum_j Pc_ij) / pic_i for unclamped marginals: the loss holds
+    // +lamb * Pc_ij * log p_i (row marginal) and +lamb * Pc_ij * log p_j (column marginal)
+    float gp = 0.f;
+    for (int i = tid; i < C; i += LNT) {
+        const float m = sVec[1][i];
+        float c = 0.f;
+        for (int t = 0; t < p.nt; ++t) c += p.corr[t * LMAXC + i];
+        const float g = m < p.eps ? 0.f : p.lamb * (m + c) / m;
+        gp += 2.f * g * m;                                     // <g_i 1^T + 1 g_j^T, P> = 2 sum_i g_i p_i
+        sVec[0][i] = g;
+    }
+    gp = block_sum(gp, sRed);
+    for (int q = 0; q < p.npairs; ++q) gp += p.partAP[q];      // <A, P>
+    if (valid) {
+        const float G = Aij + sVec[0][gi] + sVec[0][gj];
+        const float d = (G - gp) / T;                          // dL/dSsym; dS = (dSsym + dSsym^T)/2 = dSsym (symmetric)
+        p.dS[(size_t)gi * C + gj] = d;
+        p.dS[(size_t)gj * C + gi] = d;
+    }
+    grid.sync();
+
+    // ---- phase 4: dz1[b,i] = sum_j z2[b,j] dS[i,j];  dz2[b,j] = sum_i z1[b,i] dS[i,j] -----------
+    // (dS symmetric => both are  z_other[b,:] . dS[col,:])
+    const int nrb = (B + LBC - 1) / LBC;
+    const int n_work = nrb * p.nt * 2;
+    float (*sZ)[LT] = sA[0];           // [LBC][LT] chunk of the other view's z
+    float (*sD)[LT + 1] = reinterpret_cast<float (*)[LT + 1]>(&sA[1][0][0]);  // [LT][LT+1] chunk of dS rows
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int which = w & 1;
+        const int ct = (w >> 1) % p.nt;
+        const int rb = (w >> 1) / p.nt;
+        float* out = which == 0 ? p.dz1 : p.dz2;
+        const float* zo = which == 0 ? p.z2 : p.z1;
+        if (!out) continue;
+        const int r0 = rb * LBC, c0 = ct * LT;
+        float acc[LBC / LT] = {0.f, 0.f, 0.f, 0.f};
+        for (int j0 = 0; j0 < C; j0 += LT) {
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < (LBC * LT) / LNT; ++q) {
+                const int idx = tid + q * LNT;
+                const int row = idx / LT, col = idx % LT;
+                sZ[row][col] = (r0 + row < B && j0 + col < C) ? zo[(size_t)(r0 + row) * C + j0 + col] : 0.f;
+            }
+            sD[ti][tj] = (c0 + ti < C && j0 + tj < C) ? p.dS[(size_t)(c0 + ti) * C + j0 + tj] : 0.f;
+            __syncthreads();
+#pragma unroll
+            for (int jj = 0; jj < LT; ++jj) {
+                const float d = sD[tj][jj];
+#pragma unroll
+                for (int q = 0; q < LBC / LT; ++q) acc[q] = fmaf(sZ[ti + q * LT][jj], d, acc[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < LBC / LT; ++q) {
+            const int b = r0 + ti + q * LT;
+            if (b < B && c0 + tj < C) out[(size_t)b * C + c0 + tj] = acc[q];
+        }
+    }
+}
+
+}  // namespace idl
+
+using namespace idl;
+
+extern "C" {
+
+int idl_iid_loss_max_clusters(void) { return LMAXC; }
+
+size_t idl_iid_loss_workspace_bytes(int C) {
+    if (C < 1 || C > LMAXC) return 0;
+    const size_t nt = (C + LT - 1) / LT, npairs = nt * (nt + 1) / 2;
+    return sizeof(float) * (3 * npairs + 2 * nt * LMAXC + (size_t)C * C) + 64;
+}
+
+int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float* d_loss,
+                 float* d_joint, float* d_dz1, float* d_dz2, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!d_z1 || !d_z2 || !d_workspace || B < 1 || C < 1) return set_error(IDL_EINVAL, "idl_iid_loss: bad argument%s", "");
+    if (C > LMAXC) return set_error(IDL_EUNSUPPORTED, "idl_iid_loss: n_clusters > 256 not supported%s (got %lld)", "", C);
+    if (workspace_bytes < idl_iid_loss_workspace_bytes(C)) return set_error(IDL_EINVAL, "idl_iid_loss: workspace too small%s", "");
+    LossParams p;
+    p.z1 = d_z1; p.z2 = d_z2; p.B = B; p.C = C;
+    p.nt = (C + LT - 1) / LT; p.npairs = p.nt * (p.nt + 1) / 2;
+    p.lamb = lamb; p.eps = eps; p.loss = d_loss; p.joint = d_joint; p.dz1 = d_dz1; p.dz2 = d_dz2;
+    float* w = reinterpret_cast<float*>(d_workspace);
+    p.partT = w; w += p.npairs;
+    p.partLoss = w; w += p.npairs;
+    p.partAP = w; w += p.npairs;
+    p.marg = w; w += (size_t)p.nt * LMAXC;
+    p.corr = w; w += (size_t)p.nt * LMAXC;
+    p.dS = w;
+    void* args[] = {(void*)&p};
+    IDL_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)iid_loss_kernel, dim3(p.npairs), dim3(LNT), args, 0, (cudaStream_t)stream));
+    return IDL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+"""K2/K3/K4 host API: k-mer profiles of a SeqSet for a list of mimic variants, scaler
+statistics and standardisation.  Thin wrappers over the C ABI; all arithmetic is in CUDA."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (KIND_BOTH, KIND_CLEAN, KIND_EXPLICIT, KIND_RANDOM_N, KIND_TRANSITION, KIND_TRANSVERSION,  # noqa: F401
+                   OUT_COUNTS_I32, OUT_FREQ_F32, OUT_FREQ_F64, OUT_STD_F32)
+
+_OUT_DTYPE = {OUT_COUNTS_I32: torch.int32, OUT_FREQ_F32: torch.float32, OUT_STD_F32: torch.float32,
+              OUT_FREQ_F64: torch.float64}
+
+# hard-coded rates of the reference's AugmentFasta (idelucs/utils.py:330-349)
+P_TRANSITION, P_TRANSVERSION, N_RANDOM_N = 1e-2, 0.5e-2, 20
+
+
+class VariantSpec(object):
+    """One mimic variant: kind + parameters (+ rng_id: its identity in the Philox counter)."""
+
+    def __init__(self, kind, p1=0.0, p2=0.0, n_bp=0, rng_id=None, explicit_idx=0):
+        self.kind, self.p1, self.p2, self.n_bp, self.rng_id, self.explicit_idx = kind, p1, p2, n_bp, rng_id, explicit_idx
+
+    def __repr__(self):
+        return "VariantSpec(kind=%d, p1=%g, p2=%g, n_bp=%d, rng_id=%s)" % (self.kind, self.p1, self.p2, self.n_bp, self.rng_id)
+
+
+def mimic_schedule(n_mimics):
+    """Variants of AugmentFasta's pass schedule (idelucs/utils.py:330-351): pass 0 =
+    transition_transversion(1e-2, 0.5e-2) (t_norm, the 'true' column), pass 1 =
+    transition(1e-2), pass 2 = transversion(0.5e-2), passes 3..n_mimics = Random_N(20).
+    Like the reference, passes 0..2 always exist (n_mimics < 2 still yields 2 mimics)."""
+    v = [VariantSpec(KIND_BOTH, P_TRANSITION, P_TRANSVERSION), VariantSpec(KIND_TRANSITION, p1=P_TRANSITION),
+         VariantSpec(KIND_TRANSVERSION, p2=P_TRANSVERSION)]
+    v += [VariantSpec(KIND_RANDOM_N, n_bp=N_RANDOM_N) for _ in range(n_mimics - 2)]
+    for i, s in enumerate(v):
+        s.rng_id = i
+    return v
+
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes, tag):
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream, tag)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def pack_edit_lists(explicit, n_seqs, device):
+    """explicit: list (one per EXPLICIT variant) of per-sequence (pos, val) pairs, val in 0..4
+    (A C G T N) -> CSR (int64 offsets, int32-typed uint32 entries pos<<3|val) on the device."""
+    offs = [0]
+    chunks = []
+    for lists in explicit:
+        assert len(lists) == n_seqs
+        for pos, val in lists:
+            pos = np.asarray(pos, dtype=np.int64)
+            val = np.asarray(val, dtype=np.int64)
+            order = np.argsort(pos, kind="stable")
+            pos, val = pos[order], val[order]
+            if pos.size and (np.diff(pos) <= 0).any():
+                raise ValueError("explicit edit positions must be unique per sequence")
+            chunks.append(((pos << 3) | val).astype(np.uint32))
+            offs.append(offs[-1] + pos.size)
+    ent = np.concatenate(chunks) if chunks else np.zeros(0, np.uint32)
+    if ent.size == 0:
+        ent = np.zeros(1, np.uint32)
+    d_off = torch.from_numpy(np.asarray(offs, dtype=np.int64)).to(device)
+    d_ent = torch.from_numpy(ent.view(np.int32)).to(device)
+    return d_off, d_ent
+
+
+def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_off=None, out_stride=None,
+             mean=None, scale=None, sidx=None, sel=None, S=None, edit_lists=None, seq_id0=0, pseudocount=None,
+             accumulate=False, status=None):
+    """Run K2+K3.  Default output: tensor [S, n_items, 4^k] (variant-major) of the out_kind's
+    dtype.  See include/idelucs_b200.h::idl_profiles for the argument meaning."""
+    lib = _lib.load()
+    device = seqset.device
+    F = 4 ** k
+    n_items = int(sidx.numel()) if sidx is not None else seqset.n
+    nv = len(variants)
+    if S is None:
+        S = nv if sel is None else int(sel.shape[1])
+    if pseudocount is None:
+        pseudocount = 0 if out_kind == OUT_COUNTS_I32 else 1
+    if out is None:
+        out = torch.empty((S, n_items, F), dtype=_OUT_DTYPE[out_kind], device=device)
+        out_off = [s * n_items * F for s in range(S)]
+        out_stride = F
+    assert out.dtype == _OUT_DTYPE[out_kind] and out.is_contiguous()
+    varr = (_lib.Variant * nv)()
+    for i, v in enumerate(variants):
+        varr[i].kind, varr[i].rng_id, varr[i].n_bp = v.kind, (v.rng_id if v.rng_id is not None else i), v.n_bp
+        varr[i].explicit_idx, varr[i].p1, varr[i].p2 = v.explicit_idx, v.p1, v.p2
+    offs = (ctypes.c_int64 * S)(*[int(o) for o in out_off])
+    d_eoff, d_ent = (None, None) if edit_lists is None else edit_lists
+    with torch.cuda.device(device):
+        ws = _workspace(device, lib.idl_profiles_workspace_bytes(), "prof")
+        _lib.check(lib.idl_profiles(
+            _lib.ptr(seqset.codes), _lib.ptr(seqset.nmask), _lib.ptr(seqset.chunk_off), _lib.ptr(seqset.len), seqset.n,
+            _lib.ptr(sidx), n_items, int(seq_id0), k, varr, nv, _lib.ptr(sel), S, ctypes.c_uint64(seed & (2 ** 64 - 1)),
+            _lib.ptr(d_eoff), _lib.ptr(d_ent), out_kind, _lib.ptr(out), offs, int(out_stride), int(pseudocount),
+            1 if accumulate else 0, _lib.ptr(mean), _lib.ptr(scale), _lib.ptr(status), _lib.ptr(ws), ws.numel(),
+            _lib.stream_ptr()))
+    return out
+
+
+def kmer_counts_batch(seqset, k, counts=None):
+    """int32 counts [n, 4^k] of every sequence (idelucs/kmers.pyx:2-50 per sequence)."""
+    lib = _lib.load()
+    accumulate = counts is not None
+    if counts is None:
+        counts = torch.empty((seqset.n, 4 ** k), dtype=torch.int32, device=seqset.device)
+    with torch.cuda.device(seqset.device):
+        ws = _workspace(seqset.device, lib.idl_profiles_workspace_bytes(), "prof")
+        _lib.check(lib.idl_kmer_counts(_lib.ptr(seqset.codes), _lib.ptr(seqset.nmask), _lib.ptr(seqset.chunk_off),
+                                       _lib.ptr(seqset.len), seqset.n, k, _lib.ptr(counts), 1 if accumulate else 0,
+                                       _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return counts
+
+
+class Scaler(object):
+    """StandardScaler statistics on the device (idelucs/utils.py:358-359, 404-405)."""
+
+    def __init__(self, mean64, var64, scale64, mean32, scale32, n):
+        self.mean64, self.var64, self.scale64, self.mean32, self.scale32, self.n = mean64, var64, scale64, mean32, scale32, n
+
+    @staticmethod
+    def partials(x):
+        """(partials [P,2,F] float64, part_n [P] float64) of a row-major [n, F] float32/float64 matrix"""
+        lib = _lib.load()
+        assert x.dim() == 2 and x.is_contiguous() and x.dtype in (torch.float32, torch.float64)
+        n, F = x.shape
+        P = lib.idl_colstats_parts(n)
+        parts = torch.empty((P, 2, F), dtype=torch.float64, device=x.device)
+        part_n = torch.empty((P,), dtype=torch.float64, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.idl_colstats(_lib.ptr(x), 1 if x.dtype == torch.float64 else 0, n, F, _lib.ptr(parts),
+                                        _lib.ptr(part_n), _lib.stream_ptr()))
+        return parts, part_n
+
+    @classmethod
+    def from_partials(cls, parts, part_n):
+        lib = _lib.load()
+        P, _, F = parts.shape
+        dev = parts.device
+        mean64, var64, scale64 = (torch.empty(F, dtype=torch.float64, device=dev) for _ in range(3))
+        mean32, scale32 = (torch.empty(F, dtype=torch.float32, device=dev) for _ in range(2))
+        with torch.cuda.device(dev):
+            _lib.check(lib.idl_scaler_finalize(_lib.ptr(parts), _lib.ptr(part_n), P, F, _lib.ptr(mean64), _lib.ptr(var64),
+                                               _lib.ptr(scale64), _lib.ptr(mean32), _lib.ptr(scale32), _lib.stream_ptr()))
+        return cls(mean64, var64, scale64, mean32, scale32, None)
+
+    @classmethod
+    def fit(cls, x, group=None):
+        """Statistics of x's columns; with a torch.distributed group the per-rank partials are
+        all-gathered (rank order) and merged identically on every rank."""
+        parts, part_n = cls.partials(x)
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                 and torch.distributed.get_world_size() > 1):
+            parts, part_n = gather_partials(parts, part_n, group)
+        return cls.from_partials(parts, part_n)
+
+    def transform32(self, x, out=None):
+        lib = _lib.load()
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        F = x.shape[-1]
+        out = x if out is None else out
+        with torch.cuda.device(x.device):
+            _lib.check(lib.idl_standardize_f32(_lib.ptr(x), _lib.ptr(out), x.numel() // F, F, _lib.ptr(self.mean32),
+                                               _lib.ptr(self.scale32), _lib.stream_ptr()))
+        return out
+
+    def transform64(self, x, want32=False):
+        lib = _lib.load()
+        assert x.dtype == torch.float64 and x.is_contiguous()
+        F = x.shape[-1]
+        out64 = None if want32 else torch.empty_like(x)
+        out32 = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want32 else None
+        with torch.cuda.device(x.device):
+            _lib.check(lib.idl_standardize_f64(_lib.ptr(x), _lib.ptr(out64), _lib.ptr(out32), x.numel() // F, F,
+                                               _lib.ptr(self.mean64), _lib.ptr(self.scale64), _lib.stream_ptr()))
+        return out32 if want32 else out64
+
+
+def gather_partials(parts, part_n, group=None):
+    """all-gather variable-length scaler partials over the ranks (padding with empty parts)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    P = torch.tensor([parts.shape[0]], dtype=torch.int64, device=parts.device)
+    allP = [torch.zeros_like(P) for _ in range(world)]
+    dist.all_gather(allP, P, group=group)
+    maxP = int(max(int(p.item()) for p in allP))
+    F = parts.shape[2]
+    pad = torch.zeros((maxP, 2, F), dtype=torch.float64, device=parts.device)
+    padn = torch.zeros((maxP,), dtype=torch.float64, device=parts.device)
+    pad[: parts.shape[0]] = parts
+    padn[: parts.shape[0]] = part_n
+    gp = [torch.empty_like(pad) for _ in range(world)]
+    gn = [torch.empty_like(padn) for _ in range(world)]
+    dist.all_gather(gp, pad, group=group)
+    dist.all_gather(gn, padn, group=group)
+    return torch.cat(gp, 0).contiguous(), torch.cat(gn, 0).contiguous()

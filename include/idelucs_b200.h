@@ -146,10 +146,15 @@ int idl_standardize_f64(const double* d_x, double* d_out64, float* d_out32, int6
  * backward in one launch.  d_z1, d_z2: float32 [B, C] row-major.  Outputs (each optional,
  * NULL to skip): d_loss float32[1]; d_joint float32[C, C] (symmetrised, normalised,
  * unclamped — compute_joint's return value); d_dz1, d_dz2 float32 [B, C] = dLoss/dz.
- * C <= idl_iid_loss_max_clusters(). */
+ * C <= idl_iid_loss_max_clusters().  d_workspace: idl_iid_loss_workspace_bytes(C) bytes of
+ * scratch (fixed-order partial sums; no float atomics, results are run-to-run identical).
+ * One cooperative launch: the device must be able to co-schedule ceil(C/16)*(ceil(C/16)+1)/2
+ * CTAs of 256 threads (136 at C = 256; a B200 has 148 SMs). */
 int idl_iid_loss_max_clusters(void);
+size_t idl_iid_loss_workspace_bytes(int C);
 int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float* d_loss,
-                 float* d_joint, float* d_dz1, float* d_dz2, void* stream);
+                 float* d_joint, float* d_dz1, float* d_dz2, void* d_workspace, size_t workspace_bytes,
+                 void* stream);
 
 #ifdef __cplusplus
 }

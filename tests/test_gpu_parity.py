@@ -1,0 +1,304 @@
+"""GPU parity tests (run with -m gpu on the B200): the CUDA path, called through the C ABI
+(ctypes), against the CPU oracle on the same inputs and against the golden vectors that the
+live reference produced (oracle/gen_golden.py).  Integer work must be bit-exact."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import idelucs_oracle as orc
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ft():
+    from idelucs_b200 import featurise
+    return featurise
+
+
+@pytest.fixture(scope="module")
+def SeqSet():
+    from idelucs_b200.seqset import SeqSet
+    return SeqSet
+
+
+def _golden(golden_dir):
+    with open(os.path.join(golden_dir, "golden.json")) as fh:
+        return json.load(fh)
+
+
+def test_kmer_count_kats(golden_dir, ft, SeqSet):
+    with open(os.path.join(golden_dir, "kmer_kats.json")) as fh:
+        kats = json.load(fh)
+    for k in (1, 2, 3, 4, 5, 6):
+        sub = [c for c in kats if c["k"] == k]
+        if not sub:
+            continue
+        ss = SeqSet.from_sequences([bytes.fromhex(c["seq_hex"]) for c in sub], alphabet="strict")
+        got = ft.kmer_counts_batch(ss, k).cpu().numpy()
+        for i, c in enumerate(sub):
+            want = np.zeros(4 ** k, np.int32)
+            want[c["nz_idx"]] = c["nz_val"]
+            assert np.array_equal(got[i], want), (k, i)
+
+
+@pytest.mark.parametrize("stem", ["Influenza-A", "Actinopterygii"])
+@pytest.mark.parametrize("k", [4, 5, 6])
+def test_fasta_counts_and_frequencies(golden_dir, fasta_files, ft, SeqSet, stem, k):
+    g = _golden(golden_dir)["files"][stem][f"k{k}"]
+    ss = SeqSet.from_fasta(fasta_files[stem])
+    assert ss.n == g["n"]
+    counts = ft.kmer_counts_batch(ss, k).cpu().numpy()
+    assert int(counts.sum()) == g["counts_sum"]
+    assert counts[0, :8].tolist() == g["counts_row0"]
+    assert sha(counts) == g["counts_sha256"]            # bit-exact vs idelucs.kmers.kmer_counts
+    clean = [ft.VariantSpec(ft.KIND_CLEAN)]
+    f64 = ft.profiles(ss, k, clean, out_kind=ft.OUT_FREQ_F64)[0].cpu().numpy()
+    assert sha(f64) == g["freq64_sha256"]               # bit-exact vs idelucs.utils.kmersFasta
+    f32 = ft.profiles(ss, k, clean, out_kind=ft.OUT_FREQ_F32)[0].cpu().numpy()
+    assert sha(f32) == g["freq32_sha256"]               # == kmersFasta(...).astype(float32)
+    # accumulate semantics of kmers.pyx (counts are added INTO the caller's buffer)
+    acc = torch.ones((ss.n, 4 ** k), dtype=torch.int32, device="cuda")
+    ft.kmer_counts_batch(ss, k, counts=acc)
+    assert np.array_equal(acc.cpu().numpy(), counts + 1)
+
+
+def test_strict_alphabet_random_bytes(ft, SeqSet):
+    rng = np.random.default_rng(3)
+    seqs = [rng.integers(0, 256, size=int(rng.integers(0, 700)), dtype=np.uint8).tobytes() for _ in range(64)]
+    seqs += [b"", b"A", b"ACGTA", bytes(range(256)) * 3]
+    ss = SeqSet.from_sequences(seqs, alphabet="strict")
+    for k in (2, 5, 6):
+        got = ft.kmer_counts_batch(ss, k).cpu().numpy()
+        for i, s in enumerate(seqs):
+            want = np.zeros(4 ** k, np.int32)
+            orc.kmer_counts(bytearray(s), k, want)
+            assert np.array_equal(got[i], want), (k, i)
+
+
+def test_check_sequence_semantics(ft, SeqSet):
+    seqs = [b"acgtuUswkmyrbdhvnSWKMYRBDHV-ACGTN" * 5, b"AC GT\tACGTAC\nGTACGT\rACGTTTGAC", b"", b"ACGTNNNNACGTACGTAC"]
+    ss = SeqSet.from_sequences(seqs, names=["a", "b", "c", "d"])
+    got = ft.kmer_counts_batch(ss, 3).cpu().numpy()
+    for i, s in enumerate(seqs):
+        want = np.zeros(64, np.int32)
+        orc.kmer_counts(orc.check_sequence("x", bytearray(s)), 3, want)
+        assert np.array_equal(got[i], want), i
+    with pytest.raises(ValueError, match=r"Invalid DNA byte in sequence s2: 'X'"):
+        SeqSet.from_sequences([b"ACGT", b"ACGTACGTACGTACGTACGTAXGT"], names=["s1", "s2"])
+    with pytest.raises(ValueError, match="Bad character in sequence header"):
+        SeqSet.from_sequences([b"ACGT"], names=[">s1"])
+    with pytest.raises(ValueError, match="tab included in header"):
+        SeqSet.from_sequences([b"ACGT"], names=["s\t1"])
+
+
+@pytest.mark.parametrize("k", [4, 5, 6])
+def test_rng_mimics_bit_exact_vs_oracle(fasta_files, ft, SeqSet, k):
+    """every variant kind of the AugmentFasta schedule, rng mode: integer counts equal the
+    oracle's mutate-and-recount, on real sequences, random ones with Ns, and edge lengths"""
+    rng = np.random.default_rng(k)
+    recs = orc.read_fasta(fasta_files["Influenza-A"])[:24] + orc.read_fasta(fasta_files["Actinopterygii"])[:3]
+    seqs = [bytes(s) for _, s in recs]
+    alph = np.frombuffer(b"ACGTACGTACGTACGTACGTN", dtype=np.uint8)
+    seqs += [alph[rng.integers(0, alph.size, size=L)].tobytes() for L in (0, 1, 5, 6, 63, 64, 65, 127, 128, 129, 300, 4099)]
+    ss = SeqSet.from_sequences(seqs)
+    variants = ft.mimic_schedule(6)
+    seed = 0xC0FFEE1234
+    got = ft.profiles(ss, k, variants, out_kind=ft.OUT_COUNTS_I32, seed=seed, seq_id0=1000).cpu().numpy()
+    want = orc.rng_mimic_counts([bytearray(s) for s in seqs], k, seed, [v.kind for v in variants], seq_id0=1000)
+    assert got.shape == want.shape
+    bad = np.argwhere((got != want).any(axis=2))
+    assert bad.size == 0, bad[:10]
+    # frequencies: float32(count+1 / sum) exactly
+    f32 = ft.profiles(ss, k, variants, out_kind=ft.OUT_FREQ_F32, seed=seed, seq_id0=1000).cpu().numpy()
+    w32 = ((want + 1) / (want + 1).sum(axis=2, keepdims=True)).astype(np.float32)
+    assert np.array_equal(f32, w32)
+
+
+def test_rng_high_rates_and_many_variants(ft, SeqSet):
+    rng = np.random.default_rng(9)
+    alph = np.frombuffer(b"ACGTACGTACGTN", dtype=np.uint8)
+    seqs = [alph[rng.integers(0, alph.size, size=L)].tobytes() for L in (900, 257, 2000, 31)]
+    ss = SeqSet.from_sequences(seqs)
+    variants = [ft.VariantSpec(ft.KIND_BOTH, 0.3, 0.25), ft.VariantSpec(ft.KIND_TRANSITION, p1=0.9),
+                ft.VariantSpec(ft.KIND_TRANSVERSION, p2=0.6), ft.VariantSpec(ft.KIND_CLEAN)]
+    variants += [ft.VariantSpec(ft.KIND_RANDOM_N, n_bp=20) for _ in range(60)]
+    variants += [ft.VariantSpec(ft.KIND_RANDOM_N, n_bp=7), ft.VariantSpec(ft.KIND_RANDOM_N, n_bp=333)]
+    for i, v in enumerate(variants):
+        v.rng_id = i
+    got = ft.profiles(ss, 5, variants, out_kind=ft.OUT_COUNTS_I32, seed=77).cpu().numpy()
+    for v, spec in enumerate(variants):
+        for i, s in enumerate(seqs):
+            edits = orc.rng_variant_edits(77, i, v, spec.kind, orc.codes_of_seq(s), len(s), spec.p1, spec.p2, spec.n_bp)
+            mut = bytearray(s)
+            for pos, val in edits:
+                mut[pos] = b"ACGTN"[val]
+            want = np.zeros(4 ** 5, np.int32)
+            orc.kmer_counts(mut, 5, want)
+            assert np.array_equal(got[v, i], want), (v, i)
+
+
+@pytest.mark.parametrize("k", [4, 5, 6])
+def test_augment_fasta_reference_mutations_bit_exact(golden_dir, fasta_files, ft, SeqSet, k):
+    """The reference's own mutations (np.random.seed(0); random.seed(0)), exported as edit
+    lists, through the explicit-list path + scaler + standardise == the reference's
+    AugmentFasta output, bit for bit (sha256 of x_train)."""
+    g = _golden(golden_dir)["files"]["Influenza-A"]["augment_seed0_nmimics3"]
+    ed = np.load(os.path.join(golden_dir, "influenza_edits_seed0.npz"))
+    ss = SeqSet.from_fasta(fasta_files["Influenza-A"])
+    n, offs = ss.n, ed["offsets"]
+    lut = np.full(256, 4, np.int64)
+    for i, ch in enumerate(b"ACGT"):
+        lut[ch] = i
+    explicit = [[(ed["pos"][offs[p * n + i]:offs[p * n + i + 1]], lut[ed["newbyte"][offs[p * n + i]:offs[p * n + i + 1]]])
+                 for i in range(n)] for p in range(4)]
+    lists = ft.pack_edit_lists(explicit, n, ss.device)
+    variants = [ft.VariantSpec(ft.KIND_EXPLICIT, explicit_idx=p) for p in range(4)]
+    F = 4 ** k
+    t_norm = ft.profiles(ss, k, variants[:1], out_kind=ft.OUT_FREQ_F32, edit_lists=lists)[0]
+    sc = ft.Scaler.fit(t_norm)
+    x = torch.empty((3 * n, 2, F), dtype=torch.float32, device=ss.device)
+    # row (j*n + i): column 0 = t_norm_i, column 1 = mimic_{j+1,i}   (utils.py:338-353, mimic-major)
+    offs_out = [0] + [((j * n) * 2 + 1) * F for j in range(3)]
+    ft.profiles(ss, k, variants, out_kind=ft.OUT_STD_F32, edit_lists=lists, mean=sc.mean32, scale=sc.scale32,
+                out=x, out_off=offs_out, out_stride=2 * F)
+    x[n:2 * n, 0] = x[:n, 0]
+    x[2 * n:, 0] = x[:n, 0]
+    xh = x.cpu().numpy()
+    rows = np.load(os.path.join(golden_dir, f"influenza_xtrain_rows_k{k}.npz"))
+    assert np.array_equal(xh[rows["rows"]], rows["x"])
+    assert sha(xh) == g[f"k{k}"]["x_train_sha256"]
+
+
+@pytest.mark.parametrize("stem", ["Influenza-A", "Actinopterygii"])
+def test_inference_profiles_bit_exact(golden_dir, fasta_files, ft, SeqSet, stem):
+    """SequenceDataset (utils.py:400-405): clean float64 profiles + own float64 scaler"""
+    g = _golden(golden_dir)["files"][stem]["inference_k6"]
+    ss = SeqSet.from_fasta(fasta_files[stem])
+    f64 = ft.profiles(ss, 6, [ft.VariantSpec(ft.KIND_CLEAN)], out_kind=ft.OUT_FREQ_F64)[0]
+    sc = ft.Scaler.fit(f64)
+    x = sc.transform64(f64).cpu().numpy()
+    rows = np.load(os.path.join(golden_dir, f"{stem}_inference_rows_k6.npz"))
+    np.testing.assert_allclose(x[rows["rows"]], rows["x"], rtol=1e-9, atol=1e-9)
+    nbad = int((x != np.asarray(orc.inference_profiles(fasta_files[stem], 6)[1])).sum())
+    assert nbad <= x.size * 1e-3, nbad  # float64 stats are merged in a different order: last-ulp noise only
+    x32 = sc.transform64(f64, want32=True).cpu().numpy()
+    np.testing.assert_allclose(x32, x.astype(np.float32), rtol=1e-6, atol=1e-6)
+
+
+def test_scaler_matches_oracle(ft):
+    rng = np.random.default_rng(4)
+    X = (rng.random((5000, 256)) * 1e-3).astype(np.float32)
+    X[:, 3] = X[0, 3]
+    X[:, 5] = 0.0
+    X[:, 7] = 1.0 + X[:, 7] * 1e-4
+    sc = ft.Scaler.fit(torch.from_numpy(X).cuda())
+    mean, var, scale = orc.standard_scaler_fit(X)
+    np.testing.assert_allclose(sc.mean64.cpu().numpy(), mean, rtol=1e-13)
+    np.testing.assert_allclose(sc.var64.cpu().numpy(), var, rtol=1e-9, atol=1e-30)
+    assert sc.scale64[3].item() == 1.0 and sc.scale64[5].item() == 1.0
+    np.testing.assert_allclose(sc.scale64.cpu().numpy(), scale, rtol=1e-9)
+    got = sc.transform32(torch.from_numpy(X).cuda().clone()).cpu().numpy()
+    want = orc.standard_scaler_transform(X, mean, scale)
+    assert (got != want).mean() < 1e-3
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-6)
+
+
+def test_selection_mode_equals_full_mode(ft, SeqSet):
+    """pair batches (sidx/sel) regenerate exactly the rows of the full featurisation"""
+    rng = np.random.default_rng(12)
+    seqs = [np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(rng.integers(200, 3000)))].tobytes() for _ in range(40)]
+    ss = SeqSet.from_sequences(seqs)
+    variants = ft.mimic_schedule(8)
+    full = ft.profiles(ss, 6, variants, out_kind=ft.OUT_FREQ_F32, seed=5)
+    B = 64
+    sidx = torch.from_numpy(rng.integers(0, 40, size=B).astype(np.int32)).cuda()
+    mim = torch.from_numpy(rng.integers(1, 9, size=B).astype(np.int32)).cuda()
+    sel = torch.stack([torch.zeros_like(mim), mim], dim=1).contiguous()
+    out = ft.profiles(ss, 6, variants, out_kind=ft.OUT_FREQ_F32, seed=5, sidx=sidx, sel=sel)
+    assert out.shape == (2, B, 4096)
+    assert torch.equal(out[0], full[0][sidx.long()])
+    assert torch.equal(out[1], full[mim.long(), sidx.long()])
+
+
+def test_full_size_properties(ft, SeqSet):
+    """BASELINE config 3 shape (10 kb sequences, k=6, n_mimics=50) on a slab: size-independent
+    properties — window-count conservation, unit row sums, determinism, N-mimic bounds."""
+    rng = np.random.default_rng(1)
+    n, L, k, n_mimics = 512, 10000, 6, 50
+    flat = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n * L)]
+    ss = SeqSet.from_ascii(flat, np.arange(n + 1, dtype=np.int64) * L)
+    variants = [ft.VariantSpec(ft.KIND_CLEAN)] + ft.mimic_schedule(n_mimics)
+    for i, v in enumerate(variants):
+        v.rng_id = i
+    c = ft.profiles(ss, k, variants, out_kind=ft.OUT_COUNTS_I32, seed=3)
+    tot = c.sum(dim=2)
+    assert bool((tot[0] == L - k + 1).all())                       # clean: every window counted
+    assert bool((tot[1:4] == L - k + 1).all())                     # substitutions keep every window
+    assert bool((tot[4:] <= L - k + 1).all()) and bool((tot[4:] >= L - k + 1 - 20 * k).all())
+    assert bool((c >= 0).all())
+    assert bool(((c[4:] - c[0:1]) <= 0).all())                     # Random_N only removes windows
+    c2 = ft.profiles(ss, k, variants, out_kind=ft.OUT_COUNTS_I32, seed=3)
+    assert torch.equal(c, c2)                                      # counter-based RNG: deterministic
+    f = ft.profiles(ss, k, variants, out_kind=ft.OUT_FREQ_F32, seed=3)
+    assert float((f.double().sum(dim=2) - 1).abs().max()) < 1e-5
+    c3 = ft.profiles(ss, k, variants, out_kind=ft.OUT_COUNTS_I32, seed=4)
+    assert not torch.equal(c[1], c3[1])
+    # mutation counts per pass follow Binomial(L, p): mean within 5 sigma over the slab
+    dist_both = (c[1] - c[0]).abs().sum(dim=1).double().mean().item() / (2 * k)
+    assert 0.8 * L * 0.015 < dist_both < 1.05 * L * 0.015, dist_both
+
+
+def _loss_inputs(B, C, salt):
+    import gen_golden
+    return gen_golden.loss_inputs(B, C, salt)
+
+
+def test_iid_loss_goldens(golden_dir):
+    from idelucs_b200.LossFunctions import IID_loss, compute_joint
+    with open(os.path.join(golden_dir, "iid_loss.json")) as fh:
+        cases = json.load(fh)
+    for c in cases:
+        z1n, z2n = _loss_inputs(c["B"], c["C"], c["salt"]), _loss_inputs(c["B"], c["C"], c["salt"] + 100)
+        z1 = torch.from_numpy(z1n).cuda().requires_grad_(True)
+        z2 = torch.from_numpy(z2n).cuda().requires_grad_(True)
+        loss = IID_loss(z1, z2, lamb=c["lamb"])
+        loss.backward()
+        assert abs(loss.item() - c["loss32"]) <= 1e-5, (c["B"], c["C"], loss.item(), c["loss32"])  # north-star tolerance
+        assert abs(loss.item() - c["loss64"]) <= 2e-5 * max(1.0, abs(c["loss64"]))
+        rows = np.asarray(c["rows"])
+        d1, d2 = z1.grad.cpu().numpy()[rows], z2.grad.cpu().numpy()[rows]
+        w1, w2 = np.asarray(c["dz1_rows64"]), np.asarray(c["dz2_rows64"])
+        scale = max(np.abs(w1).max(), 1e-12)
+        assert np.abs(d1 - w1).max() <= 2e-5 * scale, (c["B"], c["C"], np.abs(d1 - w1).max(), scale)
+        assert np.abs(d2 - w2).max() <= 2e-5 * max(np.abs(w2).max(), 1e-12)
+        j = compute_joint(z1.detach(), z2.detach()).cpu().numpy()
+        wj = orc.compute_joint(z1n.astype(np.float64), z2n.astype(np.float64))
+        np.testing.assert_allclose(j, wj, rtol=1e-5, atol=1e-12)
+        assert np.array_equal(j, j.T)
+
+
+def test_iid_loss_clamped_and_deterministic():
+    from idelucs_b200.LossFunctions import IID_loss
+    torch.manual_seed(0)
+    B, C = 300, 40
+    z1 = torch.softmax(torch.randn(B, C, device="cuda") * 30, 1).requires_grad_(True)   # near one-hot -> clamps
+    z2 = torch.softmax(torch.randn(B, C, device="cuda") * 30, 1).requires_grad_(True)
+    l1 = IID_loss(z1, z2, lamb=2.8)
+    l1.backward()
+    g1 = z1.grad.clone()
+    wl, wd1, wd2 = orc.IID_loss_grad(z1.detach().cpu().numpy(), z2.detach().cpu().numpy(), lamb=2.8)
+    assert abs(l1.item() - wl) <= 1e-5 * max(1.0, abs(wl))
+    np.testing.assert_allclose(g1.cpu().numpy(), wd1, rtol=1e-3, atol=2e-5 * np.abs(wd1).max())
+    z1.grad = None
+    l2 = IID_loss(z1, z2, lamb=2.8)
+    l2.backward()
+    assert l1.item() == l2.item() and torch.equal(g1, z1.grad)
