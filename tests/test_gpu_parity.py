@@ -188,8 +188,11 @@ def test_inference_profiles_bit_exact(golden_dir, fasta_files, ft, SeqSet, stem)
     x = sc.transform64(f64).cpu().numpy()
     rows = np.load(os.path.join(golden_dir, f"{stem}_inference_rows_k6.npz"))
     np.testing.assert_allclose(x[rows["rows"]], rows["x"], rtol=1e-9, atol=1e-9)
-    nbad = int((x != np.asarray(orc.inference_profiles(fasta_files[stem], 6)[1])).sum())
-    assert nbad <= x.size * 1e-3, nbad  # float64 stats are merged in a different order: last-ulp noise only
+    # float64 statistics are merged in a different order than numpy's pairwise sum: the
+    # standardised values agree to ~1e-12 relative (far inside the float32 cast of models.py:163)
+    want = np.asarray(orc.inference_profiles(fasta_files[stem], 6)[1])
+    np.testing.assert_allclose(x, want, rtol=1e-10, atol=1e-10)
+    assert sha(f64.cpu().numpy()) == _golden(golden_dir)["files"][stem]["k6"]["freq64_sha256"]
     x32 = sc.transform64(f64, want32=True).cpu().numpy()
     np.testing.assert_allclose(x32, x.astype(np.float32), rtol=1e-6, atol=1e-6)
 
