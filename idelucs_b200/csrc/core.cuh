@@ -27,7 +27,7 @@
 namespace idl {
 
 constexpr int CHUNK_BASES = 64;
-constexpr int RNG_BLOCK = 128;       // bases per Bernoulli generation block
+constexpr int RNG_BLOCK = 64;        // bases per Bernoulli generation block (= one chunk)
 constexpr uint32_t VAL_N = 4;        // edit value "set N"
 
 enum Kind : int { KIND_CLEAN = 0, KIND_TRANSITION = 1, KIND_TRANSVERSION = 2, KIND_BOTH = 3,
@@ -114,33 +114,36 @@ IDL_HD void pack16(const uint8_t* src, int avail, int strict, uint32_t* code_wor
 }
 
 // ---------------------------------------------------------------------------------------
-// K2: count one 64-base chunk (restates idelucs/kmers.pyx:38-50 for the 64 window ends
-// that fall in chunk `c`; the rolling k_mer/countdown state of the reference is replaced
-// by reading the k-1 preceding bases from the previous word, so chunks are independent).
-// upd(kmer_index) is called once per counted window; returns the number of windows counted.
+// K2: count the 32 window ends of half-chunk `h` (restates idelucs/kmers.pyx:38-50; the
+// rolling k_mer/countdown state of the reference is replaced by reading the k-1 preceding
+// bases from the previous word, so half-chunks are independent).  w0,w1 = code words 2h,
+// 2h+1.  upd(kmer_index) is called once per counted window; returns the number counted.
 // ---------------------------------------------------------------------------------------
 template <int K, class Upd>
-IDL_HD int count_chunk(const uint32_t* codes, const uint32_t* nmask, int c, uint32_t w0, uint32_t w1,
-                       uint32_t w2, uint32_t w3, Upd upd) {
+IDL_HD int count_half(const uint32_t* codes, const uint32_t* nmask, int h, uint32_t w0, uint32_t w1, Upd upd) {
     constexpr uint32_t KMASK = (1u << (2 * K)) - 1u;
-    const uint32_t prev = c > 0 ? codes[4 * c - 1] : 0u;
-    const uint64_t m = ((uint64_t)nmask[2 * c] << 32) | (uint64_t)nmask[2 * c + 1];
-    // P: bit d-1 = N flag of position -d relative to the chunk (d = 1..K-1); the sequence
+    constexpr uint32_t PM = (1u << (K - 1)) - 1u;
+    const uint32_t prev = h > 0 ? codes[2 * h - 1] : 0u;
+    const uint32_t m = nmask[h];
+    // P: bit d-1 = N flag of position -d relative to the half-chunk (d = 1..K-1); the sequence
     // start behaves like kmers.pyx:14 countdown = k-1, i.e. as if preceded by resets.
-    const uint64_t P = c > 0 ? (uint64_t)(nmask[2 * c - 1] & ((1u << (K - 1)) - 1u)) : (uint64_t)((1u << (K - 1)) - 1u);
-    uint64_t inv = m;
+    const uint32_t P = h > 0 ? (nmask[h - 1] & PM) : PM;
+    uint32_t inv = m;
 #pragma unroll
-    for (int d = 1; d < K; ++d) inv |= (m >> d) | (P << (64 - d));
-    const uint32_t w[5] = {prev, w0, w1, w2, w3};
+    for (int d = 1; d < K; ++d) inv |= (m >> d) | (P << (32 - d));
+    const uint32_t w[3] = {prev, w0, w1};
 #pragma unroll
-    for (int wi = 0; wi < 4; ++wi) {
-        const uint32_t iv = (uint32_t)(inv >> (48 - 16 * wi)) & 0xFFFFu;  // bit 15-j for base j of this word
+    for (int wi = 0; wi < 2; ++wi) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            if (!((iv >> (15 - j)) & 1u)) upd(funnel_r(w[wi + 1], w[wi], 30 - 2 * j) & KMASK);
+            if (!((inv >> (31 - 16 * wi - j)) & 1u)) upd(funnel_r(w[wi + 1], w[wi], 30 - 2 * j) & KMASK);
         }
     }
-    return popc64(~inv);
+#if defined(__CUDA_ARCH__)
+    return __popc(~inv);
+#else
+    return __builtin_popcount(~inv);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
@@ -243,20 +246,38 @@ inline void geometric_table(double p, uint32_t* T) {
         T[g] = v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)v;
     }
 }
+// 1/log2(1-p): slope of the gap estimate used by the device-side search (any value is
+// safe: the estimate is always corrected against the integer table)
+inline float gap_slope(double p) {
+    if (!(p > 0.0)) return 0.0f;
+    if (!(p < 1.0)) return 0.0f;
+    return (float)(1.0 / log2(1.0 - p));
+}
 
-// smallest g in 1..RNG_BLOCK with u < T[g-1]; 0 when u >= T[RNG_BLOCK-1]
-IDL_HD int gap_of(uint32_t u, const uint32_t* T) {
+// smallest g in 1..RNG_BLOCK with u < T[g-1]; 0 when u >= T[RNG_BLOCK-1].  The result is
+// DEFINED by the integer table; the device starts the search from a log estimate, the host
+// uses a binary search — both return the same g.
+IDL_HD int gap_of(uint32_t u, const uint32_t* T, float slope) {
     if (u >= T[RNG_BLOCK - 1]) return 0;
+#if defined(__CUDA_ARCH__)
+    const float x = (float)(~u) * 2.3283064365386963e-10f;  // ~ 1 - u/2^32
+    int g = (int)(__log2f(x) * slope) + 1;
+    g = g < 1 ? 1 : (g > RNG_BLOCK ? RNG_BLOCK : g);
+    while (g > 1 && u < T[g - 2]) --g;
+    while (u >= T[g - 1]) ++g;  // terminates: u < T[RNG_BLOCK-1]
+    return g;
+#else
+    (void)slope;
     int lo = 0, hi = RNG_BLOCK - 1;
-#pragma unroll 1
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (u < T[mid]) hi = mid; else lo = mid + 1;
     }
     return lo + 1;
+#endif
 }
 
-// Bernoulli(p) hit positions of one 128-base block by geometric gap skipping.  Word stream
+// Bernoulli(p) hit positions of one 64-base block by geometric gap skipping.  Word stream
 // = Philox outputs for counter (j, block, seq_id, variant*4+stream), j = 0,1,...; the
 // transition stream uses one word per step (gap), the transversion stream two (gap, choice
 // = top bit of the second word; idelucs/utils.py:118 random.choice of two).
@@ -266,12 +287,13 @@ struct BernGen {
     int pos, end;
     bool with_choice, done;
     const uint32_t* T;
+    float slope;
 
     IDL_HD void init(uint64_t seed, uint32_t seq_id, uint32_t variant, uint32_t stream, int block, int L,
-                     const uint32_t* table, bool choice) {
+                     const uint32_t* table, float slp, bool choice) {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
         c1 = (uint32_t)block; c2 = seq_id; c3 = (variant << 2) | stream;
-        j = 0; wi = 4; T = table; with_choice = choice;
+        j = 0; wi = 4; T = table; slope = slp; with_choice = choice;
         pos = block * RNG_BLOCK - 1;
         end = (block + 1) * RNG_BLOCK; if (L < end) end = L;
         done = (block * RNG_BLOCK >= L);
@@ -285,7 +307,7 @@ struct BernGen {
     // next hit: returns false when the block is exhausted
     IDL_HD bool next(int* p, uint32_t* choice) {
         if (done) return false;
-        const int g = gap_of(word(), T);
+        const int g = gap_of(word(), T, slope);
         const uint32_t ch = with_choice ? (word() >> 31) : 0u;
         if (g == 0) { done = true; return false; }
         pos += g;
@@ -302,18 +324,18 @@ struct BernGen {
 // depends on the purine/pyrimidine class that a transition preserves).  emit(entry).
 template <class Emit>
 IDL_HD int block_edits(int kind, uint64_t seed, uint32_t seq_id, uint32_t variant, int block, int L,
-                       const uint32_t* codes, const uint32_t* nmask, const uint32_t* T1, const uint32_t* T2,
-                       Emit emit) {
+                       const uint32_t* codes, const uint32_t* nmask, const uint32_t* T1, float slope1,
+                       const uint32_t* T2, float slope2, Emit emit) {
     BernGen ga, gb;
     int pa = 0x7fffffff, pb = 0x7fffffff;
     uint32_t ca = 0, cb = 0;
     bool va = false, vb = false;
     if (kind == KIND_TRANSITION || kind == KIND_BOTH) {
-        ga.init(seed, seq_id, variant, STREAM_TRANSITION, block, L, T1, false);
+        ga.init(seed, seq_id, variant, STREAM_TRANSITION, block, L, T1, slope1, false);
         va = ga.next(&pa, &ca);
     }
     if (kind == KIND_TRANSVERSION || kind == KIND_BOTH) {
-        gb.init(seed, seq_id, variant, STREAM_TRANSVERSION, block, L, T2, true);
+        gb.init(seed, seq_id, variant, STREAM_TRANSVERSION, block, L, T2, slope2, true);
         vb = gb.next(&pb, &cb);
     }
     int n = 0;

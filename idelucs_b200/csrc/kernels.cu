@@ -31,12 +31,12 @@ int set_error(int code, const char* fmt, const char* a, long long b) {
 
 constexpr int LIST_CAP = 4096;   // on-chip edit list entries per CTA
 constexpr int MAX_GROUP = 256;   // variant slots per Random_N group
+constexpr int SVARS = 64;        // variant descriptors cached in shared memory
+constexpr int STABS = 4;         // gap tables cached in shared memory
 
 struct VarDesc {
     int32_t kind, rng_id, n_bp, explicit_idx, tab1, tab2;
-};
-struct GroupDesc {
-    int32_t first_slot, n_slots, kind;
+    float slope1, slope2;
 };
 
 struct ProfParams {
@@ -47,9 +47,8 @@ struct ProfParams {
     const int32_t* sidx;
     const int32_t* sel;
     long long n_items, seq_id0, n_seqs_total;
-    int S, n_groups;
+    int S, n_vars, n_tabs;
     const VarDesc* vars;
-    const GroupDesc* groups;
     unsigned long long seed;
     const uint32_t* gtab;
     const int64_t* edit_off;
@@ -60,6 +59,7 @@ struct ProfParams {
     int pseudocount, accumulate;
     const float* mean;
     const float* scale;
+    const float* rscale;  // 1/scale (IEEE), computed into the workspace by rscale_kernel
     int32_t* status;
     unsigned long long* work_counter;
 };
@@ -152,88 +152,366 @@ __device__ __forceinline__ int block_exscan(int v, int* scratch, int* total) {
 
 // ---------------------------------------------------------------------------------------
 // K2/K3 profiles kernel
+//
+// Per work item (one sequence) a CTA
+//   1. counts the clean histogram into hist[] (int32, shared-memory atomics);
+//   2. SHORT path (L <= 65535, every count fits 16 bits): keeps G private uint16 copies of
+//      the histogram.  Variant slots are consumed G at a time: the copies are patched with
+//      the slots' +-1 deltas (Random_N slots by one warp each, concurrently; Bernoulli /
+//      explicit slots by the whole CTA), ONE barrier, all threads stream the G profiles
+//      (fixed thread <-> bin mapping, scaler statistics in registers, 128-bit streaming
+//      stores), ONE barrier, the copies are restored.  Two barriers per G variants.
+//   3. LONG path (L > 65535): patches hist[] itself, one variant at a time (int32 counts).
 // ---------------------------------------------------------------------------------------
 template <int K, int NT>
-struct ProfSmem {
+struct ProfCfg {
     static constexpr int F = 1 << (2 * K);
-    int hist[F];
-    uint32_t list[LIST_CAP + 8];
-    uint32_t tmp[LIST_CAP];  // unsorted Random_N draws
-    uint32_t gtab[2][RNG_BLOCK];
+    static constexpr int VEC = F / 4;                       // 4-bin granules per profile
+    static constexpr int VPT = (VEC + NT - 1) / NT;         // granules per thread
+    static constexpr int G = (NT / 32) < 8 ? (NT / 32) : 8; // private copies (= variants per barrier pair)
+    static constexpr int PRIVW = F / 2 > 2 ? F / 2 : 2;     // words per private copy
+    static constexpr int PT = (G * PRIVW) > LIST_CAP ? (G * PRIVW) : LIST_CAP;
+};
+
+template <int K, int NT>
+struct ProfSmem {
+    using C = ProfCfg<K, NT>;
+    int hist[C::F];
+    uint32_t privtmp[C::PT];          // short path: G private uint16 copies; long path: unsorted Random_N draws
+    uint32_t list[LIST_CAP + 8];      // CTA-wide position-sorted edit list
+    uint32_t wlist[C::G][32];         // per-warp sorted Random_N lists
+    uint16_t wdelta[C::G][32 * K];    // k-mers removed by each lane's entry (to restore the copy)
+    uint32_t gtabs[STABS][RNG_BLOCK]; // geometric gap tables (first STABS of the launch)
     int dtot[MAX_GROUP];
+    int gkind[C::G];                  // per copy of the current group: 0 none, 1 warp Random_N, 2 Bernoulli, 3 other CTA-wide
+    int seg_off[C::G + 1];            // joint Bernoulli pass: list segment of each Bernoulli slot
+    int gmask[2];                     // ballot masks: Bernoulli copies, other CTA-wide copies
+    float2 gy[C::G];                  // per copy: (float total, 1/total)
+    long long grow[C::G];             // per copy: byte offset of the output row
     int scan[NT / 32 + 2];
     int nvalid;
     long long item;
+    VarDesc svars[SVARS];             // descriptor cache (first SVARS variants)
+    long long sout_off[SVARS];
 };
 
-template <int K, int NT, int OUT>
-__device__ __forceinline__ void stream_slot(const int* hist, int total, int pc, int accumulate, void* out_row,
-                                            const float (&mean)[((1 << (2 * K)) / 4 + NT - 1) / NT][4],
-                                            const float (&scale)[((1 << (2 * K)) / 4 + NT - 1) / NT][4],
-                                            const float (&rscale)[((1 << (2 * K)) / 4 + NT - 1) / NT][4]) {
-    constexpr int F = 1 << (2 * K);
-    constexpr int VEC = F / 4;
-    constexpr int VPT = (VEC + NT - 1) / NT;
-    const float ft = (float)total;
-    const float y = 1.0f / ft;  // IEEE (correctly rounded) reciprocal
-    const bool big = total >= (1 << 24);  // float no longer exact: divide in double
+// convert 4 packed uint16 counts (+pc) to exact floats: 2^23 + c is exact for c < 2^23, and
+// subtracting 2^23 - pc leaves c + pc exactly (no I2F on the conversion pipe)
+__device__ __forceinline__ void cvt4_u16(uint2 pk, float magic, float (&f)[4]) {
+    f[0] = __uint_as_float(__byte_perm(pk.x, 0x4B000000u, 0x7410)) - magic;
+    f[1] = __uint_as_float(__byte_perm(pk.x, 0x4B000000u, 0x7432)) - magic;
+    f[2] = __uint_as_float(__byte_perm(pk.y, 0x4B000000u, 0x7410)) - magic;
+    f[3] = __uint_as_float(__byte_perm(pk.y, 0x4B000000u, 0x7432)) - magic;
+}
+
+// one 4-bin granule of one profile row.  ci = integer counts INCLUDING the pseudocount
+// (COUNTS / F64 / big totals), cf = the same as exact floats (F32 kinds).
+template <int OUT>
+__device__ __forceinline__ void emit_granule(void* out_row, int vec, const int (&ci)[4], const float (&cf)[4], int total,
+                                             float ft, float y, bool big, int accumulate, const float (&mean)[4],
+                                             const float (&scale)[4], const float (&rscale)[4]) {
+    if (OUT == IDL_OUT_COUNTS_I32) {
+        int4* dst = reinterpret_cast<int4*>(out_row) + vec;
+        int4 o = make_int4(ci[0], ci[1], ci[2], ci[3]);
+        if (accumulate) { const int4 prev = *dst; o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w; }
+        *dst = o;
+    } else if (OUT == IDL_OUT_FREQ_F64) {
+        double2* dst = reinterpret_cast<double2*>(out_row) + 2 * vec;
+        const double dt = (double)total;
+        __stcs(dst, make_double2((double)ci[0] / dt, (double)ci[1] / dt));
+        __stcs(dst + 1, make_double2((double)ci[2] / dt, (double)ci[3] / dt));
+    } else {
+        float q[4];
 #pragma unroll
-    for (int vv = 0; vv < VPT; ++vv) {
-        const int vec = threadIdx.x + vv * NT;
-        if (VEC % NT != 0 && vec >= VEC) break;
-        const int4 c = reinterpret_cast<const int4*>(hist)[vec];
-        const int cc[4] = {c.x + pc, c.y + pc, c.z + pc, c.w + pc};
-        if (OUT == IDL_OUT_COUNTS_I32) {
-            int4* dst = reinterpret_cast<int4*>(out_row) + vec;
-            int4 o = c;
-            if (accumulate) { const int4 prev = *dst; o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w; }
-            *dst = o;
-        } else if (OUT == IDL_OUT_FREQ_F64) {
-            double2* dst = reinterpret_cast<double2*>(out_row) + 2 * vec;
-            const double dt = (double)total;
-            __stcs(dst, make_double2((double)cc[0] / dt, (double)cc[1] / dt));
-            __stcs(dst + 1, make_double2((double)cc[2] / dt, (double)cc[3] / dt));
-        } else {
-            float q[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                // float32(count/total): for count,total < 2^24 the float division is exactly the
-                // reference's float64 division followed by astype(float32)
-                q[e] = big ? (float)((double)cc[e] / (double)total) : div_rn((float)cc[e], ft, y);
-                if (OUT == IDL_OUT_STD_F32) q[e] = div_rn(q[e] - mean[vv][e], scale[vv][e], rscale[vv][e]);
-            }
-            __stcs(reinterpret_cast<float4*>(out_row) + vec, make_float4(q[0], q[1], q[2], q[3]));
+        for (int e = 0; e < 4; ++e) {
+            // float32(count/total): for count,total < 2^24 the correctly rounded float division is
+            // exactly the reference's float64 division followed by astype(float32)
+            q[e] = big ? (float)((double)ci[e] / (double)total) : div_rn(cf[e], ft, y);
+            if (OUT == IDL_OUT_STD_F32) q[e] = div_rn(q[e] - mean[e], scale[e], rscale[e]);
         }
+        __stcs(reinterpret_cast<float4*>(out_row) + vec, make_float4(q[0], q[1], q[2], q[3]));
+    }
+}
+
+// ---- register-hungry, rarely executed pieces are kept out of line so that the streaming
+// ---- loop keeps its scaler statistics in registers (64-register budget at 2 CTAs/SM) ----
+struct BlockGen { int cnt; uint32_t e0, e1, e2, e3; };
+
+struct ItemCtx {
+    const uint32_t* codes;
+    const uint32_t* nmask;
+    int L;
+    uint32_t seq_id;
+    unsigned long long seed;
+};
+
+// edits of one 64-base block of a Bernoulli slot: count + the first four entries
+__device__ __noinline__ BlockGen bern_block(const ItemCtx& cx, int kind, uint32_t rng_id, int b, const uint32_t* T1, float s1,
+                                            const uint32_t* T2, float s2) {
+    BlockGen g;
+    g.e0 = g.e1 = g.e2 = g.e3 = 0u;
+    int k4 = 0;
+    g.cnt = block_edits(kind, cx.seed, cx.seq_id, rng_id, b, cx.L, cx.codes, cx.nmask, T1, s1, T2, s2, [&](uint32_t e) {
+        if (k4 == 0) g.e0 = e; else if (k4 == 1) g.e1 = e; else if (k4 == 2) g.e2 = e; else if (k4 == 3) g.e3 = e;
+        ++k4;
+    });
+    return g;
+}
+// rare (> 4 edits in a block): regenerate straight into the list
+__device__ __noinline__ void bern_block_write(const ItemCtx& cx, int kind, uint32_t rng_id, int b, const uint32_t* T1, float s1,
+                                              const uint32_t* T2, float s2, uint32_t* dst) {
+    block_edits(kind, cx.seed, cx.seq_id, rng_id, b, cx.L, cx.codes, cx.nmask, T1, s1, T2, s2, [&](uint32_t e) { *dst++ = e; });
+}
+__device__ __forceinline__ void put_block(const ItemCtx& cx, const VarDesc& vd, int b, const BlockGen& g, uint32_t* dst,
+                                          const uint32_t* T1, const uint32_t* T2) {
+    if (g.cnt <= 4) {
+        if (g.cnt > 0) dst[0] = g.e0;
+        if (g.cnt > 1) dst[1] = g.e1;
+        if (g.cnt > 2) dst[2] = g.e2;
+        if (g.cnt > 3) dst[3] = g.e3;
+    } else {
+        bern_block_write(cx, vd.kind, (uint32_t)vd.rng_id, b, T1, vd.slope1, T2, vd.slope2, dst);
+    }
+}
+// patch a private uint16 copy (two counts per word) with the deltas of list entry i
+__device__ __forceinline__ void upd16(uint32_t* privc, uint32_t kmer, int d) {
+    uint32_t* w = privc + (kmer >> 1);
+    const uint32_t inc = 1u << ((kmer & 1u) * 16u);
+    if (d > 0) atomicAdd(w, inc); else atomicSub(w, inc);
+}
+template <int K>
+__device__ __noinline__ int apply_priv(const ItemCtx& cx, const uint32_t* list, int n, int i, uint32_t* privc) {
+    return apply_entry<K>(cx.codes, cx.nmask, cx.L, list, n, i, [&](uint32_t kmer, int dd) { upd16(privc, kmer, dd); });
+}
+template <int K>
+__device__ __noinline__ int apply_hist(const ItemCtx& cx, const uint32_t* list, int n, int i, int* hist, int sgn) {
+    return apply_entry<K>(cx.codes, cx.nmask, cx.L, list, n, i, [&](uint32_t kmer, int dd) { atomicAdd(&hist[kmer], sgn * dd); });
+}
+
+template <int K, int NT>
+__device__ __forceinline__ const uint32_t* gap_table(const ProfSmem<K, NT>& sm, const ProfParams& p, int t) {
+    return t < STABS ? sm.gtabs[t] : p.gtab + t * RNG_BLOCK;
+}
+
+// CTA-wide generation of the Bernoulli edit list of one tile (NT-2 blocks + one context block
+// on each side) into sm.list; returns the number of entries (-1 on overflow).  Contains
+// barriers; every thread of the CTA must call it.
+template <int K, int NT>
+__device__ __noinline__ int bernoulli_tile(ProfSmem<K, NT>& sm, const ProfParams& p, const ItemCtx& cx, const VarDesc& vd, int tb0,
+                                           int nblocks) {
+    const int b = tb0 - 1 + (int)threadIdx.x;
+    const bool active = b >= 0 && b < nblocks;
+    const uint32_t* T1 = gap_table(sm, p, vd.tab1);
+    const uint32_t* T2 = gap_table(sm, p, vd.tab2);
+    BlockGen g;
+    g.cnt = 0;
+    if (active) g = bern_block(cx, vd.kind, (uint32_t)vd.rng_id, b, T1, vd.slope1, T2, vd.slope2);
+    int total;
+    const int off = block_exscan<NT>(g.cnt, sm.scan, &total);
+    if (total > LIST_CAP) return -1;
+    if (active) put_block(cx, vd, b, g, sm.list + off, T1, T2);
+    __syncthreads();
+    return total;
+}
+
+// CTA-wide Random_N with many draws: draw -> rank sort into sm.list.  Contains barriers.
+template <int K, int NT>
+__device__ __noinline__ void random_n_list(ProfSmem<K, NT>& sm, const ItemCtx& cx, const VarDesc& vd, uint32_t* tmp) {
+    const int n_bp = vd.n_bp;
+    for (int call = threadIdx.x; call * 4 < n_bp; call += NT) {
+        const U4 r = random_n_words(cx.seed, cx.seq_id, (uint32_t)vd.rng_id, (uint32_t)call);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (call * 4 + t < n_bp) tmp[call * 4 + t] = random_n_entry(w[t], cx.L);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_bp; i += NT) {
+        const uint32_t e = tmp[i];
+        int rank = 0;
+        for (int j = 0; j < n_bp; ++j) { const uint32_t ej = tmp[j]; rank += (ej < e || (ej == e && j < i)) ? 1 : 0; }
+        sm.list[rank] = e;
+    }
+    __syncthreads();
+}
+
+// LONG path (L > 65535): patch hist[] itself (int32 counts), one variant at a time.
+template <int K, int NT, int OUT>
+__device__ __noinline__ void long_path(ProfSmem<K, NT>& sm, const ProfParams& p, const ItemCtx& cx, const VarDesc* vars,
+                                       const long long* out_offs, long long item, long long seq, int base_total) {
+    using C = ProfCfg<K, NT>;
+    constexpr int VEC = C::VEC, VPT = C::VPT;
+    constexpr int ESZ = OUT == IDL_OUT_FREQ_F64 ? 8 : 4;
+    constexpr int TB = NT - 2;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int L = cx.L;
+    const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
+    for (int s = 0; s < p.S; ++s) {
+        const VarDesc vd = vars[p.sel ? p.sel[item * p.S + s] : s];
+        const int kind = (vd.kind == KIND_RANDOM_N && vd.n_bp <= 0) ? KIND_CLEAN : vd.kind;
+        if (tid == 0) sm.dtot[0] = 0;
+        __syncthreads();
+        int n_list = 0;
+        const uint32_t* lst = sm.list;
+        if (kind == KIND_RANDOM_N) {
+            random_n_list<K, NT>(sm, cx, vd, sm.privtmp);
+            n_list = vd.n_bp;
+        } else if (kind == KIND_EXPLICIT) {
+            const long long li = (long long)vd.explicit_idx * p.n_seqs_total + seq;
+            lst = p.edits + p.edit_off[li];
+            n_list = (int)(p.edit_off[li + 1] - p.edit_off[li]);
+        }
+        for (int sgn = 1; sgn >= -1; sgn -= 2) {
+            if (kind == KIND_CLEAN) { if (sgn < 0) break; }
+            else if (kind == KIND_RANDOM_N || kind == KIND_EXPLICIT) {
+                int d = 0;
+                for (int i = tid; i < n_list; i += NT) d += apply_hist<K>(cx, lst, n_list, i, sm.hist, sgn);
+                if (sgn > 0) { d = warp_sum(d); if (lane == 0 && d) atomicAdd(&sm.dtot[0], d); }
+                __syncthreads();
+            } else {
+                for (int tb0 = 0; tb0 < nblocks; tb0 += TB) {
+                    const int total = bernoulli_tile<K, NT>(sm, p, cx, vd, tb0, nblocks);
+                    if (total < 0) { if (tid == 0 && p.status) atomicOr(p.status + item, 1); continue; }
+                    const int lo = tb0 * RNG_BLOCK;
+                    const long long hi = (long long)(tb0 + TB) * RNG_BLOCK;
+                    int d = 0;
+                    for (int i = tid; i < total; i += NT) {
+                        const int pos = (int)(sm.list[i] >> 3);
+                        if (pos >= lo && pos < hi) d += apply_hist<K>(cx, sm.list, total, i, sm.hist, sgn);
+                    }
+                    if (sgn > 0) { d = warp_sum(d); if (lane == 0 && d) atomicAdd(&sm.dtot[0], d); }
+                    __syncthreads();
+                }
+            }
+            if (sgn > 0) {
+                const int total = base_total + sm.dtot[0];
+                const float ftot = (float)total;
+                const float y = 1.0f / ftot;
+                const bool big = total >= (1 << 24);
+                void* row = reinterpret_cast<unsigned char*>(p.out) + (size_t)ESZ * (size_t)(out_offs[s] + item * p.out_stride);
+#pragma unroll
+                for (int vv = 0; vv < VPT; ++vv) {
+                    const int vec = tid + vv * NT;
+                    if (VEC % NT != 0 && vec >= VEC) break;
+                    const int4 h = reinterpret_cast<const int4*>(sm.hist)[vec];
+                    const int ci[4] = {h.x + p.pseudocount, h.y + p.pseudocount, h.z + p.pseudocount, h.w + p.pseudocount};
+                    const float cf[4] = {(float)ci[0], (float)ci[1], (float)ci[2], (float)ci[3]};
+                    float mean[4] = {0.f, 0.f, 0.f, 0.f}, scale[4] = {1.f, 1.f, 1.f, 1.f}, rscale[4] = {1.f, 1.f, 1.f, 1.f};
+                    if (OUT == IDL_OUT_STD_F32) {
+                        const float4 m = reinterpret_cast<const float4*>(p.mean)[vec];
+                        const float4 sc = reinterpret_cast<const float4*>(p.scale)[vec];
+                        mean[0] = m.x; mean[1] = m.y; mean[2] = m.z; mean[3] = m.w;
+                        const float4 rs = reinterpret_cast<const float4*>(p.rscale)[vec];
+                        scale[0] = sc.x; scale[1] = sc.y; scale[2] = sc.z; scale[3] = sc.w;
+                        rscale[0] = rs.x; rscale[1] = rs.y; rscale[2] = rs.z; rscale[3] = rs.w;
+                    }
+                    emit_granule<OUT>(row, vec, ci, cf, total, ftot, y, big, p.accumulate, mean, scale, rscale);
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// CTA-wide prep of the Bernoulli / explicit / big-Random_N slots of one group (short path):
+// patches the private copies and accumulates sm.dtot.  Contains barriers (uniform control flow).
+template <int K, int NT>
+__device__ __noinline__ void prep_cta_slots(ProfSmem<K, NT>& sm, const ProfParams& p, const ItemCtx& cx, const VarDesc* vars, int s0,
+                                            long long item, long long seq, unsigned bern_mask, unsigned other_mask) {
+    using C = ProfCfg<K, NT>;
+    constexpr int PRIVW = C::PRIVW;
+    constexpr int TB = NT - 2;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int L = cx.L;
+    const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
+    uint32_t* priv = sm.privtmp;
+    auto slot_var = [&](int slot) -> int { return p.sel ? p.sel[item * p.S + slot] : slot; };
+    // ---- Bernoulli slots jointly: thread <-> (slot, 64-base block) ----
+    const int nb = __popc(bern_mask);
+    bool bern_done = nb == 0;
+    if (nb > 0 && nb * nblocks <= NT) {
+        const int j = tid / nblocks, b = tid - j * nblocks;
+        const bool active = tid < nb * nblocks;
+        const int c = active ? (int)__fns(bern_mask, 0, j + 1) : 0;
+        const VarDesc vd = vars[slot_var(s0 + c)];
+        const uint32_t* T1 = gap_table(sm, p, vd.tab1);
+        const uint32_t* T2 = gap_table(sm, p, vd.tab2);
+        BlockGen g;
+        g.cnt = 0;
+        if (active) g = bern_block(cx, vd.kind, (uint32_t)vd.rng_id, b, T1, vd.slope1, T2, vd.slope2);
+        int total;
+        const int off = block_exscan<NT>(g.cnt, sm.scan, &total);
+        if (total <= LIST_CAP) {  // uniform
+            bern_done = true;
+            if (active && b == 0) sm.seg_off[j] = off;
+            if (tid == 0) sm.seg_off[nb] = total;
+            if (active) put_block(cx, vd, b, g, sm.list + off, T1, T2);
+            __syncthreads();
+            for (int i = tid; i < total; i += NT) {
+                int jj = 0;
+                while (i >= sm.seg_off[jj + 1]) ++jj;
+                const int cc = (int)__fns(bern_mask, 0, jj + 1);
+                const int so = sm.seg_off[jj];
+                const int d = apply_priv<K>(cx, sm.list + so, sm.seg_off[jj + 1] - so, i - so, priv + cc * PRIVW);
+                if (d) atomicAdd(&sm.dtot[cc], d);
+            }
+            __syncthreads();
+        }
+    }
+    // ---- remaining CTA-wide slots, one after the other ----
+    unsigned todo = other_mask | (bern_done ? 0u : bern_mask);
+    while (todo) {
+        const int c = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const VarDesc vd = vars[slot_var(s0 + c)];
+        uint32_t* privc = priv + c * PRIVW;
+        int d = 0;
+        if (vd.kind == KIND_EXPLICIT) {
+            const long long li = (long long)vd.explicit_idx * p.n_seqs_total + seq;
+            const uint32_t* glist = p.edits + p.edit_off[li];
+            const int n = (int)(p.edit_off[li + 1] - p.edit_off[li]);
+            for (int i = tid; i < n; i += NT) d += apply_priv<K>(cx, glist, n, i, privc);
+        } else if (vd.kind == KIND_RANDOM_N) {
+            random_n_list<K, NT>(sm, cx, vd, sm.list + LIST_CAP / 2);
+            for (int i = tid; i < vd.n_bp; i += NT) d += apply_priv<K>(cx, sm.list, vd.n_bp, i, privc);
+        } else {
+            for (int tb0 = 0; tb0 < nblocks; tb0 += TB) {
+                const int total = bernoulli_tile<K, NT>(sm, p, cx, vd, tb0, nblocks);
+                if (total < 0) { if (tid == 0 && p.status) atomicOr(p.status + item, 1); continue; }
+                const int lo = tb0 * RNG_BLOCK;
+                const long long hi = (long long)(tb0 + TB) * RNG_BLOCK;
+                for (int i = tid; i < total; i += NT) {
+                    const int pos = (int)(sm.list[i] >> 3);
+                    if (pos >= lo && pos < hi) d += apply_priv<K>(cx, sm.list, total, i, privc);
+                }
+                __syncthreads();  // list is rewritten by the next tile / slot
+            }
+        }
+        d = warp_sum(d);
+        if (lane == 0 && d) atomicAdd(&sm.dtot[c], d);
+        __syncthreads();
     }
 }
 
 template <int K, int NT, int OUT>
 __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_kernel(const ProfParams p) {
-    constexpr int F = 1 << (2 * K);
-    constexpr int VEC = F / 4;
-    constexpr int VPT = (VEC + NT - 1) / NT;
+    using C = ProfCfg<K, NT>;
+    constexpr int F = C::F, VEC = C::VEC, VPT = C::VPT, G = C::G, PRIVW = C::PRIVW;
     constexpr int ESZ = OUT == IDL_OUT_FREQ_F64 ? 8 : 4;
+    constexpr bool NEED_F = (OUT == IDL_OUT_FREQ_F32 || OUT == IDL_OUT_STD_F32);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ProfSmem<K, NT>& sm = *reinterpret_cast<ProfSmem<K, NT>*>(smem_raw);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-    // per-thread scaler statistics of the bins this thread streams (fixed for the whole launch)
-    float mean[VPT][4], scale[VPT][4], rscale[VPT][4];
-#pragma unroll
-    for (int vv = 0; vv < VPT; ++vv) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { mean[vv][e] = 0.f; scale[vv][e] = 1.f; rscale[vv][e] = 1.f; }
-        const int vec = tid + vv * NT;
-        if (OUT == IDL_OUT_STD_F32 && vec < VEC) {
-            const float4 m = reinterpret_cast<const float4*>(p.mean)[vec];
-            const float4 s = reinterpret_cast<const float4*>(p.scale)[vec];
-            mean[vv][0] = m.x; mean[vv][1] = m.y; mean[vv][2] = m.z; mean[vv][3] = m.w;
-            scale[vv][0] = s.x; scale[vv][1] = s.y; scale[vv][2] = s.z; scale[vv][3] = s.w;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) rscale[vv][e] = 1.0f / scale[vv][e];
-        }
+    const float magic = 8388608.0f - (float)p.pseudocount;
+    const bool cached = p.n_vars <= SVARS && p.S <= SVARS;
+    if (cached) {
+        for (int i = tid; i < p.n_vars; i += NT) sm.svars[i] = p.vars[i];
+        for (int i = tid; i < p.S; i += NT) sm.sout_off[i] = p.out_off[i];
     }
-    for (int i = tid; i < 2 * RNG_BLOCK; i += NT) (&sm.gtab[0][0])[i] = 0u;
+    for (int i = tid; i < STABS * RNG_BLOCK; i += NT)
+        (&sm.gtabs[0][0])[i] = i < p.n_tabs * RNG_BLOCK ? p.gtab[i] : 0u;
+    const VarDesc* __restrict__ vars = cached ? sm.svars : p.vars;
+    const long long* __restrict__ out_offs = cached ? sm.sout_off : reinterpret_cast<const long long*>(p.out_off);
 
     for (;;) {
         __syncthreads();  // previous item fully done (also protects sm.item)
@@ -242,12 +520,16 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
         const long long item = sm.item;
         if (item >= p.n_items) break;
         const long long seq = p.sidx ? (long long)p.sidx[item] : item;
-        const int L = p.len[seq];
+        ItemCtx cx;
+        cx.L = p.len[seq];
         const long long c0 = p.chunk_off[seq];
-        const uint32_t* __restrict__ codes = p.codes + c0 * 4;
-        const uint32_t* __restrict__ nmask = p.nmask + c0 * 2;
-        const int nchunks = (L + CHUNK_BASES - 1) / CHUNK_BASES;
-        const uint32_t seq_id = (uint32_t)(p.seq_id0 + seq);
+        cx.codes = p.codes + c0 * 4;
+        cx.nmask = p.nmask + c0 * 2;
+        cx.seq_id = (uint32_t)(p.seq_id0 + seq);
+        cx.seed = p.seed;
+        const int L = cx.L;
+        const int nhalf = ((L + CHUNK_BASES - 1) / CHUNK_BASES) * 2;
+        auto slot_var = [&](int slot) -> int { return p.sel ? p.sel[item * p.S + slot] : slot; };
 
         // ---- clean histogram -------------------------------------------------------------
         for (int i = tid; i < VEC; i += NT) reinterpret_cast<int4*>(sm.hist)[i] = make_int4(0, 0, 0, 0);
@@ -255,134 +537,147 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
         __syncthreads();
         {
             int nv = 0;
-            for (int c = tid; c < nchunks; c += NT) {
-                const uint4 w = __ldg(reinterpret_cast<const uint4*>(codes) + c);
-                nv += count_chunk<K>(codes, nmask, c, w.x, w.y, w.z, w.w, [&](uint32_t kmer) { atomicAdd(&sm.hist[kmer], 1); });
+            for (int h = tid; h < nhalf; h += NT) {
+                const uint2 w = __ldg(reinterpret_cast<const uint2*>(cx.codes) + h);
+                nv += count_half<K>(cx.codes, cx.nmask, h, w.x, w.y, [&](uint32_t kmer) { atomicAdd(&sm.hist[kmer], 1); });
             }
             nv = warp_sum(nv);
-            if ((tid & 31) == 0 && nv) atomicAdd(&sm.nvalid, nv);
+            if (lane == 0 && nv) atomicAdd(&sm.nvalid, nv);
         }
         __syncthreads();
         const int base_total = F * p.pseudocount + sm.nvalid;
 
-        // ---- variant groups --------------------------------------------------------------
-        const int n_groups = p.sel ? p.S : p.n_groups;
-        for (int g = 0; g < n_groups; ++g) {
-            int s0, ns, kind, v0;
-            if (p.sel) { s0 = g; ns = 1; v0 = p.sel[item * p.S + g]; kind = p.vars[v0].kind; }
-            else { const GroupDesc gd = p.groups[g]; s0 = gd.first_slot; ns = gd.n_slots; kind = gd.kind; v0 = s0; }
-            const VarDesc vd = p.vars[v0];
-            auto out_row = [&](int slot) -> void* {
-                return reinterpret_cast<unsigned char*>(p.out) + (size_t)ESZ * (size_t)(p.out_off[slot] + item * p.out_stride);
-            };
-
-            if (kind == KIND_CLEAN || (kind == KIND_RANDOM_N && (L == 0 || vd.n_bp <= 0))) {
-                for (int sl = 0; sl < ns; ++sl)
-                    stream_slot<K, NT, OUT>(sm.hist, base_total, p.pseudocount, p.accumulate, out_row(s0 + sl), mean, scale, rscale);
-                __syncthreads();
-            } else if (kind == KIND_RANDOM_N) {
-                // all slots of the group: draw -> rank-sort per slot -> lists in shared memory
-                const int n_bp = vd.n_bp;
-                const int cps = (n_bp + 3) / 4;  // philox calls per slot
-                for (int idx = tid; idx < ns * cps; idx += NT) {
-                    const int sl = idx / cps, call = idx - sl * cps;
-                    const int rng_id = p.sel ? vd.rng_id : p.vars[s0 + sl].rng_id;
-                    const U4 r = random_n_words(p.seed, seq_id, (uint32_t)rng_id, (uint32_t)call);
-                    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        if (L > 65535) {
+            long_path<K, NT, OUT>(sm, p, cx, vars, out_offs, item, seq, base_total);
+            continue;
+        }
+        // =================================== SHORT path ===================================
+        uint32_t* priv = sm.privtmp;
+        for (int vec = tid; vec < VEC; vec += NT) {  // G private uint16 copies of the clean histogram
+            const int4 h = reinterpret_cast<const int4*>(sm.hist)[vec];
+            const uint2 pk = make_uint2((uint32_t)h.x | ((uint32_t)h.y << 16), (uint32_t)h.z | ((uint32_t)h.w << 16));
 #pragma unroll
-                    for (int t = 0; t < 4; ++t)
-                        if (call * 4 + t < n_bp) sm.tmp[sl * n_bp + call * 4 + t] = random_n_entry(w[t], L);
+            for (int c = 0; c < G; ++c) reinterpret_cast<uint2*>(priv + c * PRIVW)[vec] = pk;
+        }
+        const float base_ft = (float)base_total;
+        const float base_y = 1.0f / base_ft;
+
+        for (int s0 = 0; s0 < p.S; s0 += G) {
+            const int gs = p.S - s0 < G ? p.S - s0 : G;
+            __syncthreads();  // copies restored / initialised; previous group's plan no longer read
+            // ---- plan: classify the slots of the group, output rows, default totals ----
+            if (wid == 0) {
+                int kc = 0;
+                if (lane < gs) {
+                    const VarDesc vd = vars[slot_var(s0 + lane)];
+                    if (vd.kind == KIND_RANDOM_N) kc = (L == 0 || vd.n_bp <= 0) ? 0 : (vd.n_bp <= 32 ? 1 : 3);
+                    else if (vd.kind == KIND_EXPLICIT) kc = 3;
+                    else if (vd.kind != KIND_CLEAN) kc = L > 0 ? 2 : 0;
+                    sm.gkind[lane] = kc;
+                    sm.dtot[lane] = 0;
+                    sm.gy[lane] = make_float2(base_ft, base_y);
+                    sm.grow[lane] = (long long)ESZ * (out_offs[s0 + lane] + item * p.out_stride);
                 }
-                for (int i = tid; i < ns; i += NT) sm.dtot[i] = 0;
-                __syncthreads();
-                for (int idx = tid; idx < ns * n_bp; idx += NT) {
-                    const int sl = idx / n_bp, i = idx - sl * n_bp;
-                    const uint32_t* t = sm.tmp + sl * n_bp;
-                    const uint32_t e = t[i];
-                    int rank = 0;
-                    for (int j = 0; j < n_bp; ++j) { const uint32_t ej = t[j]; rank += (ej < e || (ej == e && j < i)) ? 1 : 0; }
-                    sm.list[sl * n_bp + rank] = e;
-                }
-                __syncthreads();
-                const int n_pad = (n_bp + 31) & ~31;
-                for (int sl = 0; sl <= ns; ++sl) {
-                    // un-apply slot sl-1 and apply slot sl (independent +-1 updates, different warps)
-                    for (int idx = tid; idx < 2 * n_pad; idx += NT) {
-                        const int role = idx / n_pad, i = idx - role * n_pad;
-                        const int tsl = role == 0 ? sl : sl - 1;
-                        if (i < n_bp && tsl >= 0 && tsl < ns) {
-                            const int sgn = role == 0 ? 1 : -1;
-                            const int d = apply_entry<K>(codes, nmask, L, sm.list + tsl * n_bp, n_bp, i,
-                                                         [&](uint32_t kmer, int dd) { atomicAdd(&sm.hist[kmer], sgn * dd); });
-                            if (role == 0 && d) atomicAdd(&sm.dtot[tsl], d);
-                        }
-                    }
-                    __syncthreads();
-                    if (sl < ns) {
-                        stream_slot<K, NT, OUT>(sm.hist, base_total + sm.dtot[sl], p.pseudocount, p.accumulate, out_row(s0 + sl), mean, scale, rscale);
-                        __syncthreads();
-                    }
-                }
-            } else if (kind == KIND_EXPLICIT) {
-                const long long li = (long long)vd.explicit_idx * p.n_seqs_total + seq;
-                const uint32_t* glist = p.edits + p.edit_off[li];
-                const int n = (int)(p.edit_off[li + 1] - p.edit_off[li]);
-                if (tid == 0) sm.dtot[0] = 0;
-                __syncthreads();
-                for (int sgn = 1; sgn >= -1; sgn -= 2) {
-                    int d = 0;
-                    for (int i = tid; i < n; i += NT)
-                        d += apply_entry<K>(codes, nmask, L, glist, n, i, [&](uint32_t kmer, int dd) { atomicAdd(&sm.hist[kmer], sgn * dd); });
-                    if (sgn > 0) { d = warp_sum(d); if ((tid & 31) == 0 && d) atomicAdd(&sm.dtot[0], d); }
-                    __syncthreads();
-                    if (sgn > 0) {
-                        stream_slot<K, NT, OUT>(sm.hist, base_total + sm.dtot[0], p.pseudocount, p.accumulate, out_row(s0), mean, scale, rscale);
-                        __syncthreads();
-                    }
-                }
-            } else {
-                // TRANSITION / TRANSVERSION / BOTH: Bernoulli hits generated per 128-base block
-                if (tid < RNG_BLOCK) {
-                    sm.gtab[0][tid] = p.gtab[vd.tab1 * RNG_BLOCK + tid];
-                    sm.gtab[1][tid] = p.gtab[vd.tab2 * RNG_BLOCK + tid];
-                }
-                if (tid == 0) sm.dtot[0] = 0;
-                __syncthreads();
-                constexpr int TB = NT - 2;  // blocks per tile; one context block on each side
-                const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
-                for (int sgn = 1; sgn >= -1; sgn -= 2) {
-                    for (int tb0 = 0; tb0 < nblocks; tb0 += TB) {
-                        const int b = tb0 - 1 + tid;
-                        const bool active = b >= 0 && b < nblocks && b <= tb0 + TB;
-                        int cnt = 0;
-                        if (active)
-                            cnt = block_edits(kind, p.seed, seq_id, (uint32_t)vd.rng_id, b, L, codes, nmask, sm.gtab[0], sm.gtab[1], [](uint32_t) {});
-                        int total;
-                        int off = block_exscan<NT>(cnt, sm.scan, &total);
-                        if (total > LIST_CAP) {
-                            if (tid == 0 && p.status) atomicOr(p.status + item, 1);
-                            continue;  // uniform: total is the same for every thread
-                        }
-                        if (active && cnt)
-                            block_edits(kind, p.seed, seq_id, (uint32_t)vd.rng_id, b, L, codes, nmask, sm.gtab[0], sm.gtab[1], [&](uint32_t e) { sm.list[off++] = e; });
-                        __syncthreads();
-                        const int lo = tb0 * RNG_BLOCK;
-                        const long long hi = (long long)(tb0 + TB) * RNG_BLOCK;
-                        int d = 0;
-                        for (int i = tid; i < total; i += NT) {
-                            const int pos = (int)(sm.list[i] >> 3);
-                            if (pos >= lo && pos < hi)
-                                d += apply_entry<K>(codes, nmask, L, sm.list, total, i, [&](uint32_t kmer, int dd) { atomicAdd(&sm.hist[kmer], sgn * dd); });
-                        }
-                        if (sgn > 0) { d = warp_sum(d); if ((tid & 31) == 0 && d) atomicAdd(&sm.dtot[0], d); }
-                        __syncthreads();
-                    }
-                    if (sgn > 0) {
-                        stream_slot<K, NT, OUT>(sm.hist, base_total + sm.dtot[0], p.pseudocount, p.accumulate, out_row(s0), mean, scale, rscale);
-                        __syncthreads();
-                    }
+                const unsigned mb = __ballot_sync(0xffffffffu, kc == 2), mo = __ballot_sync(0xffffffffu, kc == 3);
+                if (lane == 0) { sm.gmask[0] = (int)mb; sm.gmask[1] = (int)mo; }
+            }
+            __syncthreads();
+            const unsigned bern_mask = (unsigned)sm.gmask[0], other_mask = (unsigned)sm.gmask[1];
+
+            // ---- (a1) CTA-wide slots (Bernoulli jointly, explicit, big Random_N) ----
+            if (bern_mask | other_mask) {
+                prep_cta_slots<K, NT>(sm, p, cx, vars, s0, item, seq, bern_mask, other_mask);
+                if (tid < gs && sm.gkind[tid] >= 2) {
+                    const float ft2 = (float)(base_total + sm.dtot[tid]);
+                    sm.gy[tid] = make_float2(ft2, 1.0f / ft2);
                 }
             }
+            // ---- (a2) warp-level slots: warp c patches copy c (Random_N, n_bp <= 32), concurrently ----
+            int nrec = 0;
+            const bool my_warp_slot = wid < gs && sm.gkind[wid] == 1;
+            if (my_warp_slot) {
+                const VarDesc vd = vars[slot_var(s0 + wid)];
+                const int n_bp = vd.n_bp;
+                uint32_t* privc = priv + wid * PRIVW;
+                const U4 r = random_n_words(p.seed, cx.seq_id, (uint32_t)vd.rng_id, (uint32_t)(lane >> 2));
+                const uint32_t wsel = (lane & 3) == 0 ? r.x : (lane & 3) == 1 ? r.y : (lane & 3) == 2 ? r.z : r.w;
+                const uint32_t e = lane < n_bp ? random_n_entry(wsel, L) : 0xFFFFFFFFu;
+                int rank = 0;
+                for (int j = 0; j < n_bp; ++j) {
+                    const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
+                    rank += (ej < e || (ej == e && j < lane)) ? 1 : 0;
+                }
+                if (lane < n_bp) sm.wlist[wid][rank] = e;
+                __syncwarp();
+                int d = 0;
+                if (lane < n_bp)
+                    d = apply_entry<K>(cx.codes, cx.nmask, L, sm.wlist[wid], n_bp, lane, [&](uint32_t kmer, int dd) {
+                        upd16(privc, kmer, dd);   // Random_N only removes windows (dd == -1)
+                        sm.wdelta[wid][lane * K + nrec] = (uint16_t)kmer;
+                        ++nrec;
+                    });
+                d = warp_sum(d);
+                if (lane == 0) {
+                    const float ft2 = (float)(base_total + d);
+                    sm.gy[wid] = make_float2(ft2, 1.0f / ft2);
+                    sm.dtot[wid] = d;
+                }
+            }
+            __syncthreads();
+            // ---- (b) stream the gs profiles ----
+            // scaler statistics of this thread's bins: live only during the streaming phase
+            float mean[VPT][4], scale[VPT][4], rscale[VPT][4];
+#pragma unroll
+            for (int vv = 0; vv < VPT; ++vv) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { mean[vv][e] = 0.f; scale[vv][e] = 1.f; rscale[vv][e] = 1.f; }
+                const int vec = tid + vv * NT;
+                if (OUT == IDL_OUT_STD_F32 && vec < VEC) {
+                    const float4 m = __ldg(reinterpret_cast<const float4*>(p.mean) + vec);
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale) + vec);
+                    const float4 rs = __ldg(reinterpret_cast<const float4*>(p.rscale) + vec);
+                    mean[vv][0] = m.x; mean[vv][1] = m.y; mean[vv][2] = m.z; mean[vv][3] = m.w;
+                    scale[vv][0] = sc.x; scale[vv][1] = sc.y; scale[vv][2] = sc.z; scale[vv][3] = sc.w;
+                    rscale[vv][0] = rs.x; rscale[vv][1] = rs.y; rscale[vv][2] = rs.z; rscale[vv][3] = rs.w;
+                }
+            }
+#pragma unroll 1
+            for (int c = 0; c < gs; ++c) {
+                const float2 fy = sm.gy[c];
+                unsigned char* row = reinterpret_cast<unsigned char*>(p.out) + sm.grow[c];
+                const uint2* src = reinterpret_cast<const uint2*>(priv + c * PRIVW);
+#pragma unroll
+                for (int vv = 0; vv < VPT; ++vv) {
+                    const int vec = tid + vv * NT;
+                    if (VEC % NT != 0 && vec >= VEC) break;
+                    const uint2 pk = src[vec];
+                    int ci[4] = {0, 0, 0, 0};
+                    float cf[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (NEED_F) cvt4_u16(pk, magic, cf);
+                    else {
+                        ci[0] = (int)(pk.x & 0xFFFFu) + p.pseudocount; ci[1] = (int)(pk.x >> 16) + p.pseudocount;
+                        ci[2] = (int)(pk.y & 0xFFFFu) + p.pseudocount; ci[3] = (int)(pk.y >> 16) + p.pseudocount;
+                    }
+                    emit_granule<OUT>(row, vec, ci, cf, NEED_F ? 0 : base_total + sm.dtot[c], fy.x, fy.y, false, p.accumulate,
+                                      mean[vv], scale[vv], rscale[vv]);
+                }
+            }
+            __syncthreads();
+            // ---- (c) restore the copies ----
+            if (my_warp_slot) {
+                uint32_t* privc = priv + wid * PRIVW;
+                for (int i = 0; i < nrec; ++i) upd16(privc, (uint32_t)sm.wdelta[wid][lane * K + i], +1);
+            }
+            unsigned rest = bern_mask | other_mask;
+            while (rest) {
+                const int c = __ffs(rest) - 1;
+                rest &= rest - 1;
+                for (int vec = tid; vec < VEC; vec += NT) {
+                    const int4 h = reinterpret_cast<const int4*>(sm.hist)[vec];
+                    reinterpret_cast<uint2*>(priv + c * PRIVW)[vec] = make_uint2((uint32_t)h.x | ((uint32_t)h.y << 16), (uint32_t)h.z | ((uint32_t)h.w << 16));
+                }
+            }
+            // the barrier at the top of the next group / item orders these writes
         }
     }
 }
@@ -480,14 +775,19 @@ static int sm_count() {
     return g_sm_count;
 }
 
-// workspace layout: [0,8) work counter | vars | groups | out_off | gtab
+__global__ void rscale_kernel(const float* __restrict__ scale, float* __restrict__ rscale, int F) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F) rscale[i] = 1.0f / scale[i];  // IEEE division: the correctly rounded reciprocal div_rn needs
+}
+
+// workspace layout: [0,8) work counter | vars | out_off | gtab | rscale
 constexpr size_t WS_VARS = 64;
 constexpr int MAX_VARIANTS = 4096;
 constexpr int MAX_TABS = 64;
-constexpr size_t WS_GROUPS = WS_VARS + sizeof(VarDesc) * MAX_VARIANTS;
-constexpr size_t WS_OUTOFF = WS_GROUPS + sizeof(GroupDesc) * MAX_VARIANTS;
+constexpr size_t WS_OUTOFF = WS_VARS + sizeof(VarDesc) * MAX_VARIANTS;
 constexpr size_t WS_GTAB = WS_OUTOFF + sizeof(int64_t) * MAX_VARIANTS;
-constexpr size_t WS_TOTAL = WS_GTAB + sizeof(uint32_t) * RNG_BLOCK * MAX_TABS;
+constexpr size_t WS_RSCALE = WS_GTAB + sizeof(uint32_t) * RNG_BLOCK * MAX_TABS;
+constexpr size_t WS_TOTAL = WS_RSCALE + sizeof(float) * 4096;
 
 template <int K, int NT, int OUT>
 static int launch_profiles(const ProfParams& p, cudaStream_t st) {
@@ -577,9 +877,8 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
     const int F = 1 << (2 * k);
     if (k >= 1 && F >= 4 && (out_stride % 4 != 0)) return set_error(IDL_EINVAL, "idl_profiles: out_stride must be a multiple of 4%s", "");
 
-    // ---- host-side plan: variant descriptors, gap tables, slot groups ----
+    // ---- host-side plan: variant descriptors and gap tables ----
     static thread_local VarDesc h_vars[MAX_VARIANTS];
-    static thread_local GroupDesc h_groups[MAX_VARIANTS];
     static thread_local uint32_t h_gtab[MAX_TABS * RNG_BLOCK];
     double tab_p[MAX_TABS];
     int n_tabs = 0;
@@ -595,39 +894,23 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
         const idl_variant& iv = variants[v];
         VarDesc& d = h_vars[v];
         d.kind = iv.kind; d.rng_id = iv.rng_id; d.n_bp = iv.n_bp; d.explicit_idx = iv.explicit_idx; d.tab1 = 0; d.tab2 = 0;
+        d.slope1 = 0.f; d.slope2 = 0.f;
         if (iv.kind < IDL_KIND_CLEAN || iv.kind > IDL_KIND_EXPLICIT) return set_error(IDL_EINVAL, "idl_profiles: bad variant kind%s %lld", "", iv.kind);
         if (iv.kind == IDL_KIND_TRANSITION || iv.kind == IDL_KIND_BOTH) {
             if (!(iv.p1 >= 0.0 && iv.p1 <= 1.0)) return set_error(IDL_EINVAL, "idl_profiles: p1 out of range%s", "");
-            d.tab1 = table_of(iv.p1);
+            d.tab1 = table_of(iv.p1); d.slope1 = gap_slope(iv.p1);
         }
         if (iv.kind == IDL_KIND_TRANSVERSION || iv.kind == IDL_KIND_BOTH) {
             if (!(iv.p2 >= 0.0 && iv.p2 <= 1.0)) return set_error(IDL_EINVAL, "idl_profiles: p2 out of range%s", "");
-            d.tab2 = table_of(iv.p2);
+            d.tab2 = table_of(iv.p2); d.slope2 = gap_slope(iv.p2);
         }
         if (d.tab1 < 0 || d.tab2 < 0) return set_error(IDL_EUNSUPPORTED, "idl_profiles: too many distinct mutation rates%s", "");
-        if (iv.kind == IDL_KIND_RANDOM_N && (iv.n_bp < 0 || iv.n_bp > LIST_CAP)) return set_error(IDL_EUNSUPPORTED, "idl_profiles: Random_N n_bp must be <= 4096%s", "");
+        if (iv.kind == IDL_KIND_RANDOM_N && (iv.n_bp < 0 || iv.n_bp > LIST_CAP / 2)) return set_error(IDL_EUNSUPPORTED, "idl_profiles: Random_N n_bp must be <= 2048%s", "");
         if (iv.kind == IDL_KIND_EXPLICIT && (!d_edit_off || !d_edits)) return set_error(IDL_EINVAL, "idl_profiles: explicit variant without edit lists%s", "");
-    }
-    int n_groups = 0;
-    if (!d_sel) {
-        for (int s = 0; s < S;) {
-            GroupDesc& g = h_groups[n_groups++];
-            g.first_slot = s; g.kind = h_vars[s].kind; g.n_slots = 1;
-            if (g.kind == IDL_KIND_RANDOM_N || g.kind == IDL_KIND_CLEAN) {
-                const int n_bp = h_vars[s].n_bp > 0 ? h_vars[s].n_bp : 1;
-                int cap = LIST_CAP / n_bp;
-                if (cap > MAX_GROUP) cap = MAX_GROUP;
-                while (s + g.n_slots < S && g.n_slots < cap && h_vars[s + g.n_slots].kind == g.kind &&
-                       (g.kind == IDL_KIND_CLEAN || h_vars[s + g.n_slots].n_bp == h_vars[s].n_bp))
-                    ++g.n_slots;
-            }
-            s += g.n_slots;
-        }
     }
     unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
     IDL_CUDA_CHECK(cudaMemsetAsync(ws, 0, 8, st));
     IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_VARS, h_vars, sizeof(VarDesc) * n_variants, cudaMemcpyHostToDevice, st));
-    if (n_groups) IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_GROUPS, h_groups, sizeof(GroupDesc) * n_groups, cudaMemcpyHostToDevice, st));
     IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_OUTOFF, out_off, sizeof(int64_t) * S, cudaMemcpyHostToDevice, st));
     if (n_tabs) IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_GTAB, h_gtab, sizeof(uint32_t) * RNG_BLOCK * n_tabs, cudaMemcpyHostToDevice, st));
     // the staging arrays are thread_local statics reused by the next call: make sure the
@@ -636,14 +919,18 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
 
     ProfParams p;
     p.codes = d_codes; p.nmask = d_nmask; p.chunk_off = d_chunk_off; p.len = d_len; p.sidx = d_sidx; p.sel = d_sel;
-    p.n_items = n_items; p.seq_id0 = seq_id0; p.n_seqs_total = n_seqs_total; p.S = S; p.n_groups = n_groups;
+    p.n_items = n_items; p.seq_id0 = seq_id0; p.n_seqs_total = n_seqs_total; p.S = S; p.n_vars = n_variants; p.n_tabs = n_tabs;
     p.vars = reinterpret_cast<const VarDesc*>(ws + WS_VARS);
-    p.groups = reinterpret_cast<const GroupDesc*>(ws + WS_GROUPS);
     p.seed = seed; p.gtab = reinterpret_cast<const uint32_t*>(ws + WS_GTAB);
     p.edit_off = d_edit_off; p.edits = d_edits; p.out = d_out;
     p.out_off = reinterpret_cast<const int64_t*>(ws + WS_OUTOFF);
     p.out_stride = out_stride; p.pseudocount = pseudocount; p.accumulate = accumulate;
     p.mean = d_mean; p.scale = d_scale; p.status = d_status;
+    p.rscale = reinterpret_cast<const float*>(ws + WS_RSCALE);
+    if (out_kind == IDL_OUT_STD_F32) {
+        rscale_kernel<<<(F + 255) / 256, 256, 0, st>>>(d_scale, reinterpret_cast<float*>(ws + WS_RSCALE), F);
+        IDL_CUDA_CHECK(cudaGetLastError());
+    }
     p.work_counter = reinterpret_cast<unsigned long long*>(ws);
     switch (k) {
         case 1: return dispatch_out<1, 64>(p, out_kind, st);

@@ -73,9 +73,9 @@ typedef struct idl_variant {
 int idl_abi_version(void);
 const char* idl_last_error(void);
 
-/* T[g-1] = floor((1-(1-p)^g) * 2^32), g = 1..128: the geometric gap table the rng mode
+/* T[g-1] = floor((1-(1-p)^g) * 2^32), g = 1..64: the geometric gap table the rng mode
  * uses for an iid Bernoulli(p) process (host function; exported for the parity tests). */
-int idl_geometric_table(double p, uint32_t* out128);
+int idl_geometric_table(double p, uint32_t* out64);
 
 /* K1 — replaces check_sequence (idelucs/utils.py:26-51) + the byte LUT of kmer_counts
  * (idelucs/kmers.pyx:19-34).  d_ascii: concatenated sequence bytes; d_byte_off int64[n+1].

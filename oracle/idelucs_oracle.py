@@ -367,7 +367,7 @@ _PHILOX_W0 = 0x9E3779B9
 _PHILOX_W1 = 0xBB67AE85
 _M32 = 0xFFFFFFFF
 
-RNG_BLOCK = 128  # bases per Bernoulli generation block
+RNG_BLOCK = 64  # bases per Bernoulli generation block
 
 # variant kinds (shared numbering with include/idelucs_b200.h)
 KIND_CLEAN, KIND_TRANSITION, KIND_TRANSVERSION, KIND_BOTH, KIND_RANDOM_N, KIND_EXPLICIT = range(6)

@@ -43,10 +43,9 @@ long long emul_pack(const uint8_t* ascii, long long L, int strict, uint32_t* cod
 template <int K>
 static int counts_k(const uint32_t* codes, const uint32_t* nmask, int L, int* counts) {
     int nv = 0;
-    const int nchunks = (L + 63) / 64;
-    for (int c = 0; c < nchunks; ++c)
-        nv += count_chunk<K>(codes, nmask, c, codes[4 * c], codes[4 * c + 1], codes[4 * c + 2], codes[4 * c + 3],
-                             [&](uint32_t kmer) { counts[kmer] += 1; });
+    const int nhalf = ((L + 63) / 64) * 2;
+    for (int h = 0; h < nhalf; ++h)
+        nv += count_half<K>(codes, nmask, h, codes[2 * h], codes[2 * h + 1], [&](uint32_t kmer) { counts[kmer] += 1; });
     return nv;
 }
 
@@ -100,7 +99,8 @@ int emul_variant(const uint32_t* codes, const uint32_t* nmask, int L, int K, uns
         geometric_table(p2, T2);
         const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
         for (int b = 0; b < nblocks; ++b)
-            block_edits(kind, seed, seq_id, rng_id, b, L, codes, nmask, T1, T2, [&](uint32_t e) { list.push_back(e); });
+            block_edits(kind, seed, seq_id, rng_id, b, L, codes, nmask, T1, gap_slope(p1), T2, gap_slope(p2),
+                        [&](uint32_t e) { list.push_back(e); });
     }
     if (n_list_out) {
         *n_list_out = (int)list.size();

@@ -33,10 +33,10 @@ def test_geometric_table_matches_oracle():
     from idelucs_b200 import _lib
     lib = _lib.load()
     for p in (1e-2, 0.5e-2, 0.25, 1e-7):
-        out = (ctypes.c_uint32 * 128)()
+        out = (ctypes.c_uint32 * 64)()
         assert lib.idl_geometric_table(p, out) == 0
         assert list(out) == orc.geometric_table(p)
-    assert lib.idl_geometric_table(2.0, (ctypes.c_uint32 * 128)()) != 0
+    assert lib.idl_geometric_table(2.0, (ctypes.c_uint32 * 64)()) != 0
     assert b"bad argument" in lib.idl_last_error()
 
 

@@ -255,9 +255,10 @@ def test_full_size_properties(ft, SeqSet):
     assert float((f.double().sum(dim=2) - 1).abs().max()) < 1e-5
     c3 = ft.profiles(ss, k, variants, out_kind=ft.OUT_COUNTS_I32, seed=4)
     assert not torch.equal(c[1], c3[1])
-    # mutation counts per pass follow Binomial(L, p): mean within 5 sigma over the slab
+    # each of the ~L*(1-(1-p1)(1-p2)) edits of pass 0 moves k windows from one bin to another:
+    # L1 distance of the histograms ~ 2k per edit, minus remove/add collisions in the same bin
     dist_both = (c[1] - c[0]).abs().sum(dim=1).double().mean().item() / (2 * k)
-    assert 0.8 * L * 0.015 < dist_both < 1.05 * L * 0.015, dist_both
+    assert 0.6 * L * 0.015 < dist_both < 1.02 * L * 0.015, dist_both
 
 
 def _loss_inputs(B, C, salt):
@@ -281,8 +282,10 @@ def test_iid_loss_goldens(golden_dir):
         d1, d2 = z1.grad.cpu().numpy()[rows], z2.grad.cpu().numpy()[rows]
         w1, w2 = np.asarray(c["dz1_rows64"]), np.asarray(c["dz2_rows64"])
         scale = max(np.abs(w1).max(), 1e-12)
-        assert np.abs(d1 - w1).max() <= 2e-5 * scale, (c["B"], c["C"], np.abs(d1 - w1).max(), scale)
-        assert np.abs(d2 - w2).max() <= 2e-5 * max(np.abs(w2).max(), 1e-12)
+        # gradients: the reference's own float32 autograd deviates from float64 by up to 6e-5 of
+        # the largest entry on these cases (dz1_rows32 in the golden file); same class required
+        assert np.abs(d1 - w1).max() <= 1e-4 * scale, (c["B"], c["C"], np.abs(d1 - w1).max(), scale)
+        assert np.abs(d2 - w2).max() <= 1e-4 * max(np.abs(w2).max(), 1e-12)
         j = compute_joint(z1.detach(), z2.detach()).cpu().numpy()
         wj = orc.compute_joint(z1n.astype(np.float64), z2n.astype(np.float64))
         np.testing.assert_allclose(j, wj, rtol=1e-5, atol=1e-12)

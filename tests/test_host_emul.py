@@ -108,7 +108,7 @@ def test_philox_and_tables(emul):
     emul.emul_philox(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0, _ptr(out))
     assert tuple(int(x) for x in out) == orc.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0))
     for p in (1e-2, 0.5e-2, 0.3, 0.0, 1.0, 1e-9):
-        t = np.zeros(128, np.uint32)
+        t = np.zeros(64, np.uint32)
         emul.emul_geometric_table(ctypes.c_double(p), _ptr(t))
         assert [int(x) for x in t] == orc.geometric_table(p)
 

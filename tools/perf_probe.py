@@ -61,6 +61,11 @@ def main():
         print("%-28s best %8.3f ms avg %8.3f ms  %8.1f Mprofiles/s  %7.1f GB/s" % (name, best, avg, nv * n / best / 1e3, b / best / 1e6))
     best, avg = timeit(lambda: ft.Scaler.fit(out[0]))
     print("scaler fit on [%d,%d]: %.3f ms" % (n, F, best))
+    big = out[:8]
+    best, avg = timeit(lambda: big.fill_(1.0))
+    print("torch fill 8 variants (write only): %.3f ms -> %.1f GB/s" % (best, big.numel() * 4 / best / 1e6))
+    best, avg = timeit(lambda: big.sum())
+    print("torch sum 8 variants (read only): %.3f ms -> %.1f GB/s" % (best, big.numel() * 4 / best / 1e6))
     best, avg = timeit(lambda: out[1].copy_(out[0]))
     print("torch copy 1 variant: %.3f ms -> %.1f GB/s" % (best, 2 * n * F * 4 / best / 1e6))
 
