@@ -220,6 +220,36 @@ IDL_HD int apply_entry(const uint32_t* codes, const uint32_t* nmask, int L, cons
 }
 
 // ---------------------------------------------------------------------------------------
+// Random_N specialisation of the delta rule (idelucs/utils.py:89-95 sets bases to N, so
+// windows are only ever REMOVED): draw i of an UNSORTED list of n draws (entry = pos<<3|4)
+// removes the clean windows ending in [p_i, min(p_i+K-1, p_next-1, L-1)], p_next = smallest
+// drawn position > p_i; among duplicate draws of one position only the first acts.
+// emit(kmer) is called once per removed window.  Same result as apply_entry on the sorted
+// list, without sorting or rebuilding the mutated window.
+// ---------------------------------------------------------------------------------------
+template <int K, class Emit>
+IDL_HD void random_n_removals(const uint32_t* codes, const uint32_t* nmask, int L, const uint32_t* ent, int n, int i,
+                              Emit emit) {
+    constexpr uint32_t KMASK = (1u << (2 * K)) - 1u;
+    constexpr uint32_t NMASKK = (1u << K) - 1u;
+    const int p = (int)(ent[i] >> 3);
+    int pn = 0x7fffffff;
+    for (int j = 0; j < n; ++j) {
+        const int pj = (int)(ent[j] >> 3);
+        if (pj == p && j < i) return;
+        if (pj > p && pj < pn) pn = pj;
+    }
+    int e_hi = p + K - 1;
+    if (pn - 1 < e_hi) e_hi = pn - 1;
+    if (L - 1 < e_hi) e_hi = L - 1;
+    const Window<K> cw = load_window<K>(codes, nmask, p - (K - 1));
+    for (int e = p; e <= e_hi; ++e) {
+        const int sh = K - 1 - (e - p);
+        if (((cw.nbits >> sh) & NMASKK) == 0u) emit((cw.bases >> (2 * sh)) & KMASK);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11), counter (c0,c1,c2,c3), key (k0,k1)
 // ---------------------------------------------------------------------------------------
 struct U4 { uint32_t x, y, z, w; };
@@ -355,6 +385,124 @@ IDL_HD int block_edits(int kind, uint64_t seed, uint32_t seq_id, uint32_t varian
         if (!nflag_at(nmask, p)) { emit(((uint32_t)p << 3) | val); ++n; }
     }
     return n;
+}
+
+// ---------------------------------------------------------------------------------------
+// FAST block generator: the same edits as block_edits(), produced without data-dependent
+// loops or a second RNG pass, for blocks with at most FAST_CAP hits per stream (the rule
+// at the reference's rates; otherwise the caller falls back to block_edits()).  All arrays
+// are statically indexed so they live in registers.
+// ---------------------------------------------------------------------------------------
+constexpr int FAST_CAP = 6;
+
+IDL_HD uint32_t u4_sel(const U4& r, int i) { return i == 0 ? r.x : i == 1 ? r.y : i == 2 ? r.z : r.w; }
+
+// hits of one stream in one block: block-relative positions, ascending, 8 bits each in
+// `pos8` (hit i at bits [8i, 8i+8); 0xFF = no hit), choice bit i in chbits.
+// Returns false when the block has more than FAST_CAP hits (overflow).
+template <bool CHOICE>
+IDL_HD bool fast_stream(uint64_t seed, uint32_t seq_id, uint32_t variant, uint32_t stream, int block, int L,
+                        const uint32_t* T, float slope, uint64_t& pos8, uint32_t& chbits) {
+    constexpr int WPS = CHOICE ? 2 : 1;  // words per step
+    int cur = -1;                        // block-relative
+    int end = L - block * RNG_BLOCK;
+    if (end > RNG_BLOCK) end = RNG_BLOCK;
+    bool done = end <= 0;
+    bool overflow = false;
+    pos8 = 0xFFFFFFFFFFFFFFFFull;
+    chbits = 0u;
+    U4 r;
+    r.x = r.y = r.z = r.w = 0u;
+#pragma unroll
+    for (int it = 0; it <= FAST_CAP; ++it) {
+        const int wi = it * WPS;
+        if ((wi & 3) == 0 && !done)
+            r = philox4x32_10((uint32_t)(wi >> 2), (uint32_t)block, seq_id, (variant << 2) | stream, (uint32_t)seed, (uint32_t)(seed >> 32));
+        if (!done) {
+            const int g = gap_of(u4_sel(r, wi & 3), T, slope);
+            const uint32_t ch = CHOICE ? (u4_sel(r, (wi & 3) + 1) >> 31) : 0u;
+            if (g == 0 || cur + g >= end) done = true;
+            else {
+                cur += g;
+                if (it < FAST_CAP) {
+                    pos8 = (pos8 & ~(0xFFull << (8 * it))) | ((uint64_t)cur << (8 * it));
+                    chbits |= ch << it;
+                } else overflow = true;
+            }
+        }
+    }
+    return !overflow;
+}
+
+struct FastBlock {
+    uint64_t a8, b8;   // transition / transversion hits (block-relative, 8 bits each, 0xFF = none)
+    uint32_t chb;      // transversion choice bits
+    uint32_t keep;     // bit i: transition hit i is emitted; bit FAST_CAP+j: transversion hit j
+    int cnt;           // number of emitted edits
+    bool ok;           // false: overflow, use block_edits()
+};
+
+IDL_HD int fast_pos(uint64_t p8, int i) { return (int)((p8 >> (8 * i)) & 0xFFull); }
+
+IDL_HD FastBlock fast_block(int kind, uint64_t seed, uint32_t seq_id, uint32_t variant, int block, int L, const uint32_t* nmask,
+                            const uint32_t* T1, float slope1, const uint32_t* T2, float slope2) {
+    FastBlock f;
+    f.a8 = f.b8 = 0xFFFFFFFFFFFFFFFFull; f.chb = 0u; f.keep = 0u; f.cnt = 0; f.ok = true;
+    uint32_t dummy;
+    if (kind == KIND_TRANSITION || kind == KIND_BOTH)
+        f.ok = fast_stream<false>(seed, seq_id, variant, STREAM_TRANSITION, block, L, T1, slope1, f.a8, dummy);
+    if (kind == KIND_TRANSVERSION || kind == KIND_BOTH)
+        f.ok = fast_stream<true>(seed, seq_id, variant, STREAM_TRANSVERSION, block, L, T2, slope2, f.b8, f.chb) && f.ok;
+    // a transition hit is dropped where a transversion hits the same base; hits on N are dropped
+    const int base = block * RNG_BLOCK;
+#pragma unroll
+    for (int i = 0; i < FAST_CAP; ++i) {
+        const int ai = fast_pos(f.a8, i), bi = fast_pos(f.b8, i);
+        bool ka = ai != 0xFF;
+#pragma unroll
+        for (int j = 0; j < FAST_CAP; ++j) ka = ka && (fast_pos(f.b8, j) != ai);
+        if (ka) ka = !nflag_at(nmask, base + ai);
+        bool kb = bi != 0xFF;
+        if (kb) kb = !nflag_at(nmask, base + bi);
+        f.keep |= (ka ? 1u : 0u) << i;
+        f.keep |= (kb ? 1u : 0u) << (FAST_CAP + i);
+    }
+#if defined(__CUDA_ARCH__)
+    f.cnt = __popc(f.keep);
+#else
+    f.cnt = __builtin_popcount(f.keep);
+#endif
+    return f;
+}
+
+// write the block's edits, position-sorted, to dst[0..cnt)
+IDL_HD void fast_block_write(const FastBlock& f, int block, const uint32_t* codes, uint32_t* dst) {
+    const int base = block * RNG_BLOCK;
+#pragma unroll
+    for (int i = 0; i < FAST_CAP; ++i) {
+        if ((f.keep >> i) & 1u) {  // transition hit i: rank = kept transitions before + kept transversions below
+            const int ai = fast_pos(f.a8, i);
+            int rank = 0;
+#pragma unroll
+            for (int t = 0; t < FAST_CAP; ++t) {
+                rank += (t < i && ((f.keep >> t) & 1u)) ? 1 : 0;
+                rank += (((f.keep >> (FAST_CAP + t)) & 1u) && fast_pos(f.b8, t) < ai) ? 1 : 0;
+            }
+            dst[rank] = ((uint32_t)(base + ai) << 3) | (code_at(codes, base + ai) ^ 2u);
+        }
+        if ((f.keep >> (FAST_CAP + i)) & 1u) {
+            const int bi = fast_pos(f.b8, i);
+            int rank = 0;
+#pragma unroll
+            for (int t = 0; t < FAST_CAP; ++t) {
+                rank += (t < i && ((f.keep >> (FAST_CAP + t)) & 1u)) ? 1 : 0;
+                rank += (((f.keep >> t) & 1u) && fast_pos(f.a8, t) < bi) ? 1 : 0;
+            }
+            const uint32_t c = code_at(codes, base + bi);
+            const uint32_t cb = (f.chb >> i) & 1u;
+            dst[rank] = ((uint32_t)(base + bi) << 3) | ((c & 1u) ? (cb << 1) : (1u | ((1u - cb) << 1)));
+        }
+    }
 }
 
 // Random_N (idelucs/utils.py:89-95): draw i of the variant -> position floor(w_i * L / 2^32)

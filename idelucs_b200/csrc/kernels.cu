@@ -11,6 +11,7 @@
 // bound by the HBM write of the profiles.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/idelucs_b200.h"
@@ -29,8 +30,12 @@ int set_error(int code, const char* fmt, const char* a, long long b) {
     return code;
 }
 
-constexpr int LIST_CAP = 4096;   // on-chip edit list entries per CTA
-constexpr int MAX_GROUP = 256;   // variant slots per Random_N group
+constexpr int LIST_CAP = 2048;   // on-chip edit list entries per CTA
+constexpr int SG = 32;           // variant slots per supergroup (Random_N removals precomputed together)
+constexpr int REM_CAP = 3840;    // removed k-mers buffered per supergroup (32 slots x 20 draws x k=6)
+constexpr int ENT_CAP = 1024;    // Random_N draws buffered per supergroup (aliases the edit list)
+constexpr int SSEQ_CHUNKS = 320; // sequences up to 20480 bases are staged in shared memory (codes + mask)
+constexpr int SSEQ_CW = SSEQ_CHUNKS * 4 + 4, SSEQ_MW = SSEQ_CHUNKS * 2 + 2;
 constexpr int SVARS = 64;        // variant descriptors cached in shared memory
 constexpr int STABS = 4;         // gap tables cached in shared memory
 
@@ -62,6 +67,7 @@ struct ProfParams {
     const float* rscale;  // 1/scale (IEEE), computed into the workspace by rscale_kernel
     int32_t* status;
     unsigned long long* work_counter;
+    unsigned long long* phase_prof;   // optional: cycles per kernel phase summed over CTAs (thread 0), IDL_PHASE_PROF=1
 };
 
 // ---------------------------------------------------------------------------------------
@@ -178,16 +184,20 @@ struct ProfSmem {
     using C = ProfCfg<K, NT>;
     int hist[C::F];
     uint32_t privtmp[C::PT];          // short path: G private uint16 copies; long path: unsorted Random_N draws
-    uint32_t list[LIST_CAP + 8];      // CTA-wide position-sorted edit list
-    uint32_t wlist[C::G][32];         // per-warp sorted Random_N lists
-    uint16_t wdelta[C::G][32 * K];    // k-mers removed by each lane's entry (to restore the copy)
+    uint32_t list[LIST_CAP + 8];      // CTA-wide position-sorted edit list; also the supergroup's Random_N draws
+    uint32_t sseq[SSEQ_CW + SSEQ_MW]; // packed bases + reset mask of the current sequence (when it fits)
+    uint16_t rem[REM_CAP];            // k-mers of the clean windows each Random_N slot removes
     uint32_t gtabs[STABS][RNG_BLOCK]; // geometric gap tables (first STABS of the launch)
-    int dtot[MAX_GROUP];
-    int gkind[C::G];                  // per copy of the current group: 0 none, 1 warp Random_N, 2 Bernoulli, 3 other CTA-wide
+    int pre_kind[SG];                 // per slot of the supergroup: 0 none, 1 small Random_N, 2 Bernoulli, 3 other CTA-wide
+    int pre_off[SG];                  // first draw of the slot in ent[] (x K = first entry in rem[])
+    int pre_nbp[SG];                  // draws of the slot
+    int remcnt[SG];                   // removed windows of the slot
+    int dtot[SG];                     // change of the counted-window total of the slot
+    float2 gy[SG];                    // per slot: (float total, 1/total)
+    long long grow[SG];               // per slot: byte offset of the output row
     int seg_off[C::G + 1];            // joint Bernoulli pass: list segment of each Bernoulli slot
-    int gmask[2];                     // ballot masks: Bernoulli copies, other CTA-wide copies
-    float2 gy[C::G];                  // per copy: (float total, 1/total)
-    long long grow[C::G];             // per copy: byte offset of the output row
+    unsigned mask_bern, mask_other;   // ballot masks over the supergroup's slots
+    int sg_n;                         // slots in the current supergroup
     int scan[NT / 32 + 2];
     int nvalid;
     long long item;
@@ -412,23 +422,74 @@ __device__ __noinline__ void long_path(ProfSmem<K, NT>& sm, const ProfParams& p,
     }
 }
 
+// development aid (IDL_PHASE_PROF=1): thread 0 attributes its elapsed cycles to kernel phases
+struct PhaseClock {
+    unsigned long long* base;
+    long long t_prev;
+    __device__ __forceinline__ void tick(int id) {
+        if (base && threadIdx.x == 0) {
+            const long long t = clock64();
+            atomicAdd(base + id, (unsigned long long)(t - t_prev));
+            t_prev = t;
+        }
+    }
+};
+
 // CTA-wide prep of the Bernoulli / explicit / big-Random_N slots of one group (short path):
 // patches the private copies and accumulates sm.dtot.  Contains barriers (uniform control flow).
 template <int K, int NT>
 __device__ __noinline__ void prep_cta_slots(ProfSmem<K, NT>& sm, const ProfParams& p, const ItemCtx& cx, const VarDesc* vars, int s0,
-                                            long long item, long long seq, unsigned bern_mask, unsigned other_mask) {
+                                            long long item, long long seq, unsigned bern_mask, unsigned other_mask, int* dtot,
+                                            int copy0, PhaseClock& pc) {
     using C = ProfCfg<K, NT>;
     constexpr int PRIVW = C::PRIVW;
     constexpr int TB = NT - 2;
     const int tid = threadIdx.x, lane = tid & 31;
     const int L = cx.L;
     const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
-    uint32_t* priv = sm.privtmp;
+    uint32_t* priv = sm.privtmp + copy0 * PRIVW;
     auto slot_var = [&](int slot) -> int { return p.sel ? p.sel[item * p.S + slot] : slot; };
     // ---- Bernoulli slots jointly: thread <-> (slot, 64-base block) ----
     const int nb = __popc(bern_mask);
     bool bern_done = nb == 0;
     if (nb > 0 && nb * nblocks <= NT) {
+        // fast path: register-only generator (<= FAST_CAP hits per stream and block)
+        const int j = tid / nblocks, b = tid - j * nblocks;
+        const bool active = tid < nb * nblocks;
+        const int c = active ? (int)__fns(bern_mask, 0, j + 1) : 0;
+        const VarDesc vd = vars[slot_var(s0 + c)];
+        FastBlock f;
+        f.cnt = 0; f.ok = true;
+        if (active)
+            f = fast_block(vd.kind, cx.seed, cx.seq_id, (uint32_t)vd.rng_id, b, L, cx.nmask, gap_table(sm, p, vd.tab1), vd.slope1,
+                           gap_table(sm, p, vd.tab2), vd.slope2);
+        pc.tick(7);
+        if (!__syncthreads_or(active && !f.ok)) {
+            int total;
+            const int off = block_exscan<NT>(f.cnt, sm.scan, &total);
+            pc.tick(8);
+            if (total <= LIST_CAP) {  // uniform
+                bern_done = true;
+                if (active && b == 0) sm.seg_off[j] = off;
+                if (tid == 0) sm.seg_off[nb] = total;
+                if (active && f.cnt) fast_block_write(f, b, cx.codes, sm.list + off);
+                __syncthreads();
+                pc.tick(9);
+                for (int i = tid; i < total; i += NT) {
+                    int jj = 0;
+                    while (i >= sm.seg_off[jj + 1]) ++jj;
+                    const int cc = (int)__fns(bern_mask, 0, jj + 1);
+                    const int so = sm.seg_off[jj];
+                    const int d = apply_priv<K>(cx, sm.list + so, sm.seg_off[jj + 1] - so, i - so, priv + cc * PRIVW);
+                    if (d) atomicAdd(&dtot[cc], d);
+                }
+                pc.tick(10);
+                __syncthreads();
+                pc.tick(11);
+            }
+        }
+    }
+    if (!bern_done && nb > 0 && nb * nblocks <= NT) {  // generic generator (any number of hits per block)
         const int j = tid / nblocks, b = tid - j * nblocks;
         const bool active = tid < nb * nblocks;
         const int c = active ? (int)__fns(bern_mask, 0, j + 1) : 0;
@@ -452,7 +513,7 @@ __device__ __noinline__ void prep_cta_slots(ProfSmem<K, NT>& sm, const ProfParam
                 const int cc = (int)__fns(bern_mask, 0, jj + 1);
                 const int so = sm.seg_off[jj];
                 const int d = apply_priv<K>(cx, sm.list + so, sm.seg_off[jj + 1] - so, i - so, priv + cc * PRIVW);
-                if (d) atomicAdd(&sm.dtot[cc], d);
+                if (d) atomicAdd(&dtot[cc], d);
             }
             __syncthreads();
         }
@@ -487,7 +548,7 @@ __device__ __noinline__ void prep_cta_slots(ProfSmem<K, NT>& sm, const ProfParam
             }
         }
         d = warp_sum(d);
-        if (lane == 0 && d) atomicAdd(&sm.dtot[c], d);
+        if (lane == 0 && d) atomicAdd(&dtot[c], d);
         __syncthreads();
     }
 }
@@ -513,6 +574,10 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
     const VarDesc* __restrict__ vars = cached ? sm.svars : p.vars;
     const long long* __restrict__ out_offs = cached ? sm.sout_off : reinterpret_cast<const long long*>(p.out_off);
 
+    PhaseClock pclk;
+    pclk.base = p.phase_prof;
+    pclk.t_prev = p.phase_prof ? clock64() : 0;
+    auto phase = [&](int id) { pclk.tick(id); };
     for (;;) {
         __syncthreads();  // previous item fully done (also protects sm.item)
         if (tid == 0) sm.item = (long long)atomicAdd(p.work_counter, 1ull);
@@ -529,6 +594,7 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
         cx.seed = p.seed;
         const int L = cx.L;
         const int nhalf = ((L + CHUNK_BASES - 1) / CHUNK_BASES) * 2;
+        const bool staged = nhalf <= 2 * SSEQ_CHUNKS;
         auto slot_var = [&](int slot) -> int { return p.sel ? p.sel[item * p.S + slot] : slot; };
 
         // ---- clean histogram -------------------------------------------------------------
@@ -539,13 +605,23 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
             int nv = 0;
             for (int h = tid; h < nhalf; h += NT) {
                 const uint2 w = __ldg(reinterpret_cast<const uint2*>(cx.codes) + h);
+                if (staged) {
+                    reinterpret_cast<uint2*>(sm.sseq)[h] = w;
+                    sm.sseq[SSEQ_CW + h] = cx.nmask[h];
+                }
                 nv += count_half<K>(cx.codes, cx.nmask, h, w.x, w.y, [&](uint32_t kmer) { atomicAdd(&sm.hist[kmer], 1); });
+            }
+            if (staged) {  // slack chunk behind the sequence (window reads run one word past the end)
+                if (tid < 4) sm.sseq[nhalf * 2 + tid] = 0u;
+                if (tid < 2) sm.sseq[SSEQ_CW + nhalf + tid] = 0xFFFFFFFFu;
             }
             nv = warp_sum(nv);
             if (lane == 0 && nv) atomicAdd(&sm.nvalid, nv);
         }
         __syncthreads();
         const int base_total = F * p.pseudocount + sm.nvalid;
+        if (staged) { cx.codes = sm.sseq; cx.nmask = sm.sseq + SSEQ_CW; }  // every later lookup hits shared memory
+        phase(0);
 
         if (L > 65535) {
             long_path<K, NT, OUT>(sm, p, cx, vars, out_offs, item, seq, base_total);
@@ -553,131 +629,180 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
         }
         // =================================== SHORT path ===================================
         uint32_t* priv = sm.privtmp;
-        for (int vec = tid; vec < VEC; vec += NT) {  // G private uint16 copies of the clean histogram
-            const int4 h = reinterpret_cast<const int4*>(sm.hist)[vec];
-            const uint2 pk = make_uint2((uint32_t)h.x | ((uint32_t)h.y << 16), (uint32_t)h.z | ((uint32_t)h.w << 16));
+        uint2 cleanpk[VPT];  // this thread's bins of the clean histogram, packed: restores the copies while streaming
 #pragma unroll
-            for (int c = 0; c < G; ++c) reinterpret_cast<uint2*>(priv + c * PRIVW)[vec] = pk;
+        for (int vv = 0; vv < VPT; ++vv) {
+            const int vec = tid + vv * NT;
+            cleanpk[vv] = make_uint2(0u, 0u);
+            if (VEC % NT == 0 || vec < VEC) {
+                const int4 h = reinterpret_cast<const int4*>(sm.hist)[vec];
+                cleanpk[vv] = make_uint2((uint32_t)h.x | ((uint32_t)h.y << 16), (uint32_t)h.z | ((uint32_t)h.w << 16));
+#pragma unroll
+                for (int c = 0; c < G; ++c) reinterpret_cast<uint2*>(priv + c * PRIVW)[vec] = cleanpk[vv];
+            }
         }
-        const float base_ft = (float)base_total;
-        const float base_y = 1.0f / base_ft;
+        phase(1);
 
-        for (int s0 = 0; s0 < p.S; s0 += G) {
-            const int gs = p.S - s0 < G ? p.S - s0 : G;
-            __syncthreads();  // copies restored / initialised; previous group's plan no longer read
-            // ---- plan: classify the slots of the group, output rows, default totals ----
+        for (int S0 = 0; S0 < p.S;) {
+            // ======== supergroup: up to SG slots; their Random_N removals are precomputed together ========
+            __syncthreads();  // copies initialised / restored; previous supergroup's tables no longer read
             if (wid == 0) {
-                int kc = 0;
-                if (lane < gs) {
-                    const VarDesc vd = vars[slot_var(s0 + lane)];
+                const int ns_try = p.S - S0 < SG ? p.S - S0 : SG;
+                int kc = 0, nb = 0;
+                if (lane < ns_try) {
+                    const VarDesc vd = vars[slot_var(S0 + lane)];
                     if (vd.kind == KIND_RANDOM_N) kc = (L == 0 || vd.n_bp <= 0) ? 0 : (vd.n_bp <= 32 ? 1 : 3);
                     else if (vd.kind == KIND_EXPLICIT) kc = 3;
                     else if (vd.kind != KIND_CLEAN) kc = L > 0 ? 2 : 0;
-                    sm.gkind[lane] = kc;
+                    nb = kc == 1 ? vd.n_bp : 0;
+                }
+                int inc = nb;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                const bool fits = inc * K <= REM_CAP && inc <= ENT_CAP;
+                const unsigned fm = __ballot_sync(0xffffffffu, fits);
+                int nfit = fm == 0xffffffffu ? 32 : __ffs(~fm) - 1;
+                int nsg = ns_try < nfit ? ns_try : nfit;
+                if (nsg < ns_try) nsg = (nsg / G) * G;   // a whole number of groups (one group always fits)
+                if (lane < nsg) {
+                    sm.pre_kind[lane] = kc; sm.pre_off[lane] = inc - nb; sm.pre_nbp[lane] = nb; sm.remcnt[lane] = 0;
                     sm.dtot[lane] = 0;
-                    sm.gy[lane] = make_float2(base_ft, base_y);
-                    sm.grow[lane] = (long long)ESZ * (out_offs[s0 + lane] + item * p.out_stride);
+                    sm.grow[lane] = (long long)ESZ * (out_offs[S0 + lane] + item * p.out_stride);
                 }
-                const unsigned mb = __ballot_sync(0xffffffffu, kc == 2), mo = __ballot_sync(0xffffffffu, kc == 3);
-                if (lane == 0) { sm.gmask[0] = (int)mb; sm.gmask[1] = (int)mo; }
+                const unsigned mb = __ballot_sync(0xffffffffu, lane < nsg && kc == 2);
+                const unsigned mo = __ballot_sync(0xffffffffu, lane < nsg && kc == 3);
+                if (lane == 0) { sm.sg_n = nsg; sm.mask_bern = mb; sm.mask_other = mo; }
             }
             __syncthreads();
-            const unsigned bern_mask = (unsigned)sm.gmask[0], other_mask = (unsigned)sm.gmask[1];
+            const int NSg = sm.sg_n;
+            // ---- (p1) draws of every small Random_N slot: thread <-> (slot, philox call) ----
+            for (int q = tid; q < NSg * 8; q += NT) {
+                const int c = q >> 3, j = q & 7;
+                const int nb = sm.pre_nbp[c];
+                if (4 * j < nb) {
+                    const U4 r = random_n_words(p.seed, cx.seq_id, (uint32_t)vars[slot_var(S0 + c)].rng_id, (uint32_t)j);
+                    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+                    uint32_t* dst = sm.list + sm.pre_off[c] + 4 * j;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) if (4 * j + t < nb) dst[t] = random_n_entry(w[t], L);
+                }
+            }
+            __syncthreads();
+            // ---- (p2) removed windows of every draw: warp <-> slot, lane <-> draw; draw i owns
+            // ---- rem[(off+i)*K .. +K), unused entries hold 0xFFFF ----
+            for (int q = tid; q < NSg * 32; q += NT) {
+                const int c = q >> 5, i = q & 31;
+                const int nb = sm.pre_nbp[c];
+                int cnt = 0;
+                if (i < nb) {
+                    const int off = sm.pre_off[c];
+                    uint16_t* dst = sm.rem + (off + i) * K;
+                    random_n_removals<K>(cx.codes, cx.nmask, L, sm.list + off, nb, i, [&](uint32_t kmer) { dst[cnt++] = (uint16_t)kmer; });
+                    for (int r = cnt; r < K; ++r) dst[r] = 0xFFFFu;
+                }
+                cnt = warp_sum(cnt);
+                if (i == 0) sm.remcnt[c] = cnt;
+            }
+            __syncthreads();
+            if (wid == 0 && lane < NSg) {  // totals of the slots whose deltas are known now
+                const int d = -sm.remcnt[lane];
+                if (sm.pre_kind[lane] == 1) sm.dtot[lane] = d;
+                const float ft2 = (float)(base_total + (sm.pre_kind[lane] == 1 ? d : 0));
+                sm.gy[lane] = make_float2(ft2, 1.0f / ft2);
+            }
+            // (visible to the streamers after the barrier that follows the first patch phase)
+            phase(2);
 
-            // ---- (a1) CTA-wide slots (Bernoulli jointly, explicit, big Random_N) ----
-            if (bern_mask | other_mask) {
-                prep_cta_slots<K, NT>(sm, p, cx, vars, s0, item, seq, bern_mask, other_mask);
-                if (tid < gs && sm.gkind[tid] >= 2) {
-                    const float ft2 = (float)(base_total + sm.dtot[tid]);
-                    sm.gy[tid] = make_float2(ft2, 1.0f / ft2);
+            // ---- half-groups of HG slots, two sets of private copies: the removals of the NEXT
+            // ---- half-group are subtracted (fire-and-forget shared atomics) while the current one streams
+            constexpr int HG = G / 2 > 0 ? G / 2 : 1;
+            constexpr int TPH = NT / HG;
+            const unsigned cta_mask = sm.mask_bern | sm.mask_other;
+            auto patch_half = [&](int h0, int hs, int set) {
+                const int c = tid / TPH;
+                if (c < hs && sm.pre_kind[h0 + c] == 1) {
+                    const int n = sm.pre_nbp[h0 + c] * K;
+                    const uint16_t* rl = sm.rem + sm.pre_off[h0 + c] * K;
+                    uint32_t* privc = priv + (set * HG + c) * PRIVW;
+                    for (int r = tid - c * TPH; r < n; r += TPH) {
+                        const uint32_t km = rl[r];
+                        if (km != 0xFFFFu) upd16(privc, km, -1);
+                    }
                 }
-            }
-            // ---- (a2) warp-level slots: warp c patches copy c (Random_N, n_bp <= 32), concurrently ----
-            int nrec = 0;
-            const bool my_warp_slot = wid < gs && sm.gkind[wid] == 1;
-            if (my_warp_slot) {
-                const VarDesc vd = vars[slot_var(s0 + wid)];
-                const int n_bp = vd.n_bp;
-                uint32_t* privc = priv + wid * PRIVW;
-                const U4 r = random_n_words(p.seed, cx.seq_id, (uint32_t)vd.rng_id, (uint32_t)(lane >> 2));
-                const uint32_t wsel = (lane & 3) == 0 ? r.x : (lane & 3) == 1 ? r.y : (lane & 3) == 2 ? r.z : r.w;
-                const uint32_t e = lane < n_bp ? random_n_entry(wsel, L) : 0xFFFFFFFFu;
-                int rank = 0;
-                for (int j = 0; j < n_bp; ++j) {
-                    const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
-                    rank += (ej < e || (ej == e && j < lane)) ? 1 : 0;
+            };
+            auto prep_half = [&](int h0, int hs, int set) {  // CTA-wide slots of a half-group (contains barriers)
+                const unsigned bm = (sm.mask_bern >> h0) & ((1u << HG) - 1u), om = (sm.mask_other >> h0) & ((1u << HG) - 1u);
+                prep_cta_slots<K, NT>(sm, p, cx, vars, S0 + h0, item, seq, bm, om, sm.dtot + h0, set * HG, pclk);
+                if (tid < hs && sm.pre_kind[h0 + tid] >= 2) {
+                    const float ft2 = (float)(base_total + sm.dtot[h0 + tid]);
+                    sm.gy[h0 + tid] = make_float2(ft2, 1.0f / ft2);
                 }
-                if (lane < n_bp) sm.wlist[wid][rank] = e;
-                __syncwarp();
-                int d = 0;
-                if (lane < n_bp)
-                    d = apply_entry<K>(cx.codes, cx.nmask, L, sm.wlist[wid], n_bp, lane, [&](uint32_t kmer, int dd) {
-                        upd16(privc, kmer, dd);   // Random_N only removes windows (dd == -1)
-                        sm.wdelta[wid][lane * K + nrec] = (uint16_t)kmer;
-                        ++nrec;
-                    });
-                d = warp_sum(d);
-                if (lane == 0) {
-                    const float ft2 = (float)(base_total + d);
-                    sm.gy[wid] = make_float2(ft2, 1.0f / ft2);
-                    sm.dtot[wid] = d;
-                }
-            }
+                phase(3);
+            };
+            const int nh = (NSg + HG - 1) / HG;
+            if ((cta_mask & ((1u << HG) - 1u)) != 0u) { __syncthreads(); prep_half(0, NSg < HG ? NSg : HG, 0); }
+            patch_half(0, NSg < HG ? NSg : HG, 0);
             __syncthreads();
-            // ---- (b) stream the gs profiles ----
-            // scaler statistics of this thread's bins: live only during the streaming phase
-            float mean[VPT][4], scale[VPT][4], rscale[VPT][4];
-#pragma unroll
-            for (int vv = 0; vv < VPT; ++vv) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { mean[vv][e] = 0.f; scale[vv][e] = 1.f; rscale[vv][e] = 1.f; }
-                const int vec = tid + vv * NT;
-                if (OUT == IDL_OUT_STD_F32 && vec < VEC) {
-                    const float4 m = __ldg(reinterpret_cast<const float4*>(p.mean) + vec);
-                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale) + vec);
-                    const float4 rs = __ldg(reinterpret_cast<const float4*>(p.rscale) + vec);
-                    mean[vv][0] = m.x; mean[vv][1] = m.y; mean[vv][2] = m.z; mean[vv][3] = m.w;
-                    scale[vv][0] = sc.x; scale[vv][1] = sc.y; scale[vv][2] = sc.z; scale[vv][3] = sc.w;
-                    rscale[vv][0] = rs.x; rscale[vv][1] = rs.y; rscale[vv][2] = rs.z; rscale[vv][3] = rs.w;
-                }
-            }
-#pragma unroll 1
-            for (int c = 0; c < gs; ++c) {
-                const float2 fy = sm.gy[c];
-                unsigned char* row = reinterpret_cast<unsigned char*>(p.out) + sm.grow[c];
-                const uint2* src = reinterpret_cast<const uint2*>(priv + c * PRIVW);
+            phase(4);
+            for (int h = 0; h < nh; ++h) {
+                const int cur = h & 1, h0 = h * HG;
+                const int hs = NSg - h0 < HG ? NSg - h0 : HG;
+                const bool has_next = h + 1 < nh;
+                const int hs_next = has_next ? (NSg - h0 - HG < HG ? NSg - h0 - HG : HG) : 0;
+                const bool next_cta = has_next && ((cta_mask >> (h0 + HG)) & ((1u << HG) - 1u)) != 0u;
+                if (has_next && !next_cta) patch_half(h0 + HG, hs_next, cur ^ 1);
+                // ---- stream the hs profiles of this half-group (and restore its copies) ----
+                // scaler statistics of this thread's bins: live only during the streaming phase
+                float mean[VPT][4], scale[VPT][4], rscale[VPT][4];
 #pragma unroll
                 for (int vv = 0; vv < VPT; ++vv) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { mean[vv][e] = 0.f; scale[vv][e] = 1.f; rscale[vv][e] = 1.f; }
                     const int vec = tid + vv * NT;
-                    if (VEC % NT != 0 && vec >= VEC) break;
-                    const uint2 pk = src[vec];
-                    int ci[4] = {0, 0, 0, 0};
-                    float cf[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (NEED_F) cvt4_u16(pk, magic, cf);
-                    else {
-                        ci[0] = (int)(pk.x & 0xFFFFu) + p.pseudocount; ci[1] = (int)(pk.x >> 16) + p.pseudocount;
-                        ci[2] = (int)(pk.y & 0xFFFFu) + p.pseudocount; ci[3] = (int)(pk.y >> 16) + p.pseudocount;
+                    if (OUT == IDL_OUT_STD_F32 && vec < VEC) {
+                        const float4 m = __ldg(reinterpret_cast<const float4*>(p.mean) + vec);
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale) + vec);
+                        const float4 rs = __ldg(reinterpret_cast<const float4*>(p.rscale) + vec);
+                        mean[vv][0] = m.x; mean[vv][1] = m.y; mean[vv][2] = m.z; mean[vv][3] = m.w;
+                        scale[vv][0] = sc.x; scale[vv][1] = sc.y; scale[vv][2] = sc.z; scale[vv][3] = sc.w;
+                        rscale[vv][0] = rs.x; rscale[vv][1] = rs.y; rscale[vv][2] = rs.z; rscale[vv][3] = rs.w;
                     }
-                    emit_granule<OUT>(row, vec, ci, cf, NEED_F ? 0 : base_total + sm.dtot[c], fy.x, fy.y, false, p.accumulate,
-                                      mean[vv], scale[vv], rscale[vv]);
+                }
+#pragma unroll 1
+                for (int c = 0; c < hs; ++c) {
+                    const float2 fy = sm.gy[h0 + c];
+                    unsigned char* row = reinterpret_cast<unsigned char*>(p.out) + sm.grow[h0 + c];
+                    uint2* src = reinterpret_cast<uint2*>(priv + (cur * HG + c) * PRIVW);
+#pragma unroll
+                    for (int vv = 0; vv < VPT; ++vv) {
+                        const int vec = tid + vv * NT;
+                        if (VEC % NT != 0 && vec >= VEC) break;
+                        const uint2 pk = src[vec];
+                        src[vec] = cleanpk[vv];  // the copy is clean again for its next user
+                        int ci[4] = {0, 0, 0, 0};
+                        float cf[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (NEED_F) cvt4_u16(pk, magic, cf);
+                        else {
+                            ci[0] = (int)(pk.x & 0xFFFFu) + p.pseudocount; ci[1] = (int)(pk.x >> 16) + p.pseudocount;
+                            ci[2] = (int)(pk.y & 0xFFFFu) + p.pseudocount; ci[3] = (int)(pk.y >> 16) + p.pseudocount;
+                        }
+                        emit_granule<OUT>(row, vec, ci, cf, NEED_F ? 0 : base_total + sm.dtot[h0 + c], fy.x, fy.y, false,
+                                          p.accumulate, mean[vv], scale[vv], rscale[vv]);
+                    }
+                }
+                __syncthreads();
+                phase(5);
+                if (next_cta) {
+                    prep_half(h0 + HG, hs_next, cur ^ 1);
+                    patch_half(h0 + HG, hs_next, cur ^ 1);
+                    __syncthreads();
+                    phase(4);
                 }
             }
-            __syncthreads();
-            // ---- (c) restore the copies ----
-            if (my_warp_slot) {
-                uint32_t* privc = priv + wid * PRIVW;
-                for (int i = 0; i < nrec; ++i) upd16(privc, (uint32_t)sm.wdelta[wid][lane * K + i], +1);
-            }
-            unsigned rest = bern_mask | other_mask;
-            while (rest) {
-                const int c = __ffs(rest) - 1;
-                rest &= rest - 1;
-                for (int vec = tid; vec < VEC; vec += NT) {
-                    const int4 h = reinterpret_cast<const int4*>(sm.hist)[vec];
-                    reinterpret_cast<uint2*>(priv + c * PRIVW)[vec] = make_uint2((uint32_t)h.x | ((uint32_t)h.y << 16), (uint32_t)h.z | ((uint32_t)h.w << 16));
-                }
-            }
-            // the barrier at the top of the next group / item orders these writes
+            S0 += NSg;
         }
     }
 }
@@ -787,7 +912,8 @@ constexpr int MAX_TABS = 64;
 constexpr size_t WS_OUTOFF = WS_VARS + sizeof(VarDesc) * MAX_VARIANTS;
 constexpr size_t WS_GTAB = WS_OUTOFF + sizeof(int64_t) * MAX_VARIANTS;
 constexpr size_t WS_RSCALE = WS_GTAB + sizeof(uint32_t) * RNG_BLOCK * MAX_TABS;
-constexpr size_t WS_TOTAL = WS_RSCALE + sizeof(float) * 4096;
+constexpr size_t WS_PROF = WS_RSCALE + sizeof(float) * 4096;
+constexpr size_t WS_TOTAL = WS_PROF + 8 * 16;
 
 template <int K, int NT, int OUT>
 static int launch_profiles(const ProfParams& p, cudaStream_t st) {
@@ -905,7 +1031,7 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
             d.tab2 = table_of(iv.p2); d.slope2 = gap_slope(iv.p2);
         }
         if (d.tab1 < 0 || d.tab2 < 0) return set_error(IDL_EUNSUPPORTED, "idl_profiles: too many distinct mutation rates%s", "");
-        if (iv.kind == IDL_KIND_RANDOM_N && (iv.n_bp < 0 || iv.n_bp > LIST_CAP / 2)) return set_error(IDL_EUNSUPPORTED, "idl_profiles: Random_N n_bp must be <= 2048%s", "");
+        if (iv.kind == IDL_KIND_RANDOM_N && (iv.n_bp < 0 || iv.n_bp > LIST_CAP / 2)) return set_error(IDL_EUNSUPPORTED, "idl_profiles: Random_N n_bp must be <= 1024%s", "");
         if (iv.kind == IDL_KIND_EXPLICIT && (!d_edit_off || !d_edits)) return set_error(IDL_EINVAL, "idl_profiles: explicit variant without edit lists%s", "");
     }
     unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
@@ -932,6 +1058,8 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
         IDL_CUDA_CHECK(cudaGetLastError());
     }
     p.work_counter = reinterpret_cast<unsigned long long*>(ws);
+    static const bool want_prof = getenv("IDL_PHASE_PROF") != nullptr;
+    p.phase_prof = want_prof ? reinterpret_cast<unsigned long long*>(ws + WS_PROF) : nullptr;
     switch (k) {
         case 1: return dispatch_out<1, 64>(p, out_kind, st);
         case 2: return dispatch_out<2, 64>(p, out_kind, st);

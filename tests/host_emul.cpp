@@ -73,7 +73,37 @@ static int apply_k(const uint32_t* codes, const uint32_t* nmask, int L, const st
     return d;
 }
 
+template <int K>
+static int randn_k(const uint32_t* codes, const uint32_t* nmask, int L, const std::vector<uint32_t>& ent, int* counts) {
+    int d = 0;
+    for (int i = 0; i < (int)ent.size(); ++i)
+        random_n_removals<K>(codes, nmask, L, ent.data(), (int)ent.size(), i, [&](uint32_t kmer) { counts[kmer] -= 1; --d; });
+    return d;
+}
+
 extern "C" {
+
+// Random_N through the kernels' specialised path (unsorted draws -> removed windows)
+int emul_random_n(const uint32_t* codes, const uint32_t* nmask, int L, int K, unsigned long long seed, unsigned seq_id,
+                  unsigned rng_id, int n_bp, int* counts) {
+    std::vector<uint32_t> ent;
+    if (L > 0)
+        for (int call = 0; call * 4 < n_bp; ++call) {
+            const U4 r = random_n_words(seed, seq_id, rng_id, (uint32_t)call);
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+            for (int t = 0; t < 4; ++t)
+                if (call * 4 + t < n_bp) ent.push_back(random_n_entry(w[t], L));
+        }
+    switch (K) {
+        case 1: return randn_k<1>(codes, nmask, L, ent, counts);
+        case 2: return randn_k<2>(codes, nmask, L, ent, counts);
+        case 3: return randn_k<3>(codes, nmask, L, ent, counts);
+        case 4: return randn_k<4>(codes, nmask, L, ent, counts);
+        case 5: return randn_k<5>(codes, nmask, L, ent, counts);
+        case 6: return randn_k<6>(codes, nmask, L, ent, counts);
+    }
+    return 0;
+}
 
 // build the variant's edit list exactly like the kernel and patch `counts` (clean histogram)
 // in place; returns the change of the counted-window total.  n_list_out / list_out optional.
@@ -115,6 +145,29 @@ int emul_variant(const uint32_t* codes, const uint32_t* nmask, int L, int K, uns
         case 6: return apply_k<6>(codes, nmask, L, list, counts);
     }
     return 0;
+}
+
+// fast block generator vs the generic one: returns number of blocks where they disagree
+// (blocks where the fast path reports overflow are counted in *n_overflow and skipped)
+int emul_fast_vs_slow(const uint32_t* codes, const uint32_t* nmask, int L, unsigned long long seed, unsigned seq_id,
+                      unsigned rng_id, int kind, double p1, double p2, int* n_overflow) {
+    uint32_t T1[RNG_BLOCK], T2[RNG_BLOCK];
+    geometric_table(p1, T1);
+    geometric_table(p2, T2);
+    int bad = 0;
+    *n_overflow = 0;
+    const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
+    for (int b = 0; b < nblocks; ++b) {
+        std::vector<uint32_t> slow;
+        block_edits(kind, seed, seq_id, rng_id, b, L, codes, nmask, T1, gap_slope(p1), T2, gap_slope(p2),
+                    [&](uint32_t e) { slow.push_back(e); });
+        const FastBlock f = fast_block(kind, seed, seq_id, rng_id, b, L, nmask, T1, gap_slope(p1), T2, gap_slope(p2));
+        if (!f.ok) { ++*n_overflow; continue; }
+        uint32_t out[2 * FAST_CAP];
+        fast_block_write(f, b, codes, out);
+        if (f.cnt != (int)slow.size() || !std::equal(slow.begin(), slow.end(), out)) ++bad;
+    }
+    return bad;
 }
 
 void emul_geometric_table(double p, uint32_t* out) { geometric_table(p, out); }

@@ -204,3 +204,45 @@ def test_div_rn_is_ieee_division(emul):
     a = (rng.standard_normal(n) * 10.0 ** rng.integers(-8, 3, size=n)).astype(np.float32)
     b = (rng.random(n) * 10.0 ** rng.integers(-7, 1, size=n) + 1e-9).astype(np.float32)
     assert emul.emul_div_check(_ptr(a), _ptr(b), ctypes.c_longlong(n)) == 0
+
+
+@pytest.mark.parametrize("k", [1, 3, 4, 6])
+def test_random_n_specialised_path(emul, k):
+    """the unsorted-draw removal rule (random_n_removals) == mutate-and-recount, including
+    duplicate draws, draws within k of each other, draws next to existing Ns and sequence ends"""
+    rng = np.random.default_rng(50 + k)
+    for L, n_rate, n_bp in [(40, 0.0, 20), (7, 0.0, 20), (300, 0.05, 20), (1409, 0.0, 20), (100, 0.3, 32), (64, 0.0, 3), (1, 0.0, 5)]:
+        for rep in range(4):
+            s = rand_seq(rng, L, n_rate)
+            codes, nmask, _ = pack(emul, s)
+            got, nv = counts(emul, codes, nmask, L, k)
+            d = emul.emul_random_n(_ptr(codes), _ptr(nmask), L, k, ctypes.c_ulonglong(99), 5 + rep, 3, n_bp, _ptr(got))
+            edits = orc.rng_variant_edits(99, 5 + rep, 3, orc.KIND_RANDOM_N, orc.codes_of_seq(s), L, n_bp=n_bp)
+            mut = bytearray(s)
+            for pos, val in edits:
+                mut[pos] = ord("N")
+            want = np.zeros(4 ** k, np.int32)
+            orc.kmer_counts(mut, k, want)
+            assert np.array_equal(got, want), (L, n_rate, n_bp, rep)
+            assert nv + d == want.sum()
+
+
+def test_fast_block_generator_equals_generic(emul):
+    """the register-only fast generator (<= 6 hits per stream and block) emits exactly the
+    edits of the generic merged generator; overflow is reported, never silently wrong"""
+    rng = np.random.default_rng(77)
+    total_over = 0
+    for L, n_rate, p1, p2 in [(10000, 0.0, 1e-2, 0.5e-2), (2000, 0.01, 1e-2, 0.5e-2), (1409, 0.05, 0.05, 0.03),
+                              (700, 0.1, 0.12, 0.1), (130, 0.0, 0.5, 0.5), (63, 0.3, 0.2, 0.2)]:
+        s = rand_seq(rng, L, n_rate)
+        codes, nmask, _ = pack(emul, s)
+        for kind in (orc.KIND_BOTH, orc.KIND_TRANSITION, orc.KIND_TRANSVERSION):
+            for seq_id in range(6):
+                nov = ctypes.c_int(0)
+                bad = emul.emul_fast_vs_slow(_ptr(codes), _ptr(nmask), L, ctypes.c_ulonglong(4242), seq_id, kind, kind,
+                                             ctypes.c_double(p1), ctypes.c_double(p2), ctypes.byref(nov))
+                assert bad == 0, (L, p1, kind, seq_id)
+                total_over += nov.value
+                if p1 <= 0.01:
+                    assert nov.value == 0
+    assert total_over > 0  # the high-rate cases do exercise the overflow report
