@@ -1,0 +1,321 @@
+"""Featurisation front-end with the reference's names and signatures (idelucs/utils.py).
+
+``kmersFasta`` / ``AugmentFasta`` / ``create_dataloader`` / ``SequenceDataset`` parse the
+FASTA file ONCE, keep the sequences packed on the GPU and produce profiles with the sm_100a
+kernels (featurise.py -> C ABI).  Mutations ("mimics") come from the counter-based device
+RNG; passing any *other* callable as ``transform`` (for instance the reference's own
+transform objects, which draw from numpy's global MT19937 stream) is honoured exactly by
+running it on the host bytes, diffing, and feeding the edits to the device as explicit edit
+lists — that path reproduces the reference bit for bit.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import featurise as ft
+from .seqset import SeqSet, read_fasta_raw
+
+_A, _C, _G, _T, _N = (ord(c) for c in "ACGTN")
+# check_sequence's alphabet (idelucs/utils.py:42-46) as one 256-entry table: canonical byte,
+# 0 = deleted whitespace, 255 = left as is (invalid unless already ACGTN)
+_CANON = np.arange(256, dtype=np.uint8)
+for _src, _dst in ((b"acgtuU", b"ACGTTT"), (b"swkmyrbdhvnSWKMYRBDHV-", b"N" * 22)):
+    for _s, _d in zip(_src, _dst):
+        _CANON[_s] = _d
+
+
+def check_sequence(header, seq):
+    """idelucs/utils.py:26-51: header checks, alphabet normalisation, ValueError on an invalid
+    byte.  Host helper kept for API compatibility (the device packer applies the same mapping)."""
+    if len(header) > 0 and (header[0] in (">", "#") or header[0].isspace()):
+        raise ValueError("Bad character in sequence header")
+    if "\t" in header:
+        raise ValueError("tab included in header")
+    a = np.frombuffer(bytes(seq), dtype=np.uint8)
+    a = a[~np.isin(a, np.frombuffer(b" \t\n\r", dtype=np.uint8))]
+    a = _CANON[a]
+    bad = ~np.isin(a, np.frombuffer(b"ACGTN", dtype=np.uint8))
+    if bad.any():
+        raise ValueError("Invalid DNA byte in sequence {}: '{}'".format(header, chr(int(a[np.argmax(bad)]))))
+    return bytearray(a.tobytes())
+
+
+# ---- transform descriptors (idelucs/utils.py:54-135) ---------------------------------------
+class _DeviceTransform(object):
+    """Marker base: kmersFasta maps these to device RNG variants instead of calling them."""
+    kind = ft.KIND_CLEAN
+    p1 = p2 = 0.0
+    n_bp = 0
+
+    def spec(self, rng_id):
+        return ft.VariantSpec(self.kind, p1=self.p1, p2=self.p2, n_bp=self.n_bp, rng_id=rng_id)
+
+
+class transition(_DeviceTransform):
+    """A<->G, C<->T with probability ``threshold`` per base (idelucs/utils.py:54-76)."""
+    kind = ft.KIND_TRANSITION
+
+    def __init__(self, threshold):
+        self.threshold = self.p1 = threshold
+
+    def __call__(self, seq):  # host compatibility path, numpy global RNG like the reference
+        x = np.random.random(len(seq))
+        for i in np.where(x < self.threshold)[0]:
+            seq[i] = {_A: _G, _G: _A, _T: _C, _C: _T}.get(seq[i], seq[i])
+
+
+class transversion(_DeviceTransform):
+    """purine <-> random pyrimidine with probability ``threshold`` (idelucs/utils.py:98-118)."""
+    kind = ft.KIND_TRANSVERSION
+
+    def __init__(self, threshold):
+        self.threshold = self.p2 = threshold
+
+    def __call__(self, seq):
+        import random
+        x = np.random.random(len(seq))
+        table = {_A: (_T, _C), _G: (_T, _C), _T: (_A, _G), _C: (_A, _G)}
+        for i in np.where(x < self.threshold)[0]:
+            seq[i] = random.choice(table.get(seq[i], (_N,)))
+
+
+class transition_transversion(_DeviceTransform):
+    """transition(threshold_1) then transversion(threshold_2) (idelucs/utils.py:120-135)."""
+    kind = ft.KIND_BOTH
+
+    def __init__(self, threshold_1, threshold_2):
+        self.tf1, self.tf2 = transition(threshold_1), transversion(threshold_2)
+        self.p1, self.p2 = threshold_1, threshold_2
+
+    def __call__(self, seq):
+        self.tf1(seq)
+        self.tf2(seq)
+
+
+class Random_N(_DeviceTransform):
+    """``n_bp`` uniformly drawn positions (with replacement) become N (idelucs/utils.py:78-95)."""
+    kind = ft.KIND_RANDOM_N
+
+    def __init__(self, n_bp):
+        self.n_bp = n_bp
+
+    def __call__(self, seq):
+        for i in np.random.randint(0, len(seq), self.n_bp):
+            seq[i] = _N
+
+
+# ---- seeds ------------------------------------------------------------------------------------
+def _draw_seed():
+    """Device RNG seed drawn from numpy's global stream, so ``np.random.seed(s)`` (which the
+    reference does at import, models.py:18-21) makes a run reproducible here too."""
+    return int(np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(np.random.randint(0, 2 ** 31 - 1))
+
+
+_seqset_cache = {}
+
+
+def load_seqset(fname, device=None):
+    """Parse + pack a FASTA file once per (path, mtime, device)."""
+    device = torch.device(device if device is not None else "cuda")
+    key = (os.path.abspath(fname), os.path.getmtime(fname), str(device))
+    ss = _seqset_cache.get(key)
+    if ss is None:
+        ss = SeqSet.from_fasta(fname, device=device)
+        ss._host_seqs = None
+        _seqset_cache.clear()
+        _seqset_cache[key] = ss
+    return ss
+
+
+def _explicit_lists_from_callable(fname, ss, transform):
+    """Run an arbitrary host transform on every record (file order, like kmersFasta does) and
+    return its effect as device edit lists."""
+    names, seqs = read_fasta_raw(fname)
+    lut = np.full(256, 4, np.int64)
+    for i, ch in enumerate(b"ACGT"):
+        lut[ch] = i
+    lists = []
+    for name, raw in zip(names, seqs):
+        before = check_sequence(name, raw)
+        after = bytearray(before)
+        transform(after)
+        if len(after) != len(before):
+            raise ValueError("transform changed the sequence length")
+        b, a = np.frombuffer(bytes(before), np.uint8), np.frombuffer(bytes(after), np.uint8)
+        pos = np.nonzero(a != b)[0]
+        lists.append((pos, lut[a[pos]]))
+    return ft.pack_edit_lists([lists], ss.n, ss.device)
+
+
+def kmersFasta(fname, k=6, transform=None, reduce=False):
+    """idelucs/utils.py:224-277 -> (names, float64[N, 4^k]) with the +1 pseudocount."""
+    if reduce:
+        raise NotImplementedError("reduce=True (canonical k-mer folding) is outside the round-1 hot path")
+    ss = load_seqset(fname)
+    if transform is None:
+        variants, lists, seed = [ft.VariantSpec(ft.KIND_CLEAN)], None, 0
+    elif isinstance(transform, _DeviceTransform):
+        variants, lists, seed = [transform.spec(0)], None, _draw_seed()
+    else:
+        variants, lists, seed = [ft.VariantSpec(ft.KIND_EXPLICIT, explicit_idx=0)], _explicit_lists_from_callable(fname, ss, transform), 0
+    out = ft.profiles(ss, k, variants, out_kind=ft.OUT_FREQ_F64, seed=seed, edit_lists=lists)
+    return list(ss.names), out[0].cpu().numpy()
+
+
+def augment_device(ss, n_mimics, k=6, seed=None, group=None, seq_id0=0):
+    """Device-resident AugmentFasta: returns (profiles float32 [n_mimics+1, N, 4^k] — slot 0 =
+    t_norm, slot j = mimic j — standardised with the t_norm statistics, and the Scaler)."""
+    seed = _draw_seed() if seed is None else seed
+    variants = ft.mimic_schedule(n_mimics)
+    t_norm = ft.profiles(ss, k, variants[:1], out_kind=ft.OUT_FREQ_F32, seed=seed, seq_id0=seq_id0)[0]
+    sc = ft.Scaler.fit(t_norm, group=group)
+    del t_norm
+    out = ft.profiles(ss, k, variants, out_kind=ft.OUT_STD_F32, seed=seed, mean=sc.mean32, scale=sc.scale32, seq_id0=seq_id0)
+    return out, sc, seed
+
+
+def AugmentFasta(sequence_file, n_mimics, k=6, reduce=False):
+    """idelucs/utils.py:321-368 -> float32 numpy [n_pairs, 2, 4^k], mimic-major, column 0 =
+    standardised t_norm, column 1 = standardised mimic (n_pairs = max(n_mimics, 2) * N)."""
+    if reduce:
+        raise NotImplementedError("reduce=True is outside the round-1 hot path")
+    ss = load_seqset(sequence_file)
+    prof, _, _ = augment_device(ss, n_mimics, k=k)
+    V, n, F = prof.shape
+    x = torch.empty((V - 1, n, 2, F), dtype=torch.float32, device=prof.device)
+    x[:, :, 0, :] = prof[0].unsqueeze(0)
+    x[:, :, 1, :] = prof[1:]
+    return x.reshape((V - 1) * n, 2, F).cpu().numpy()
+
+
+class AugmentedDataset(torch.utils.data.Dataset):
+    """idelucs/utils.py:370-389."""
+
+    def __init__(self, data):
+        self.data = data
+
+    def __len__(self):
+        return self.data.shape[0]
+
+    def __getitem__(self, idx):
+        if torch.is_tensor(idx):
+            idx = idx.tolist()
+        return {"true": self.data[idx, 0, :], "modified": self.data[idx, 1, :]}
+
+
+class PairBatchLoader(object):
+    """Replaces DataLoader(AugmentedDataset, shuffle=True, num_workers=4) (utils.py:422-429):
+    yields ``{'true': [B,F], 'modified': [B,F]}`` float32 CUDA tensors.  Pairs are
+    (sequence i, mimic j); the pair set is fixed for the whole run like the reference's
+    (same seed => same mimic).  When the standardised profiles fit ``materialize_bytes`` they
+    are produced once and batches are gathers; otherwise every batch is regenerated from the
+    packed sequences by the mimic kernel (selection mode), which gives identical values."""
+
+    def __init__(self, ss, n_mimics, k=6, batch_size=512, seed=None, materialize_bytes=8 << 30, group=None,
+                 seq_id0=0, drop_last=False):
+        self.ss, self.k, self.batch_size, self.drop_last = ss, k, batch_size, drop_last
+        self.variants = ft.mimic_schedule(n_mimics)
+        self.n_pairs = (len(self.variants) - 1) * ss.n
+        self.seed = _draw_seed() if seed is None else seed
+        self.seq_id0 = seq_id0
+        F = 4 ** k
+        if len(self.variants) * ss.n * F * 4 <= materialize_bytes:
+            self.profiles, self.scaler, _ = augment_device(ss, n_mimics, k, seed=self.seed, group=group, seq_id0=seq_id0)
+        else:
+            t_norm = ft.profiles(ss, k, self.variants[:1], out_kind=ft.OUT_FREQ_F32, seed=self.seed, seq_id0=seq_id0)[0]
+            self.scaler = ft.Scaler.fit(t_norm, group=group)
+            del t_norm
+            self.profiles = None
+
+    def __len__(self):
+        return self.n_pairs // self.batch_size if self.drop_last else (self.n_pairs + self.batch_size - 1) // self.batch_size
+
+    def batch(self, pair_ids):
+        """pair id = (mimic-1) * N + sequence  (the reference's mimic-major row order)"""
+        n = self.ss.n
+        mim = torch.div(pair_ids, n, rounding_mode="floor") + 1
+        sidx = pair_ids - (mim - 1) * n
+        if self.profiles is not None:
+            return {"true": self.profiles[0][sidx], "modified": self.profiles[mim, sidx]}
+        sel = torch.stack([torch.zeros_like(mim), mim], dim=1).to(torch.int32).contiguous()
+        out = ft.profiles(self.ss, self.k, self.variants, out_kind=ft.OUT_STD_F32, seed=self.seed, sidx=sidx.to(torch.int32),
+                          sel=sel, mean=self.scaler.mean32, scale=self.scaler.scale32, seq_id0=self.seq_id0)
+        return {"true": out[0], "modified": out[1]}
+
+    def __iter__(self):
+        perm = torch.randperm(self.n_pairs, device=self.ss.device)
+        for b in range(len(self)):
+            yield self.batch(perm[b * self.batch_size:(b + 1) * self.batch_size])
+
+
+def create_dataloader(sequence_file, n_mimics, k=6, batch_size=512, GT_file=None, reduce=False):
+    """idelucs/utils.py:422-429 -> iterable of {'true','modified'} batches (shuffled every epoch)."""
+    if reduce:
+        raise NotImplementedError("reduce=True is outside the round-1 hot path")
+    return PairBatchLoader(load_seqset(sequence_file), n_mimics, k=k, batch_size=batch_size)
+
+
+def SummaryFasta(fname, GT_file=None):
+    """idelucs/utils.py:137-188 -> (names, lengths, ground_truth, cluster_dis)."""
+    ss = load_seqset(fname)
+    ground_truth = cluster_dis = None
+    if GT_file:
+        import pandas as pd
+        df = pd.read_csv(GT_file, sep="\t")
+        gt = dict(zip(df.sequence_id, df.cluster_id))
+        cluster_dis = df["cluster_id"].value_counts().to_dict()
+        for name in ss.names:
+            if name not in gt:
+                raise ValueError("Check GT for sequence {}".format(name))
+        ground_truth = [gt[name] for name in ss.names]
+    return list(ss.names), [int(x) for x in ss.lengths], ground_truth, cluster_dis
+
+
+class SequenceDataset(torch.utils.data.Dataset):
+    """idelucs/utils.py:391-420: clean float64 profiles + their own StandardScaler.  ``kmers``
+    is a float64 numpy array like the reference's; ``kmers32`` is the float32 CUDA tensor the
+    trainer feeds to the network (models.py:163 casts to float32)."""
+
+    def __init__(self, fasta_file, k=6, transform=None, GT_file=None, reduce=False, group=None):
+        if reduce:
+            raise NotImplementedError("reduce=True is outside the round-1 hot path")
+        self.names, self.lengths, self.GT, self.cluster_dis = SummaryFasta(fasta_file, GT_file)
+        ss = load_seqset(fasta_file)
+        if transform is None:
+            f64 = ft.profiles(ss, k, [ft.VariantSpec(ft.KIND_CLEAN)], out_kind=ft.OUT_FREQ_F64)[0]
+        else:
+            f64 = torch.from_numpy(kmersFasta(fasta_file, k, transform)[1]).to(ss.device)
+        sc = ft.Scaler.fit(f64, group=group)
+        self._k64 = sc.transform64(f64)
+        self.kmers32 = sc.transform64(f64, want32=True)
+        self._kmers = None
+
+    @property
+    def kmers(self):
+        if self._kmers is None:
+            self._kmers = self._k64.cpu().numpy()
+        return self._kmers
+
+    def __len__(self):
+        return len(self.lengths)
+
+    def __getitem__(self, idx):
+        if torch.is_tensor(idx):
+            idx = idx.tolist()
+        sample = {"kmer": self.kmers[idx, :], "name": self.names[idx]}
+        if self.GT:
+            sample["cluster_id"] = self.GT[idx]
+        return sample
+
+
+def cluster_acc(y_true, y_pred):
+    """Hungarian-matched clustering accuracy (idelucs/utils.py:489-508) -> (assignment, acc)."""
+    from scipy.optimize import linear_sum_assignment
+    y_true = np.asarray(y_true).astype(np.int64)
+    y_pred = np.asarray(y_pred).astype(np.int64)
+    D = int(max(y_pred.max(), y_true.max())) + 1
+    w = np.zeros((D, D), dtype=np.int64)
+    np.add.at(w, (y_pred, y_true), 1)
+    rows, cols = linear_sum_assignment(w.max() - w)
+    return np.stack([rows, cols], axis=1), float(w[rows, cols].sum()) / y_pred.size

@@ -505,3 +505,29 @@ def rng_mimic_counts(seqs, k, seed, kinds, seq_id0=0, p1=1e-2, p2=0.5e-2, n_bp=2
                 mut[pos] = int(ASCII_OF_CODE[val])
             kmer_counts(mut, k, out[v, i])
     return out
+
+
+def colstats_partials(X, rows_per_part=2048):
+    """Checker restatement of the scaler partials the CUDA path exchanges between ranks:
+    per block of rows the (count, mean, M2) of every column."""
+    parts, ns = [], []
+    for lo in range(0, X.shape[0], rows_per_part):
+        blk = X[lo:lo + rows_per_part].astype(np.float64)
+        m = blk.mean(axis=0)
+        parts.append(np.stack([m, ((blk - m) ** 2).sum(axis=0)]))
+        ns.append(float(blk.shape[0]))
+    return np.stack(parts), np.asarray(ns)
+
+
+def merge_partials(parts, ns):
+    """Chan et al. pairwise merge in index order -> (mean, population variance)."""
+    na, ma, M2 = 0.0, np.zeros(parts.shape[2]), np.zeros(parts.shape[2])
+    for (mb, Mb), nb in zip(parts, ns):
+        if nb <= 0:
+            continue
+        nt = na + nb
+        delta = mb - ma
+        ma = ma + delta * (nb / nt)
+        M2 = M2 + Mb + delta * delta * (na * nb / nt)
+        na = nt
+    return ma, M2 / na

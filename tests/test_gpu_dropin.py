@@ -1,0 +1,126 @@
+"""GPU tests of the drop-in Python surface (same names / signatures as the reference's
+idelucs.kmers, idelucs.utils, idelucs.LossFunctions, idelucs.models, idelucs.cluster)."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import idelucs_oracle as orc
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _golden(golden_dir):
+    with open(os.path.join(golden_dir, "golden.json")) as fh:
+        return json.load(fh)
+
+
+def test_kmer_counts_signature():
+    from idelucs_b200 import kmer_counts
+    c = np.zeros(16, np.int32)
+    assert kmer_counts(bytearray(b"ACGTNACGTACGTTTT"), 2, c) is None
+    assert c.tolist() == [0, 3, 0, 0, 0, 0, 3, 0, 0, 0, 0, 3, 1, 0, 0, 3]      # SURVEY §4 KAT
+    kmer_counts(bytearray(b"ACGTNACGTACGTTTT"), 2, c)                           # accumulates
+    assert c.tolist() == [0, 6, 0, 0, 0, 0, 6, 0, 0, 0, 0, 6, 2, 0, 0, 6]
+    c = np.zeros(4, np.int32)
+    kmer_counts(bytearray(b"ANCG"), 1, c)
+    assert c.tolist() == [1, 1, 1, 0]
+    with pytest.raises(BufferError):
+        kmer_counts(b"ACGT", 2, np.zeros(16, np.int32))                        # read-only buffer, like the memoryview
+    with pytest.raises(ValueError):
+        kmer_counts(bytearray(b"ACGT"), 2, np.zeros(16, np.int64))
+
+
+@pytest.mark.parametrize("k", [4, 6])
+def test_kmersFasta_matches_reference(golden_dir, fasta_files, k):
+    from idelucs_b200.utils import kmersFasta
+    g = _golden(golden_dir)["files"]["Influenza-A"][f"k{k}"]
+    names, x = kmersFasta(fasta_files["Influenza-A"], k=k)
+    assert x.dtype == np.float64 and x.shape == (949, 4 ** k)
+    assert sha(x) == g["freq64_sha256"]
+    assert hashlib.sha256("\n".join(names).encode()).hexdigest() == g["names_sha256"]
+
+
+def test_kmersFasta_with_reference_style_transform(fasta_files):
+    """any host callable (here the oracle's restatement of the reference transform, numpy global
+    RNG) is honoured exactly through the explicit-edit-list path"""
+    from idelucs_b200.utils import kmersFasta
+    np.random.seed(11)
+    random.seed(11)
+    _, want = orc.kmersFasta(fasta_files["Actinopterygii"], k=5, transform=orc.transition_transversion(1e-2, 0.5e-2))
+    np.random.seed(11)
+    random.seed(11)
+    _, got = kmersFasta(fasta_files["Actinopterygii"], k=5, transform=orc.transition_transversion(1e-2, 0.5e-2))
+    assert np.array_equal(got, want)
+
+
+def test_AugmentFasta_shape_and_statistics(fasta_files):
+    from idelucs_b200.utils import AugmentFasta
+    np.random.seed(0)
+    x = AugmentFasta(fasta_files["Influenza-A"], 4, k=5)
+    assert x.shape == (4 * 949, 2, 1024) and x.dtype == np.float32
+    # t_norm column is standardised with its own statistics: zero mean, unit variance per feature
+    t = x[:949, 0, :].astype(np.float64)
+    assert np.abs(t.mean(axis=0)).max() < 1e-4
+    sd = t.std(axis=0)
+    assert np.abs(sd[sd > 0.5] - 1).max() < 1e-3
+    assert np.array_equal(x[:949, 0], x[949:1898, 0])                       # 'true' column repeated per mimic
+    np.random.seed(0)
+    assert np.array_equal(AugmentFasta(fasta_files["Influenza-A"], 4, k=5), x)   # reproducible under np.random.seed
+
+
+def test_pair_loader_matches_materialised(fasta_files):
+    from idelucs_b200.utils import PairBatchLoader, load_seqset
+    ss = load_seqset(fasta_files["Actinopterygii"])
+    a = PairBatchLoader(ss, 5, k=6, batch_size=64, seed=123)
+    b = PairBatchLoader(ss, 5, k=6, batch_size=64, seed=123, materialize_bytes=0)   # regenerate every batch
+    assert a.profiles is not None and b.profiles is None and len(a) == (5 * 113 + 63) // 64
+    ids = torch.randperm(a.n_pairs, device=ss.device)[:64]
+    ba, bb = a.batch(ids), b.batch(ids)
+    assert torch.equal(ba["true"], bb["true"]) and torch.equal(ba["modified"], bb["modified"])
+    seen = sum(batch["true"].shape[0] for batch in a)
+    assert seen == a.n_pairs
+
+
+def test_sequence_dataset_matches_reference(golden_dir, fasta_files):
+    from idelucs_b200.utils import SequenceDataset
+    ds = SequenceDataset(fasta_files["Actinopterygii"], k=6, GT_file=os.path.join(golden_dir, "Actinopterygii_GT.tsv"))
+    rows = np.load(os.path.join(golden_dir, "Actinopterygii_inference_rows_k6.npz"))
+    np.testing.assert_allclose(ds.kmers[rows["rows"]], rows["x"], rtol=1e-9, atol=1e-9)
+    assert len(ds) == 113 and ds[0]["name"] == ds.names[0] and "cluster_id" in ds[0]
+
+
+def test_training_recovers_clusters(golden_dir, fasta_files):
+    """end to end through the reference-shaped trainer: Actinopterygii (113 mitogenomes, 3
+    classes): the reference reaches ACC 0.92-1.0 single-voter; a short run must
+    land in the same regime."""
+    from idelucs_b200 import models
+    from idelucs_b200.utils import SummaryFasta, cluster_acc
+    torch.manual_seed(0)
+    np.random.seed(0)
+    gt = os.path.join(golden_dir, "Actinopterygii_GT.tsv")
+    args = dict(sequence_file=fasta_files["Actinopterygii"], GT_file=gt, n_clusters=3, k=6, n_mimics=3, batch_sz=256,
+                optimizer="RMSprop", weight=0.25, lr=1e-3, model_size="linear", scheduler="None", n_epochs=35, n_voters=1)
+    args["lambda"] = 2.8
+    best = 0.0
+    for seed in range(3):
+        torch.manual_seed(seed)
+        model = models.IID_model(args)
+        model.build_dataloader()
+        losses = [model.contrastive_training_epoch() for _ in range(35)]
+        assert np.isfinite(losses).all()
+        y_pred, probs, latent = model.predict()
+        assert y_pred.shape == (113,) and latent.shape == (113, 64) and probs.shape == (113,)
+        names, lengths, GT, dis = SummaryFasta(args["sequence_file"], gt)
+        labels = {c: i for i, c in enumerate(sorted(set(GT)))}
+        _, acc = cluster_acc(np.array([labels[c] for c in GT]), y_pred)
+        best = max(best, acc)
+    assert best >= 0.85, best
