@@ -93,7 +93,7 @@ def cpu_reference(n_seq_per_core, cores):
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -103,7 +103,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -322,8 +322,8 @@ def main():
     ap.add_argument("--n_seqs", type=int, default=100000, help="sequences per GPU (BASELINE configs[2]: 100000)")
     ap.add_argument("--seed", type=int, default=20240607)
     ap.add_argument("--e2e_seqs", type=int, default=2048, help="sequences per end-to-end step (host buffers)")
-    ap.add_argument("--cpu_seqs_per_core", type=int, default=1024)
-    ap.add_argument("--ref_seqs_per_core", type=int, default=512)
+    ap.add_argument("--cpu_seqs_per_core", type=int, default=4096)
+    ap.add_argument("--ref_seqs_per_core", type=int, default=1024)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--kernel_timing", action="store_true", help="time the dominant kernel inside the timed loop (adds syncs)")
     args = ap.parse_args()

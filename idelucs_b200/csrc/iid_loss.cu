@@ -74,6 +74,9 @@ __global__ void __launch_bounds__(LNT) iid_loss_kernel(const LossParams p) {
     const int I0 = I * LT, J0 = J * LT;
     const int gi = I0 + ti, gj = J0 + tj;
     const bool valid = gi < C && gj < C;
+    // (i,j) and (j,i) are written together by ONE thread (in a diagonal tile both orientations
+    // exist: only the upper triangle writes), so the outputs are exactly symmetric and race free
+    const bool writer = valid && (I != J || ti <= tj);
     const float wgt = (I == J) ? 1.f : 2.f;
 
     // ---- phase 1: S tile and its transpose ------------------------------------------------
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(LNT) iid_loss_kernel(const LossParams p) {
             if (I0 + tid < C) p.corr[J * LMAXC + I0 + tid] = rs;
             if (I != J && J0 + tid < C) p.corr[I * LMAXC + J0 + tid] = cs;
         }
-        if (p.joint && valid) {                                // compute_joint's return value
+        if (p.joint && writer) {                               // compute_joint's return value
             p.joint[(size_t)gi * C + gj] = P;
             p.joint[(size_t)gj * C + gi] = P;
         }
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(LNT) iid_loss_kernel(const LossParams p) {
     }
     gp = block_sum(gp, sRed);
     for (int q = 0; q < p.npairs; ++q) gp += p.partAP[q];      // <A, P>
-    if (valid) {
+    if (writer) {
         const float G = Aij + sVec[0][gi] + sVec[0][gj];
         const float d = (G - gp) / T;                          // dL/dSsym; dS = (dSsym + dSsym^T)/2 = dSsym (symmetric)
         p.dS[(size_t)gi * C + gj] = d;
