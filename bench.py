@@ -265,6 +265,41 @@ def run_ours(args):
                "sequences_per_step": ne, "api": "SeqSet.from_ascii(pinned host bytes) -> idl_pack/idl_profiles/idl_colstats/"
                "idl_scaler_finalize -> pinned host float32 [51, n, 4096]"}
 
+    # ---- secondary metric: training pairs/s (BASELINE configs[3]: 1 M x 2 kb sharded, B=512 per rank) ----
+    train = None
+    if args.train_steps > 0:
+        del out
+        torch.cuda.empty_cache()
+        from idelucs_b200.train import ShardedTrainer
+        nt, Lt = args.train_seqs // world, 2000
+        gt = torch.Generator(device=dev).manual_seed(99 + rank)
+        a = torch.randint(0, 4, (nt * Lt,), device=dev, generator=gt, dtype=torch.uint8)
+        a.mul_(2).add_(65).add_((a >= 69).to(torch.uint8) * 2).add_((a >= 73).to(torch.uint8) * 11)
+        st = SeqSet.from_ascii(a, np.arange(nt + 1, dtype=np.int64) * Lt, device=dev)
+        st._d_ascii = None
+        del a
+        tr = ShardedTrainer(st, k=K, n_clusters=5, n_mimics=N_MIMICS, batch_sz=512, seed=7, seq_id0=rank * nt, world=world)
+        for _ in range(10):
+            tr.step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ta, tb = ev(), ev()
+        ta.record()
+        for _ in range(args.train_steps):
+            loss = tr.step()
+        tb.record()
+        torch.cuda.synchronize()
+        tms = ta.elapsed_time(tb)
+        if world > 1:
+            t = torch.tensor([tms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tms = float(t.item())
+        train = {"pairs_per_s": world * 512 * args.train_steps / (tms * 1e-3), "ms_per_step": tms / args.train_steps,
+                 "steps": args.train_steps, "final_loss": float(loss.item()),
+                 "config": "synthetic %d sequences x 2000 bp sharded over %d GPU(s), k=6, n_mimics=50, batch_sz=512 per rank, "
+                           "n_clusters=5, RMSprop, (1-w) InfoNCE + w IIC (BASELINE.json configs[3]); batches regenerated on the "
+                           "fly by the mimic kernel; MLP / InfoNCE in PyTorch fp32" % (nt * world, world)}
     if rank != 0:
         return
     cpu = None
@@ -283,7 +318,7 @@ def run_ours(args):
                        "profiles_per_step": world * n * V, "output": "float32 [51, N, 4096] standardised, %.1f GB per GPU per step"
                                    % (V * n * F * 4 / 1e9), "cache": "inputs+outputs per step exceed L2 (126 MB) by >100x, no flush needed",
                        "mutation_rates": "transition 1e-2, transversion 5e-3, Random_N 20 (idelucs/utils.py:330-349)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "train": train}
     print(json.dumps(line))
 
 
@@ -325,6 +360,8 @@ def main():
     ap.add_argument("--cpu_seqs_per_core", type=int, default=4096)
     ap.add_argument("--ref_seqs_per_core", type=int, default=1024)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--train_steps", type=int, default=200, help="steps of the secondary training-pairs/s measurement (0 = skip)")
+    ap.add_argument("--train_seqs", type=int, default=1000000, help="total sequences of the training workload (configs[3])")
     ap.add_argument("--kernel_timing", action="store_true", help="time the dominant kernel inside the timed loop (adds syncs)")
     args = ap.parse_args()
     if args.impl == "reference":

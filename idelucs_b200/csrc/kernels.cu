@@ -191,13 +191,13 @@ struct ProfSmem {
     int pre_kind[SG];                 // per slot of the supergroup: 0 none, 1 small Random_N, 2 Bernoulli, 3 other CTA-wide
     int pre_off[SG];                  // first draw of the slot in ent[] (x K = first entry in rem[])
     int pre_nbp[SG];                  // draws of the slot
-    int remcnt[SG];                   // removed windows of the slot
     int dtot[SG];                     // change of the counted-window total of the slot
     float2 gy[SG];                    // per slot: (float total, 1/total)
     long long grow[SG];               // per slot: byte offset of the output row
     int seg_off[C::G + 1];            // joint Bernoulli pass: list segment of each Bernoulli slot
     unsigned mask_bern, mask_other;   // ballot masks over the supergroup's slots
     int sg_n;                         // slots in the current supergroup
+    int sg_ent;                       // Random_N draws in the current supergroup
     int scan[NT / 32 + 2];
     int nvalid;
     long long item;
@@ -629,16 +629,29 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
         }
         // =================================== SHORT path ===================================
         uint32_t* priv = sm.privtmp;
-        uint2 cleanpk[VPT];  // this thread's bins of the clean histogram, packed: restores the copies while streaming
+        // pack the clean histogram to uint16: G private copies + one pristine copy that overwrites
+        // (the first half of) the int32 histogram in place and restores the copies while streaming
+        uint2* clean16 = reinterpret_cast<uint2*>(sm.hist);
+        {
+            uint2 pk[VPT];
 #pragma unroll
-        for (int vv = 0; vv < VPT; ++vv) {
-            const int vec = tid + vv * NT;
-            cleanpk[vv] = make_uint2(0u, 0u);
-            if (VEC % NT == 0 || vec < VEC) {
-                const int4 h = reinterpret_cast<const int4*>(sm.hist)[vec];
-                cleanpk[vv] = make_uint2((uint32_t)h.x | ((uint32_t)h.y << 16), (uint32_t)h.z | ((uint32_t)h.w << 16));
+            for (int vv = 0; vv < VPT; ++vv) {
+                const int vec = tid + vv * NT;
+                pk[vv] = make_uint2(0u, 0u);
+                if (VEC % NT == 0 || vec < VEC) {
+                    const int4 h = reinterpret_cast<const int4*>(sm.hist)[vec];
+                    pk[vv] = make_uint2((uint32_t)h.x | ((uint32_t)h.y << 16), (uint32_t)h.z | ((uint32_t)h.w << 16));
+                }
+            }
+            __syncthreads();  // every int32 bin has been read before the region is overwritten
 #pragma unroll
-                for (int c = 0; c < G; ++c) reinterpret_cast<uint2*>(priv + c * PRIVW)[vec] = cleanpk[vv];
+            for (int vv = 0; vv < VPT; ++vv) {
+                const int vec = tid + vv * NT;
+                if (VEC % NT == 0 || vec < VEC) {
+                    clean16[vec] = pk[vv];
+#pragma unroll
+                    for (int c = 0; c < G; ++c) reinterpret_cast<uint2*>(priv + c * PRIVW)[vec] = pk[vv];
+                }
             }
         }
         phase(1);
@@ -668,17 +681,20 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
                 int nsg = ns_try < nfit ? ns_try : nfit;
                 if (nsg < ns_try) nsg = (nsg / G) * G;   // a whole number of groups (one group always fits)
                 if (lane < nsg) {
-                    sm.pre_kind[lane] = kc; sm.pre_off[lane] = inc - nb; sm.pre_nbp[lane] = nb; sm.remcnt[lane] = 0;
+                    sm.pre_kind[lane] = kc; sm.pre_off[lane] = inc - nb; sm.pre_nbp[lane] = nb;
                     sm.dtot[lane] = 0;
                     sm.grow[lane] = (long long)ESZ * (out_offs[S0 + lane] + item * p.out_stride);
                 }
                 const unsigned mb = __ballot_sync(0xffffffffu, lane < nsg && kc == 2);
                 const unsigned mo = __ballot_sync(0xffffffffu, lane < nsg && kc == 3);
-                if (lane == 0) { sm.sg_n = nsg; sm.mask_bern = mb; sm.mask_other = mo; }
+                const int ent_total = __shfl_sync(0xffffffffu, inc, nsg > 0 ? nsg - 1 : 0);
+                if (lane == 0) { sm.sg_n = nsg; sm.sg_ent = nsg > 0 ? ent_total : 0; sm.mask_bern = mb; sm.mask_other = mo; }
             }
             __syncthreads();
             const int NSg = sm.sg_n;
-            // ---- (p1) draws of every small Random_N slot: thread <-> (slot, philox call) ----
+            phase(12);
+            // ---- (p1) draws of every small Random_N slot: thread <-> (slot, philox call).  The slot id
+            // ---- rides in bits 27..31 of the entry (positions are < 2^16 on this path) ----
             for (int q = tid; q < NSg * 8; q += NT) {
                 const int c = q >> 3, j = q & 7;
                 const int nb = sm.pre_nbp[c];
@@ -687,31 +703,72 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
                     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
                     uint32_t* dst = sm.list + sm.pre_off[c] + 4 * j;
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) if (4 * j + t < nb) dst[t] = random_n_entry(w[t], L);
+                    for (int t = 0; t < 4; ++t) if (4 * j + t < nb) dst[t] = random_n_entry(w[t], L) | ((uint32_t)c << 27);
                 }
             }
             __syncthreads();
-            // ---- (p2) removed windows of every draw: warp <-> slot, lane <-> draw; draw i owns
-            // ---- rem[(off+i)*K .. +K), unused entries hold 0xFFFF ----
-            for (int q = tid; q < NSg * 32; q += NT) {
-                const int c = q >> 5, i = q & 31;
-                const int nb = sm.pre_nbp[c];
-                int cnt = 0;
-                if (i < nb) {
-                    const int off = sm.pre_off[c];
-                    uint16_t* dst = sm.rem + (off + i) * K;
-                    random_n_removals<K>(cx.codes, cx.nmask, L, sm.list + off, nb, i, [&](uint32_t kmer) { dst[cnt++] = (uint16_t)kmer; });
+            phase(13);
+            // ---- (p2) removed windows of every draw: thread <-> draw (dense over all slots); draw q
+            // ---- owns rem[q*K .. +K), unused entries hold 0xFFFF (random_n_removals' rule, core.cuh) ----
+            {
+                constexpr uint32_t KMASK = (1u << (2 * K)) - 1u, NMASKK = (1u << K) - 1u;
+                const int n_ent = sm.sg_ent;
+                for (int q = tid; q < n_ent; q += NT) {
+                    const uint32_t me = sm.list[q];
+                    const int c = (int)(me >> 27);
+                    const int nb = sm.pre_nbp[c], off = sm.pre_off[c], i = q - off;
+                    const uint32_t pme = me >> 3;            // position | slot bits: comparable within the slot
+                    uint32_t pnx = 0xFFFFFFFFu;
+                    bool dup = false;
+                    const uint32_t* e = sm.list + off;
+                    int j = 0;
+                    if ((off & 3) == 0) {
+                        for (; j + 4 <= nb; j += 4) {
+                            const uint4 v = *reinterpret_cast<const uint4*>(e + j);
+                            const uint32_t pv[4] = {v.x >> 3, v.y >> 3, v.z >> 3, v.w >> 3};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                dup = dup || (pv[t] == pme && j + t < i);
+                                if (pv[t] > pme && pv[t] < pnx) pnx = pv[t];
+                            }
+                        }
+                    }
+                    for (; j < nb; ++j) {
+                        const uint32_t pj = e[j] >> 3;
+                        dup = dup || (pj == pme && j < i);
+                        if (pj > pme && pj < pnx) pnx = pj;
+                    }
+                    uint16_t* dst = sm.rem + q * K;
+                    int cnt = 0;
+                    if (!dup) {
+                        const int pos = (int)(pme & 0xFFFFFFu);
+                        int e_hi = pos + K - 1;
+                        if (pnx != 0xFFFFFFFFu && (int)(pnx & 0xFFFFFFu) - 1 < e_hi) e_hi = (int)(pnx & 0xFFFFFFu) - 1;
+                        if (L - 1 < e_hi) e_hi = L - 1;
+                        const Window<K> cw = load_window<K>(cx.codes, cx.nmask, pos - (K - 1));
+                        for (int ee = pos; ee <= e_hi; ++ee) {
+                            const int sh = K - 1 - (ee - pos);
+                            if (((cw.nbits >> sh) & NMASKK) == 0u) dst[cnt++] = (uint16_t)((cw.bases >> (2 * sh)) & KMASK);
+                        }
+                    }
                     for (int r = cnt; r < K; ++r) dst[r] = 0xFFFFu;
                 }
-                cnt = warp_sum(cnt);
-                if (i == 0) sm.remcnt[c] = cnt;
             }
             __syncthreads();
-            if (wid == 0 && lane < NSg) {  // totals of the slots whose deltas are known now
-                const int d = -sm.remcnt[lane];
-                if (sm.pre_kind[lane] == 1) sm.dtot[lane] = d;
-                const float ft2 = (float)(base_total + (sm.pre_kind[lane] == 1 ? d : 0));
-                sm.gy[lane] = make_float2(ft2, 1.0f / ft2);
+            phase(14);
+            for (int c = wid; c < NSg; c += NT / 32) {  // totals of the slots whose deltas are known now: warp <-> slot
+                int d = 0;
+                if (sm.pre_kind[c] == 1) {
+                    const uint16_t* rl = sm.rem + sm.pre_off[c] * K;
+                    const int n = sm.pre_nbp[c] * K;
+                    for (int r = lane; r < n; r += 32) d -= rl[r] != 0xFFFFu ? 1 : 0;
+                    d = warp_sum(d);
+                }
+                if (lane == 0) {
+                    if (sm.pre_kind[c] == 1) sm.dtot[c] = d;
+                    const float ft2 = (float)(base_total + d);
+                    sm.gy[c] = make_float2(ft2, 1.0f / ft2);
+                }
             }
             // (visible to the streamers after the barrier that follows the first patch phase)
             phase(2);
@@ -755,33 +812,28 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
                 const bool next_cta = has_next && ((cta_mask >> (h0 + HG)) & ((1u << HG) - 1u)) != 0u;
                 if (has_next && !next_cta) patch_half(h0 + HG, hs_next, cur ^ 1);
                 // ---- stream the hs profiles of this half-group (and restore its copies) ----
-                // scaler statistics of this thread's bins: live only during the streaming phase
-                float mean[VPT][4], scale[VPT][4], rscale[VPT][4];
+                // granule-major: the scaler statistics of ONE granule (12 registers) are live at a time
 #pragma unroll
                 for (int vv = 0; vv < VPT; ++vv) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { mean[vv][e] = 0.f; scale[vv][e] = 1.f; rscale[vv][e] = 1.f; }
                     const int vec = tid + vv * NT;
-                    if (OUT == IDL_OUT_STD_F32 && vec < VEC) {
+                    if (VEC % NT != 0 && vec >= VEC) break;
+                    float mean[4] = {0.f, 0.f, 0.f, 0.f}, scale[4] = {1.f, 1.f, 1.f, 1.f}, rscale[4] = {1.f, 1.f, 1.f, 1.f};
+                    if (OUT == IDL_OUT_STD_F32) {
                         const float4 m = __ldg(reinterpret_cast<const float4*>(p.mean) + vec);
                         const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale) + vec);
                         const float4 rs = __ldg(reinterpret_cast<const float4*>(p.rscale) + vec);
-                        mean[vv][0] = m.x; mean[vv][1] = m.y; mean[vv][2] = m.z; mean[vv][3] = m.w;
-                        scale[vv][0] = sc.x; scale[vv][1] = sc.y; scale[vv][2] = sc.z; scale[vv][3] = sc.w;
-                        rscale[vv][0] = rs.x; rscale[vv][1] = rs.y; rscale[vv][2] = rs.z; rscale[vv][3] = rs.w;
+                        mean[0] = m.x; mean[1] = m.y; mean[2] = m.z; mean[3] = m.w;
+                        scale[0] = sc.x; scale[1] = sc.y; scale[2] = sc.z; scale[3] = sc.w;
+                        rscale[0] = rs.x; rscale[1] = rs.y; rscale[2] = rs.z; rscale[3] = rs.w;
                     }
-                }
-#pragma unroll 1
-                for (int c = 0; c < hs; ++c) {
-                    const float2 fy = sm.gy[h0 + c];
-                    unsigned char* row = reinterpret_cast<unsigned char*>(p.out) + sm.grow[h0 + c];
-                    uint2* src = reinterpret_cast<uint2*>(priv + (cur * HG + c) * PRIVW);
-#pragma unroll
-                    for (int vv = 0; vv < VPT; ++vv) {
-                        const int vec = tid + vv * NT;
-                        if (VEC % NT != 0 && vec >= VEC) break;
+                    const uint2 clean = clean16[vec];
+#pragma unroll 2
+                    for (int c = 0; c < hs; ++c) {
+                        const float2 fy = sm.gy[h0 + c];
+                        unsigned char* row = reinterpret_cast<unsigned char*>(p.out) + sm.grow[h0 + c];
+                        uint2* src = reinterpret_cast<uint2*>(priv + (cur * HG + c) * PRIVW);
                         const uint2 pk = src[vec];
-                        src[vec] = cleanpk[vv];  // the copy is clean again for its next user
+                        src[vec] = clean;  // the copy is clean again for its next user
                         int ci[4] = {0, 0, 0, 0};
                         float cf[4] = {0.f, 0.f, 0.f, 0.f};
                         if (NEED_F) cvt4_u16(pk, magic, cf);
@@ -790,7 +842,7 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
                             ci[2] = (int)(pk.y & 0xFFFFu) + p.pseudocount; ci[3] = (int)(pk.y >> 16) + p.pseudocount;
                         }
                         emit_granule<OUT>(row, vec, ci, cf, NEED_F ? 0 : base_total + sm.dtot[h0 + c], fy.x, fy.y, false,
-                                          p.accumulate, mean[vv], scale[vv], rscale[vv]);
+                                          p.accumulate, mean, scale, rscale);
                     }
                 }
                 __syncthreads();
@@ -913,7 +965,7 @@ constexpr size_t WS_OUTOFF = WS_VARS + sizeof(VarDesc) * MAX_VARIANTS;
 constexpr size_t WS_GTAB = WS_OUTOFF + sizeof(int64_t) * MAX_VARIANTS;
 constexpr size_t WS_RSCALE = WS_GTAB + sizeof(uint32_t) * RNG_BLOCK * MAX_TABS;
 constexpr size_t WS_PROF = WS_RSCALE + sizeof(float) * 4096;
-constexpr size_t WS_TOTAL = WS_PROF + 8 * 16;
+constexpr size_t WS_TOTAL = WS_PROF + 8 * 16;  // 16 phase counters
 
 template <int K, int NT, int OUT>
 static int launch_profiles(const ProfParams& p, cudaStream_t st) {
