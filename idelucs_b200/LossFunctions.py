@@ -64,17 +64,13 @@ def compute_joint(x_out, x_tf_out):
 
 
 def info_nce_loss(z1, z2, temperature):
-    """SimCLR NT-Xent (idelucs/LossFunctions.py:65-98), PyTorch ops; written for the device
-    the inputs live on (the reference builds its masks on the CPU and moves them)."""
+    """SimCLR NT-Xent (idelucs/LossFunctions.py:65-98).  The reference gathers [positive,
+    negatives] per row with boolean masks and takes cross-entropy against label 0; that equals
+    the cross-entropy of the self-masked similarity row against the index of the other view,
+    which needs no mask gathers (and no host synchronisation)."""
     n = z1.shape[0]
     feats = F.normalize(torch.cat((z1, z2), 0).float(), dim=1)
-    sim = feats @ feats.T
-    idx = torch.arange(2 * n, device=sim.device)
-    pos = sim[idx, (idx + n) % (2 * n)].unsqueeze(1)                   # the other view of the same sample
-    neg_mask = torch.ones_like(sim, dtype=torch.bool)
-    neg_mask[idx, idx] = False
-    neg_mask[idx, (idx + n) % (2 * n)] = False
-    neg = sim[neg_mask].view(2 * n, -1)
-    logits = torch.cat([pos, neg], dim=1) / temperature
-    labels = torch.zeros(2 * n, dtype=torch.long, device=sim.device)
-    return F.cross_entropy(logits, labels)
+    logits = (feats @ feats.T) / temperature
+    idx = torch.arange(2 * n, device=logits.device)
+    logits = logits.masked_fill(idx.unsqueeze(0) == idx.unsqueeze(1), float("-inf"))
+    return F.cross_entropy(logits, (idx + n) % (2 * n))

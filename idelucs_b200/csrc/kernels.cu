@@ -68,6 +68,7 @@ struct ProfParams {
     int32_t* status;
     unsigned long long* work_counter;
     unsigned long long* phase_prof;   // optional: cycles per kernel phase summed over CTAs (thread 0), IDL_PHASE_PROF=1
+    int only_deferred;                // generic kernel: redo only the items the producer/consumer kernel flagged (status bit 1)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -580,7 +581,16 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
     auto phase = [&](int id) { pclk.tick(id); };
     for (;;) {
         __syncthreads();  // previous item fully done (also protects sm.item)
-        if (tid == 0) sm.item = (long long)atomicAdd(p.work_counter, 1ull);
+        if (tid == 0) {
+            long long it;
+            if (!p.only_deferred) it = (long long)atomicAdd(p.work_counter, 1ull);
+            else if (p.work_counter[1] == 0ull) it = p.n_items;   // nothing was deferred
+            else {
+                do { it = (long long)atomicAdd(p.work_counter + 2, 1ull); } while (it < p.n_items && !(p.status[it] & 2));
+                if (it < p.n_items) atomicAnd(p.status + it, ~2);
+            }
+            sm.item = it;
+        }
         __syncthreads();
         const long long item = sm.item;
         if (item >= p.n_items) break;
@@ -859,6 +869,10 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
     }
 }
 
+}  // namespace idl
+#include "profiles_pc.cuh"
+namespace idl {
+
 // ---------------------------------------------------------------------------------------
 // K4: column statistics / scaler / standardise
 // ---------------------------------------------------------------------------------------
@@ -1087,14 +1101,27 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
         if (iv.kind == IDL_KIND_EXPLICIT && (!d_edit_off || !d_edits)) return set_error(IDL_EINVAL, "idl_profiles: explicit variant without edit lists%s", "");
     }
     unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
-    IDL_CUDA_CHECK(cudaMemsetAsync(ws, 0, 8, st));
-    IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_VARS, h_vars, sizeof(VarDesc) * n_variants, cudaMemcpyHostToDevice, st));
-    IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_OUTOFF, out_off, sizeof(int64_t) * S, cudaMemcpyHostToDevice, st));
-    if (n_tabs) IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_GTAB, h_gtab, sizeof(uint32_t) * RNG_BLOCK * n_tabs, cudaMemcpyHostToDevice, st));
-    // the staging arrays are thread_local statics reused by the next call: make sure the
-    // async copies have read them before returning (pageable memcpy is staged synchronously
-    // by the runtime with respect to the host buffer, so no stream sync is required)
-
+    IDL_CUDA_CHECK(cudaMemsetAsync(ws, 0, 24, st));   // work counter, deferred-item counter, deferred scan cursor
+    // descriptor upload, skipped when this workspace already holds exactly these descriptors
+    // (repeated calls of a training loop then enqueue no host->device copies at all)
+    struct PlanCache { void* ws; int n_variants, S, n_tabs; VarDesc vars[SVARS]; int64_t out_off[SVARS]; double tab_p[MAX_TABS]; };
+    static thread_local PlanCache cache = {nullptr, 0, 0, 0, {}, {}, {}};
+    bool same = cache.ws == d_workspace && cache.n_variants == n_variants && cache.S == S && cache.n_tabs == n_tabs &&
+                n_variants <= SVARS && S <= SVARS;
+    if (same) same = memcmp(cache.vars, h_vars, sizeof(VarDesc) * n_variants) == 0 && memcmp(cache.out_off, out_off, sizeof(int64_t) * S) == 0 &&
+                     memcmp(cache.tab_p, tab_p, sizeof(double) * n_tabs) == 0;
+    if (!same) {
+        IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_VARS, h_vars, sizeof(VarDesc) * n_variants, cudaMemcpyHostToDevice, st));
+        IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_OUTOFF, out_off, sizeof(int64_t) * S, cudaMemcpyHostToDevice, st));
+        if (n_tabs) IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_GTAB, h_gtab, sizeof(uint32_t) * RNG_BLOCK * n_tabs, cudaMemcpyHostToDevice, st));
+        cache.ws = nullptr;
+        if (n_variants <= SVARS && S <= SVARS) {
+            cache.ws = d_workspace; cache.n_variants = n_variants; cache.S = S; cache.n_tabs = n_tabs;
+            memcpy(cache.vars, h_vars, sizeof(VarDesc) * n_variants);
+            memcpy(cache.out_off, out_off, sizeof(int64_t) * S);
+            memcpy(cache.tab_p, tab_p, sizeof(double) * n_tabs);
+        }
+    }
     ProfParams p;
     p.codes = d_codes; p.nmask = d_nmask; p.chunk_off = d_chunk_off; p.len = d_len; p.sidx = d_sidx; p.sel = d_sel;
     p.n_items = n_items; p.seq_id0 = seq_id0; p.n_seqs_total = n_seqs_total; p.S = S; p.n_vars = n_variants; p.n_tabs = n_tabs;
@@ -1112,6 +1139,34 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
     p.work_counter = reinterpret_cast<unsigned long long*>(ws);
     static const bool want_prof = getenv("IDL_PHASE_PROF") != nullptr;
     p.phase_prof = want_prof ? reinterpret_cast<unsigned long long*>(ws + WS_PROF) : nullptr;
+    p.only_deferred = 0;
+    // ---- producer/consumer kernel (k = 6, float outputs, whole-schedule featurisation) ----
+    bool pc_ok = k == 6 && (out_kind == IDL_OUT_FREQ_F32 || out_kind == IDL_OUT_STD_F32) && !d_sel && d_status &&
+                 n_variants <= PC_MAXS && n_items >= 2LL * sm_count() && getenv("IDL_NO_PC") == nullptr;
+    if (pc_ok) {
+        int n_bern = 0, n_ent = 0;
+        for (int v = 0; v < n_variants; ++v) {
+            const VarDesc& d = h_vars[v];
+            if (d.kind == IDL_KIND_EXPLICIT) pc_ok = false;
+            else if (d.kind == IDL_KIND_RANDOM_N) { if (d.n_bp > 32) pc_ok = false; else if (d.n_bp > 0) n_ent += d.n_bp; }
+            else if (d.kind != IDL_KIND_CLEAN) ++n_bern;
+        }
+        if (n_bern > PC_MAXB || n_ent > LIST_CAP || n_ent * PC_K > PC_REM) pc_ok = false;
+    }
+    if (pc_ok) {
+        auto kern = out_kind == IDL_OUT_STD_F32 ? profiles_pc_kernel<IDL_OUT_STD_F32> : profiles_pc_kernel<IDL_OUT_FREQ_F32>;
+        static bool configured[2] = {false, false};
+        const int ci = out_kind == IDL_OUT_STD_F32 ? 1 : 0;
+        if (!configured[ci]) {
+            IDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PcSmem)));
+            configured[ci] = true;
+        }
+        long long grid = sm_count();
+        if (grid > n_items) grid = n_items;
+        kern<<<(unsigned)grid, PC_NT, sizeof(PcSmem), st>>>(p);
+        IDL_CUDA_CHECK(cudaGetLastError());
+        p.only_deferred = 1;   // whatever the fast kernel could not take is redone by the generic one
+    }
     switch (k) {
         case 1: return dispatch_out<1, 64>(p, out_kind, st);
         case 2: return dispatch_out<2, 64>(p, out_kind, st);

@@ -40,6 +40,24 @@ def mimic_schedule(n_mimics):
 
 
 _workspaces = {}
+_varr_cache = {}
+
+
+def _variant_array(variants):
+    """ctypes idl_variant[] of a VariantSpec list (cached per list object)"""
+    key = id(variants)
+    hit = _varr_cache.get(key)
+    sig = tuple((v.kind, v.rng_id, v.n_bp, v.explicit_idx, v.p1, v.p2) for v in variants)
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    varr = (_lib.Variant * len(variants))()
+    for i, v in enumerate(variants):
+        varr[i].kind, varr[i].rng_id, varr[i].n_bp = v.kind, (v.rng_id if v.rng_id is not None else i), v.n_bp
+        varr[i].explicit_idx, varr[i].p1, varr[i].p2 = v.explicit_idx, v.p1, v.p2
+    if len(_varr_cache) > 64:
+        _varr_cache.clear()
+    _varr_cache[key] = (sig, varr)
+    return varr
 
 
 def _workspace(device, nbytes, tag):
@@ -95,10 +113,10 @@ def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_o
         out_off = [s * n_items * F for s in range(S)]
         out_stride = F
     assert out.dtype == _OUT_DTYPE[out_kind] and out.is_contiguous()
-    varr = (_lib.Variant * nv)()
-    for i, v in enumerate(variants):
-        varr[i].kind, varr[i].rng_id, varr[i].n_bp = v.kind, (v.rng_id if v.rng_id is not None else i), v.n_bp
-        varr[i].explicit_idx, varr[i].p1, varr[i].p2 = v.explicit_idx, v.p1, v.p2
+    varr = _variant_array(variants)
+    if status is None and sel is None and k == 6 and n_items >= 512 and out_kind in (OUT_FREQ_F32, OUT_STD_F32):
+        # lets the library use its producer/consumer kernel (items it defers are flagged here and redone)
+        status = torch.zeros(n_items, dtype=torch.int32, device=device)
     offs = (ctypes.c_int64 * S)(*[int(o) for o in out_off])
     d_eoff, d_ent = (None, None) if edit_lists is None else edit_lists
     with torch.cuda.device(device):
@@ -160,11 +178,11 @@ class Scaler(object):
 
     @classmethod
     def fit(cls, x, group=None):
-        """Statistics of x's columns; with a torch.distributed group the per-rank partials are
-        all-gathered (rank order) and merged identically on every rank."""
+        """Statistics of x's columns.  group=None: this process only.  With a torch.distributed
+        group the per-rank partials are all-gathered (rank order) and merged identically on
+        every rank (a collective: every rank of the group must call it)."""
         parts, part_n = cls.partials(x)
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                 and torch.distributed.get_world_size() > 1):
+        if group is not None:
             parts, part_n = gather_partials(parts, part_n, group)
         return cls.from_partials(parts, part_n)
 

@@ -308,3 +308,46 @@ def test_iid_loss_clamped_and_deterministic():
     l2 = IID_loss(z1, z2, lamb=2.8)
     l2.backward()
     assert l1.item() == l2.item() and torch.equal(g1, z1.grad)
+
+
+def test_pc_kernel_equals_generic(ft, SeqSet):
+    """the producer/consumer kernel (k=6, float outputs, >= 512 items) must reproduce the generic
+    kernel bit for bit, including items it defers (too long for its staging buffer) and Ns"""
+    rng = np.random.default_rng(21)
+    alph = np.frombuffer(b"ACGTACGTACGTACGTACGTACGTN", dtype=np.uint8)
+    lens = rng.integers(50, 12000, size=700)
+    lens[[5, 77, 300]] = [20481, 30000, 66000]      # deferred to the generic kernel (66000: long path)
+    lens[[9, 10]] = [0, 3]
+    seqs = [alph[rng.integers(0, alph.size, size=int(L))].tobytes() for L in lens]
+    ss = SeqSet.from_sequences(seqs)
+    variants = [ft.VariantSpec(ft.KIND_CLEAN)] + ft.mimic_schedule(20)
+    for i, v in enumerate(variants):
+        v.rng_id = i
+    sc_mean = torch.rand(4096, device="cuda") * 1e-4
+    sc_scale = torch.rand(4096, device="cuda") * 1e-5 + 1e-6
+    outs = {}
+    for mode in ("pc", "generic"):
+        if mode == "generic":
+            os.environ["IDL_NO_PC"] = "1"
+        try:
+            f = ft.profiles(ss, 6, variants, out_kind=ft.OUT_FREQ_F32, seed=99, seq_id0=7)
+            s = ft.profiles(ss, 6, variants, out_kind=ft.OUT_STD_F32, seed=99, seq_id0=7, mean=sc_mean, scale=sc_scale)
+        finally:
+            os.environ.pop("IDL_NO_PC", None)
+        outs[mode] = (f, s)
+    assert torch.equal(outs["pc"][0], outs["generic"][0])
+    assert torch.equal(outs["pc"][1], outs["generic"][1])
+    # and against the oracle on a few sequences
+    c = ft.profiles(ss, 6, variants, out_kind=ft.OUT_COUNTS_I32, seed=99, seq_id0=7).cpu().numpy()
+    idx = [0, 5, 9, 10, 123]
+    f32 = outs["pc"][0].cpu().numpy()
+    for i in idx:
+        for v, spec in enumerate(variants):
+            edits = orc.rng_variant_edits(99, 7 + i, v, spec.kind, orc.codes_of_seq(seqs[i]), len(seqs[i]), spec.p1, spec.p2, spec.n_bp)
+            mut = bytearray(seqs[i])
+            for pos, val in edits:
+                mut[pos] = b"ACGTN"[val]
+            cnt = np.zeros(4096, np.int32)
+            orc.kmer_counts(mut, 6, cnt)
+            assert np.array_equal(c[v, i], cnt), (i, v)
+            assert np.array_equal(f32[v, i], ((cnt + 1) / (cnt + 1).sum()).astype(np.float32)), (i, v)
