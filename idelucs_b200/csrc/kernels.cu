@@ -244,6 +244,48 @@ __device__ __forceinline__ void emit_granule(void* out_row, int vec, const int (
     }
 }
 
+// Blackwell packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2, sm_100+): IEEE round-to-nearest per
+// lane, so the results are bit-identical to the scalar path at half the issue slots.
+struct Stats2 {           // scaler statistics of one 4-bin granule, ready for the packed ops
+    float2 nm01, nm23;    // -mean
+    float2 ns01, ns23;    // -scale
+    float2 rs01, rs23;    // RN(1/scale)
+};
+__device__ __forceinline__ Stats2 load_stats2(const float* mean, const float* scale, const float* rscale, int vec, bool on) {
+    Stats2 s;
+    s.nm01 = s.nm23 = make_float2(0.f, 0.f);
+    s.ns01 = s.ns23 = make_float2(-1.f, -1.f);
+    s.rs01 = s.rs23 = make_float2(1.f, 1.f);
+    if (on) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + vec);
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + vec);
+        const float4 rs = __ldg(reinterpret_cast<const float4*>(rscale) + vec);
+        s.nm01 = make_float2(-m.x, -m.y); s.nm23 = make_float2(-m.z, -m.w);
+        s.ns01 = make_float2(-sc.x, -sc.y); s.ns23 = make_float2(-sc.z, -sc.w);
+        s.rs01 = make_float2(rs.x, rs.y); s.rs23 = make_float2(rs.z, rs.w);
+    }
+    return s;
+}
+// one granule: 4 packed uint16 counts -> float32(count+pc)/total [-> standardised] -> one 128-bit streaming store.
+// fy = (total, RN(1/total)); same arithmetic as div_rn (core.cuh), two lanes per instruction.
+template <bool STD>
+__device__ __forceinline__ void emit_granule_u16x2(void* out_row, int vec, uint2 pk, float magic, float2 fy, const Stats2& st) {
+    const float2 nmag = make_float2(-magic, -magic), yy = make_float2(fy.y, fy.y), nt = make_float2(-fy.x, -fy.x);
+    float2 c01 = make_float2(__uint_as_float(__byte_perm(pk.x, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(pk.x, 0x4B000000u, 0x7432)));
+    float2 c23 = make_float2(__uint_as_float(__byte_perm(pk.y, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(pk.y, 0x4B000000u, 0x7432)));
+    c01 = __fadd2_rn(c01, nmag); c23 = __fadd2_rn(c23, nmag);                    // exact count + pseudocount
+    float2 q01 = __fmul2_rn(c01, yy), q23 = __fmul2_rn(c23, yy);
+    const float2 r01 = __ffma2_rn(q01, nt, c01), r23 = __ffma2_rn(q23, nt, c23);
+    q01 = __ffma2_rn(r01, yy, q01); q23 = __ffma2_rn(r23, yy, q23);             // RN(count / total)
+    if (STD) {
+        const float2 d01 = __fadd2_rn(q01, st.nm01), d23 = __fadd2_rn(q23, st.nm23);
+        const float2 t01 = __fmul2_rn(d01, st.rs01), t23 = __fmul2_rn(d23, st.rs23);
+        const float2 e01 = __ffma2_rn(t01, st.ns01, d01), e23 = __ffma2_rn(t23, st.ns23, d23);
+        q01 = __ffma2_rn(e01, st.rs01, t01); q23 = __ffma2_rn(e23, st.rs23, t23);   // RN((q - mean) / scale)
+    }
+    __stcs(reinterpret_cast<float4*>(out_row) + vec, make_float4(q01.x, q01.y, q23.x, q23.y));
+}
+
 // ---- register-hungry, rarely executed pieces are kept out of line so that the streaming
 // ---- loop keeps its scaler statistics in registers (64-register budget at 2 CTAs/SM) ----
 struct BlockGen { int cnt; uint32_t e0, e1, e2, e3; };
@@ -827,15 +869,8 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
                 for (int vv = 0; vv < VPT; ++vv) {
                     const int vec = tid + vv * NT;
                     if (VEC % NT != 0 && vec >= VEC) break;
-                    float mean[4] = {0.f, 0.f, 0.f, 0.f}, scale[4] = {1.f, 1.f, 1.f, 1.f}, rscale[4] = {1.f, 1.f, 1.f, 1.f};
-                    if (OUT == IDL_OUT_STD_F32) {
-                        const float4 m = __ldg(reinterpret_cast<const float4*>(p.mean) + vec);
-                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale) + vec);
-                        const float4 rs = __ldg(reinterpret_cast<const float4*>(p.rscale) + vec);
-                        mean[0] = m.x; mean[1] = m.y; mean[2] = m.z; mean[3] = m.w;
-                        scale[0] = sc.x; scale[1] = sc.y; scale[2] = sc.z; scale[3] = sc.w;
-                        rscale[0] = rs.x; rscale[1] = rs.y; rscale[2] = rs.z; rscale[3] = rs.w;
-                    }
+                    const Stats2 st2 = load_stats2(p.mean, p.scale, p.rscale, vec, OUT == IDL_OUT_STD_F32);
+                    const float mean[4] = {0.f, 0.f, 0.f, 0.f}, scale[4] = {1.f, 1.f, 1.f, 1.f}, rscale[4] = {1.f, 1.f, 1.f, 1.f};
                     const uint2 clean = clean16[vec];
 #pragma unroll 2
                     for (int c = 0; c < hs; ++c) {
@@ -844,15 +879,15 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
                         uint2* src = reinterpret_cast<uint2*>(priv + (cur * HG + c) * PRIVW);
                         const uint2 pk = src[vec];
                         src[vec] = clean;  // the copy is clean again for its next user
-                        int ci[4] = {0, 0, 0, 0};
-                        float cf[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (NEED_F) cvt4_u16(pk, magic, cf);
-                        else {
+                        if (NEED_F) {
+                            emit_granule_u16x2<OUT == IDL_OUT_STD_F32>(row, vec, pk, magic, fy, st2);
+                        } else {
+                            int ci[4];
+                            const float cf[4] = {0.f, 0.f, 0.f, 0.f};
                             ci[0] = (int)(pk.x & 0xFFFFu) + p.pseudocount; ci[1] = (int)(pk.x >> 16) + p.pseudocount;
                             ci[2] = (int)(pk.y & 0xFFFFu) + p.pseudocount; ci[3] = (int)(pk.y >> 16) + p.pseudocount;
+                            emit_granule<OUT>(row, vec, ci, cf, base_total + sm.dtot[h0 + c], fy.x, fy.y, false, p.accumulate, mean, scale, rscale);
                         }
-                        emit_granule<OUT>(row, vec, ci, cf, NEED_F ? 0 : base_total + sm.dtot[h0 + c], fy.x, fy.y, false,
-                                          p.accumulate, mean, scale, rscale);
                     }
                 }
                 __syncthreads();

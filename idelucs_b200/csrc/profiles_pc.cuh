@@ -97,6 +97,10 @@ __device__ __noinline__ void pc_producer(PcSmem& sm, const ProfParams& p) {
     constexpr int K = PC_K;
     const int ptid = threadIdx.x - PC_HALF, lane = ptid & 31;
     int b = 0;
+    long long t_prev = p.phase_prof ? clock64() : 0;
+    auto tick = [&](int id) {
+        if (p.phase_prof && ptid == 0) { const long long t = clock64(); atomicAdd(p.phase_prof + id, (unsigned long long)(t - t_prev)); t_prev = t; }
+    };
     for (;;) {
         PcCtx& cx = sm.ctx[b];
         if (ptid == 0) sm.next_item = (long long)atomicAdd(p.work_counter, 1ull);
@@ -135,6 +139,7 @@ __device__ __noinline__ void pc_producer(PcSmem& sm, const ProfParams& p) {
             bar_named(1, PC_HALF);
             const uint32_t* codes = sm.sseq;
             const uint32_t* nmask = sm.sseq + SSEQ_CW;
+            tick(2);
             if (ptid == 0) cx.base_total = PC_F * p.pseudocount + sm.nvalid;
             for (int vec = ptid; vec < PC_VEC; vec += PC_HALF) {
                 const int4 h = reinterpret_cast<const int4*>(sm.hist)[vec];
@@ -202,6 +207,7 @@ __device__ __noinline__ void pc_producer(PcSmem& sm, const ProfParams& p) {
                 }
                 bar_named(1, PC_HALF);
             }
+            tick(3);
             // ---- Bernoulli slots jointly: thread <-> (slot, 64-base block) ----
             const int nbs = sm.n_bern;
             const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
@@ -263,7 +269,9 @@ __device__ __noinline__ void pc_producer(PcSmem& sm, const ProfParams& p) {
             if (ptid == 0 && cx.n_delta > PC_DELTA) cx.defer = 1;
         }
         if (ptid == 0 && cx.defer) { atomicOr(p.status + item, 2); atomicAdd(p.work_counter + 1, 1ull); }
+        tick(4);
         __syncthreads();   // hand the context over to the consumers
+        tick(5);
         b ^= 1;
     }
 }
@@ -276,9 +284,19 @@ __device__ __forceinline__ void pc_consumer(PcSmem& sm, const ProfParams& p) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float magic = 8388608.0f - (float)p.pseudocount;
     uint32_t* priv = sm.priv;
+    // scaler statistics of this thread's two granules: fixed for the whole launch, kept in registers
+    Stats2 st[VPT];
+#pragma unroll
+    for (int vv = 0; vv < VPT; ++vv) st[vv] = load_stats2(p.mean, p.scale, p.rscale, tid + vv * NT, OUT == IDL_OUT_STD_F32);
     int b = 0;
+    long long t_prev = p.phase_prof ? clock64() : 0;
+    auto tick = [&](int id) {
+        if (p.phase_prof && tid == 0) { const long long t = clock64(); atomicAdd(p.phase_prof + id, (unsigned long long)(t - t_prev)); t_prev = t; }
+    };
     for (;;) {
+        tick(1);
         __syncthreads();   // context b is ready
+        tick(0);
         PcCtx& cx = sm.ctx[b];
         b ^= 1;
         const long long item = cx.item;
@@ -330,31 +348,17 @@ __device__ __forceinline__ void pc_consumer(PcSmem& sm, const ProfParams& p) {
             const int cur = h & 1, h0 = h * HG;
             const int hs = S - h0 < HG ? S - h0 : HG;
             if (h + 1 < nh) patch_half(h0 + HG, S - h0 - HG < HG ? S - h0 - HG : HG, cur ^ 1);
-#pragma unroll
-            for (int vv = 0; vv < VPT; ++vv) {
-                const int vec = tid + vv * NT;
-                float mean[4] = {0.f, 0.f, 0.f, 0.f}, scale[4] = {1.f, 1.f, 1.f, 1.f}, rscale[4] = {1.f, 1.f, 1.f, 1.f};
-                if (OUT == IDL_OUT_STD_F32) {
-                    const float4 m = __ldg(reinterpret_cast<const float4*>(p.mean) + vec);
-                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale) + vec);
-                    const float4 rs = __ldg(reinterpret_cast<const float4*>(p.rscale) + vec);
-                    mean[0] = m.x; mean[1] = m.y; mean[2] = m.z; mean[3] = m.w;
-                    scale[0] = sc.x; scale[1] = sc.y; scale[2] = sc.z; scale[3] = sc.w;
-                    rscale[0] = rs.x; rscale[1] = rs.y; rscale[2] = rs.z; rscale[3] = rs.w;
-                }
-                const uint2 clean = cx.clean16[vec];
+            const uint2 clean0 = cx.clean16[tid], clean1 = cx.clean16[tid + NT];
 #pragma unroll 2
-                for (int c = 0; c < hs; ++c) {
-                    const float2 fy = sm.gy[h0 + c];
-                    unsigned char* row = reinterpret_cast<unsigned char*>(p.out) + sm.grow[h0 + c];
-                    uint2* src = reinterpret_cast<uint2*>(priv + (cur * HG + c) * PRIVW);
-                    const uint2 pk = src[vec];
-                    src[vec] = clean;
-                    const int ci[4] = {0, 0, 0, 0};
-                    float cf[4];
-                    cvt4_u16(pk, magic, cf);
-                    emit_granule<OUT>(row, vec, ci, cf, 0, fy.x, fy.y, false, 0, mean, scale, rscale);
-                }
+            for (int c = 0; c < hs; ++c) {
+                const float2 fy = sm.gy[h0 + c];
+                unsigned char* row = reinterpret_cast<unsigned char*>(p.out) + sm.grow[h0 + c];
+                uint2* src = reinterpret_cast<uint2*>(priv + (cur * HG + c) * PRIVW);
+                const uint2 pk0 = src[tid], pk1 = src[tid + NT];
+                src[tid] = clean0;
+                src[tid + NT] = clean1;
+                emit_granule_u16x2<OUT == IDL_OUT_STD_F32>(row, tid, pk0, magic, fy, st[0]);
+                emit_granule_u16x2<OUT == IDL_OUT_STD_F32>(row, tid + NT, pk1, magic, fy, st[1]);
             }
             bar_named(2, NT);
         }

@@ -64,7 +64,7 @@ def main():
             prof = ws[-128:].view(torch.int64)
             torch.cuda.synchronize()
             cyc = prof.cpu().numpy().astype(float) / (4 * n)   # 4 launches (1 warm + 3 timed), per sequence
-            names = ["count", "copies", "sg-plan+randN", "cta-prep", "patch", "stream", "restore", "b.gen", "b.scan", "b.write", "b.apply", "b.bar", "sg.plan", "sg.p1", "sg.p2"]
+            names = ["C.wait", "C.stream", "P.count", "P.randN", "P.bern", "P.wait", "restore", "b.gen", "b.scan", "b.write", "b.apply", "b.bar", "sg.plan", "sg.p1", "sg.p2"]
             print("     cycles/sequence (thread 0): " + "  ".join("%s %.0f" % (nm, c) for nm, c in zip(names, cyc)) + "  total %.0f" % cyc[:7].sum())
             prof.zero_()
     best, avg = timeit(lambda: ft.Scaler.fit(out[0]))
