@@ -279,6 +279,7 @@ def run_ours(args):
         st._d_ascii = None
         del a
         tr = ShardedTrainer(st, k=K, n_clusters=5, n_mimics=N_MIMICS, batch_sz=512, seed=7, seq_id0=rank * nt, world=world)
+        graphed = tr.enable_cuda_graph() if world == 1 else False   # DDP replicas stay eager in this round
         for _ in range(10):
             tr.step()
         torch.cuda.synchronize()
@@ -296,7 +297,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             tms = float(t.item())
         train = {"pairs_per_s": world * 512 * args.train_steps / (tms * 1e-3), "ms_per_step": tms / args.train_steps,
-                 "steps": args.train_steps, "final_loss": float(loss.item()),
+                 "steps": args.train_steps, "final_loss": float(loss.item()), "cuda_graph": bool(graphed),
                  "config": "synthetic %d sequences x 2000 bp sharded over %d GPU(s), k=6, n_mimics=50, batch_sz=512 per rank, "
                            "n_clusters=5, RMSprop, (1-w) InfoNCE + w IIC (BASELINE.json configs[3]); batches regenerated on the "
                            "fly by the mimic kernel; MLP / InfoNCE in PyTorch fp32" % (nt * world, world)}

@@ -30,14 +30,45 @@ class ShardedTrainer(object):
         net.apply(weights_init)
         net.to(self.dev)
         self.net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[self.dev.index]) if world > 1 else net
-        self.opt = torch.optim.RMSprop(self.net.parameters(), lr=lr, weight_decay=0.01)
+        self.opt = torch.optim.RMSprop(self.net.parameters(), lr=lr, weight_decay=0.01, capturable=True)
         self.lamb, self.weight, self.batch_sz = lamb, weight, batch_sz
         self.gen = torch.Generator(device=self.dev).manual_seed(seed * 1000003 + seq_id0 + 1)
+        self._graph = None
+        self._ids = torch.zeros(batch_sz, dtype=torch.int64, device=self.dev)
+
+    def enable_cuda_graph(self, warmup=11):
+        """Capture featurise -> forward x2 -> losses -> backward -> RMSprop in ONE CUDA graph: the
+        step is launch-bound (~100 small kernels), so replaying a graph removes the host from the
+        loop.  The pair ids are the only input (static buffer filled before every replay).
+        Returns False (and stays eager) if capture is not possible."""
+        try:
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):
+                for _ in range(warmup):
+                    self._step_from_ids()
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                self._loss = self._step_from_ids()
+            self._graph = g
+            return True
+        except Exception as e:  # noqa: BLE001 — eager fallback of an optimisation, not of the CUDA path
+            self._graph = None
+            self._graph_error = repr(e)
+            torch.cuda.synchronize(self.dev)
+            return False
 
     def step(self):
         """one training step on a random batch of this rank's pairs; returns the loss tensor"""
-        ids = torch.randint(0, self.loader.n_pairs, (self.batch_sz,), device=self.dev, generator=self.gen)
-        batch = self.loader.batch(ids)
+        self._ids.copy_(torch.randint(0, self.loader.n_pairs, (self.batch_sz,), device=self.dev, generator=self.gen))
+        if self._graph is not None:
+            self._graph.replay()
+            return self._loss
+        return self._step_from_ids()
+
+    def _step_from_ids(self):
+        batch = self.loader.batch(self._ids)
         self.opt.zero_grad(set_to_none=True)
         z1, h1 = self.net(batch["true"])
         z2, h2 = self.net(batch["modified"])
