@@ -172,16 +172,16 @@ def run_ours(args):
     k_ev = [ev(), ev()]
 
     def step():
-        # pass 1: t_norm (slot 0) frequencies -> out[0]; statistics; pass 2: all slots standardised
-        ft.profiles(ss, K, variants[:1], out_kind=ft.OUT_FREQ_F32, seed=args.seed, out=out, out_off=off[:1], out_stride=F, seq_id0=seq_id0)
-        sc = ft.Scaler.fit(out[0], group=group)
+        # pass A: statistics of the t_norm (slot 0) frequencies, accumulated inside the kernel (idl_profile_stats);
+        # pass B: all 51 slots standardised with them
+        sc = ft.profile_stats(ss, K, variants[0], seed=args.seed, seq_id0=seq_id0, group=group)
         k_ev[0].record()
         ft.profiles(ss, K, variants, out_kind=ft.OUT_STD_F32, seed=args.seed, out=out, out_off=off, out_stride=F,
                     mean=sc.mean32, scale=sc.scale32, seq_id0=seq_id0)
         k_ev[1].record()
         return sc
 
-    launches_per_step = 7  # pass A: profiles_pc + deferred pass; colstats; scaler_finalize; pass B: rscale, profiles_pc + deferred pass
+    launches_per_step = 5  # pass A: profiles_kernel<STATS>, scaler_finalize; pass B: rscale, profiles_pc + deferred-item pass
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -241,8 +241,7 @@ def run_ours(args):
 
         def e2e_step():
             s2 = SeqSet.from_ascii(host_ascii, boff, device=dev, validate=True)  # H2D + pack + alphabet check (D2H of flags)
-            ft.profiles(s2, K, variants[:1], out_kind=ft.OUT_FREQ_F32, seed=args.seed, out=dev_out, out_off=offe[:1], out_stride=F)
-            sc = ft.Scaler.fit(dev_out[0])
+            sc = ft.profile_stats(s2, K, variants[0], seed=args.seed)
             ft.profiles(s2, K, variants, out_kind=ft.OUT_STD_F32, seed=args.seed, out=dev_out, out_off=offe, out_stride=F,
                         mean=sc.mean32, scale=sc.scale32)
             host_out.copy_(dev_out, non_blocking=True)

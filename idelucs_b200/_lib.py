@@ -33,6 +33,9 @@ PROTOTYPES = {
                              ctypes.POINTER(Variant), c_int, c_void_p, c_int, c_u64, c_void_p, c_void_p, c_int,
                              c_void_p, ctypes.POINTER(c_i64), c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_void_p]),
+    "idl_profile_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, ctypes.POINTER(Variant),
+                                  c_u64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, ctypes.POINTER(c_int), c_void_p, c_void_p,
+                                  c_size_t, c_void_p]),
     "idl_kmer_counts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "idl_colstats_parts": (c_int, [c_i64]),
     "idl_colstats": (c_int, [c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p]),

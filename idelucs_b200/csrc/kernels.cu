@@ -69,7 +69,11 @@ struct ProfParams {
     unsigned long long* work_counter;
     unsigned long long* phase_prof;   // optional: cycles per kernel phase summed over CTAs (thread 0), IDL_PHASE_PROF=1
     int only_deferred;                // generic kernel: redo only the items the producer/consumer kernel flagged (status bit 1)
+    double* stats_partials;           // OUT_STATS: per-CTA (mean, M2) [gridDim][2][4^k]
+    double* stats_n;                  // OUT_STATS: per-CTA row count [gridDim]
 };
+
+constexpr int OUT_STATS = 4;          // internal out kind: column statistics of slot 0's float32 frequencies, nothing is written per row
 
 // ---------------------------------------------------------------------------------------
 // K1 pack
@@ -621,11 +625,20 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
     pclk.base = p.phase_prof;
     pclk.t_prev = p.phase_prof ? clock64() : 0;
     auto phase = [&](int id) { pclk.tick(id); };
+    // OUT_STATS: shifted-data column sums of this CTA's rows (shift = first row seen), float64
+    double acc1[VPT][4], acc2[VPT][4];
+    float shiftK[VPT][4];
+    int n_acc = 0;
+#pragma unroll
+    for (int vv = 0; vv < VPT; ++vv)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc1[vv][e] = 0.0; acc2[vv][e] = 0.0; shiftK[vv][e] = 0.f; }
     for (;;) {
         __syncthreads();  // previous item fully done (also protects sm.item)
         if (tid == 0) {
             long long it;
-            if (!p.only_deferred) it = (long long)atomicAdd(p.work_counter, 1ull);
+            if (OUT == OUT_STATS) it = (long long)blockIdx.x + (long long)n_acc * gridDim.x;   // static rows per CTA: reproducible sums
+            else if (!p.only_deferred) it = (long long)atomicAdd(p.work_counter, 1ull);
             else if (p.work_counter[1] == 0ull) it = p.n_items;   // nothing was deferred
             else {
                 do { it = (long long)atomicAdd(p.work_counter + 2, 1ull); } while (it < p.n_items && !(p.status[it] & 2));
@@ -675,6 +688,91 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
         if (staged) { cx.codes = sm.sseq; cx.nmask = sm.sseq + SSEQ_CW; }  // every later lookup hits shared memory
         phase(0);
 
+        if (OUT == OUT_STATS) {
+            // ---- statistics mode: patch hist[] in place with slot 0's deltas, accumulate, next item ----
+            const VarDesc vd = vars[slot_var(0)];
+            if (tid == 0) sm.dtot[0] = 0;
+            __syncthreads();
+            const int nblk = (L + RNG_BLOCK - 1) / RNG_BLOCK;
+            const bool bern = vd.kind == KIND_TRANSITION || vd.kind == KIND_TRANSVERSION || vd.kind == KIND_BOTH;
+            if (bern && nblk > 0) {
+                bool done = false;
+                if (nblk <= NT) {   // fast generator, thread <-> 64-base block
+                    FastBlock f;
+                    f.cnt = 0; f.ok = true;
+                    if (tid < nblk)
+                        f = fast_block(vd.kind, cx.seed, cx.seq_id, (uint32_t)vd.rng_id, tid, L, cx.nmask, gap_table(sm, p, vd.tab1), vd.slope1,
+                                       gap_table(sm, p, vd.tab2), vd.slope2);
+                    if (!__syncthreads_or(tid < nblk && !f.ok)) {
+                        int total;
+                        const int off = block_exscan<NT>(f.cnt, sm.scan, &total);
+                        if (total <= LIST_CAP) {
+                            done = true;
+                            if (tid < nblk && f.cnt) fast_block_write(f, tid, cx.codes, sm.list + off);
+                            __syncthreads();
+                            int d = 0;
+                            for (int i = tid; i < total; i += NT) d += apply_hist<K>(cx, sm.list, total, i, sm.hist, 1);
+                            d = warp_sum(d);
+                            if (lane == 0 && d) atomicAdd(&sm.dtot[0], d);
+                        }
+                    }
+                }
+                if (!done) {        // generic generator, tile by tile
+                    constexpr int TBs = NT - 2;
+                    for (int tb0 = 0; tb0 < nblk; tb0 += TBs) {
+                        const int total = bernoulli_tile<K, NT>(sm, p, cx, vd, tb0, nblk);
+                        if (total < 0) { if (tid == 0 && p.status) atomicOr(p.status + item, 1); continue; }
+                        const int lo = tb0 * RNG_BLOCK;
+                        const long long hi = (long long)(tb0 + TBs) * RNG_BLOCK;
+                        int d = 0;
+                        for (int i = tid; i < total; i += NT) {
+                            const int pos = (int)(sm.list[i] >> 3);
+                            if (pos >= lo && pos < hi) d += apply_hist<K>(cx, sm.list, total, i, sm.hist, 1);
+                        }
+                        d = warp_sum(d);
+                        if (lane == 0 && d) atomicAdd(&sm.dtot[0], d);
+                        __syncthreads();
+                    }
+                }
+            }
+            if (vd.kind == KIND_EXPLICIT || (vd.kind == KIND_RANDOM_N && vd.n_bp > 0 && L > 0)) {
+                const uint32_t* lst = sm.list;
+                int n_list = vd.n_bp;
+                if (vd.kind == KIND_EXPLICIT) {
+                    const long long li = (long long)vd.explicit_idx * p.n_seqs_total + seq;
+                    lst = p.edits + p.edit_off[li];
+                    n_list = (int)(p.edit_off[li + 1] - p.edit_off[li]);
+                } else {
+                    random_n_list<K, NT>(sm, cx, vd, sm.privtmp);
+                }
+                int d = 0;
+                for (int i = tid; i < n_list; i += NT) d += apply_hist<K>(cx, lst, n_list, i, sm.hist, 1);
+                d = warp_sum(d);
+                if (lane == 0 && d) atomicAdd(&sm.dtot[0], d);
+            }
+            __syncthreads();
+            const int total = base_total + sm.dtot[0];
+            const float ftot = (float)total;
+            const float y = 1.0f / ftot;
+            const bool big = total >= (1 << 24);
+#pragma unroll
+            for (int vv = 0; vv < VPT; ++vv) {
+                const int vec = tid + vv * NT;
+                if (VEC % NT != 0 && vec >= VEC) break;
+                const int4 h = reinterpret_cast<const int4*>(sm.hist)[vec];
+                const int ci[4] = {h.x + p.pseudocount, h.y + p.pseudocount, h.z + p.pseudocount, h.w + p.pseudocount};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float q = big ? (float)((double)ci[e] / (double)total) : div_rn((float)ci[e], ftot, y);
+                    if (n_acc == 0) shiftK[vv][e] = q;
+                    const double dd = (double)q - (double)shiftK[vv][e];
+                    acc1[vv][e] += dd;
+                    acc2[vv][e] = fma(dd, dd, acc2[vv][e]);
+                }
+            }
+            ++n_acc;
+            continue;
+        }
         if (L > 65535) {
             long_path<K, NT, OUT>(sm, p, cx, vars, out_offs, item, seq, base_total);
             continue;
@@ -902,6 +1000,20 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
             S0 += NSg;
         }
     }
+    if (OUT == OUT_STATS) {   // this CTA's part: (rows, mean, M2) per column, merged by scaler_finalize_kernel
+        if (tid == 0) p.stats_n[blockIdx.x] = (double)n_acc;
+        const double m = n_acc > 0 ? (double)n_acc : 1.0;
+#pragma unroll
+        for (int vv = 0; vv < VPT; ++vv) {
+            const int vec = tid + vv * NT;
+            if (VEC % NT != 0 && vec >= VEC) break;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                p.stats_partials[((size_t)blockIdx.x * 2 + 0) * F + vec * 4 + e] = (double)shiftK[vv][e] + acc1[vv][e] / m;
+                p.stats_partials[((size_t)blockIdx.x * 2 + 1) * F + vec * 4 + e] = acc2[vv][e] - acc1[vv][e] * acc1[vv][e] / m;
+            }
+        }
+    }
 }
 
 }  // namespace idl
@@ -1017,7 +1129,7 @@ constexpr size_t WS_PROF = WS_RSCALE + sizeof(float) * 4096;
 constexpr size_t WS_TOTAL = WS_PROF + 8 * 16;  // 16 phase counters
 
 template <int K, int NT, int OUT>
-static int launch_profiles(const ProfParams& p, cudaStream_t st) {
+static int launch_profiles(const ProfParams& p, cudaStream_t st, int* grid_out = nullptr) {
     const size_t smem = sizeof(ProfSmem<K, NT>);
     auto kern = profiles_kernel<K, NT, OUT>;
     static bool configured = false;
@@ -1031,14 +1143,16 @@ static int launch_profiles(const ProfParams& p, cudaStream_t st) {
     long long grid = (long long)sm_count() * per_sm;
     if (grid > p.n_items) grid = p.n_items;
     if (grid < 1) grid = 1;
+    if (grid_out) *grid_out = (int)grid;
     kern<<<(unsigned)grid, NT, smem, st>>>(p);
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }
 
 template <int K, int NT>
-static int dispatch_out(const ProfParams& p, int out_kind, cudaStream_t st) {
+static int dispatch_out(const ProfParams& p, int out_kind, cudaStream_t st, int* grid_out = nullptr) {
     switch (out_kind) {
+        case OUT_STATS: return launch_profiles<K, NT, OUT_STATS>(p, st, grid_out);
         case IDL_OUT_COUNTS_I32: return launch_profiles<K, NT, IDL_OUT_COUNTS_I32>(p, st);
         case IDL_OUT_FREQ_F32: return launch_profiles<K, NT, IDL_OUT_FREQ_F32>(p, st);
         case IDL_OUT_STD_F32: return launch_profiles<K, NT, IDL_OUT_STD_F32>(p, st);
@@ -1083,15 +1197,17 @@ int idl_pack(const uint8_t* d_ascii, const int64_t* d_byte_off, int64_t n, int a
 
 size_t idl_profiles_workspace_bytes(void) { return WS_TOTAL; }
 
-int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
-                 const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
-                 int64_t seq_id0, int k, const idl_variant* variants, int n_variants, const int32_t* d_sel,
-                 int S, uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits, int out_kind,
-                 void* d_out, const int64_t* out_off, int64_t out_stride, int pseudocount, int accumulate,
-                 const float* d_mean, const float* d_scale, int32_t* d_status, void* d_workspace,
-                 size_t workspace_bytes, void* stream) {
+static int profiles_impl(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
+                         const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
+                         int64_t seq_id0, int k, const idl_variant* variants, int n_variants, const int32_t* d_sel,
+                         int S, uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits, int out_kind,
+                         void* d_out, const int64_t* out_off, int64_t out_stride, int pseudocount, int accumulate,
+                         const float* d_mean, const float* d_scale, int32_t* d_status, void* d_workspace,
+                         size_t workspace_bytes, void* stream, double* d_stats_partials, double* d_stats_n, int* n_parts_out) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!d_codes || !d_nmask || !d_chunk_off || !d_len || !variants || !d_out || !out_off || !d_workspace)
+    const int64_t zero_off = 0;
+    if (out_kind == OUT_STATS) { out_off = &zero_off; out_stride = 0; }
+    if (!d_codes || !d_nmask || !d_chunk_off || !d_len || !variants || (!d_out && out_kind != OUT_STATS) || !out_off || !d_workspace)
         return set_error(IDL_EINVAL, "idl_profiles: null pointer%s", "");
     if (workspace_bytes < WS_TOTAL) return set_error(IDL_EINVAL, "idl_profiles: workspace too small%s (need %lld bytes)", "", (long long)WS_TOTAL);
     if (k < 1 || k > 6) return set_error(IDL_EUNSUPPORTED, "idl_profiles: k must be in 1..6%s (got %lld)", "", k);
@@ -1175,6 +1291,17 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
     static const bool want_prof = getenv("IDL_PHASE_PROF") != nullptr;
     p.phase_prof = want_prof ? reinterpret_cast<unsigned long long*>(ws + WS_PROF) : nullptr;
     p.only_deferred = 0;
+    p.stats_partials = d_stats_partials; p.stats_n = d_stats_n;
+    if (out_kind == OUT_STATS) {
+        switch (k) {
+            case 1: return dispatch_out<1, 64>(p, out_kind, st, n_parts_out);
+            case 2: return dispatch_out<2, 64>(p, out_kind, st, n_parts_out);
+            case 3: return dispatch_out<3, 64>(p, out_kind, st, n_parts_out);
+            case 4: return dispatch_out<4, 128>(p, out_kind, st, n_parts_out);
+            case 5: return dispatch_out<5, 256>(p, out_kind, st, n_parts_out);
+            case 6: return dispatch_out<6, 512>(p, out_kind, st, n_parts_out);
+        }
+    }
     // ---- producer/consumer kernel (k = 6, float outputs, whole-schedule featurisation) ----
     bool pc_ok = k == 6 && (out_kind == IDL_OUT_FREQ_F32 || out_kind == IDL_OUT_STD_F32) && !d_sel && d_status &&
                  n_variants <= PC_MAXS && n_items >= 2LL * sm_count() && getenv("IDL_NO_PC") == nullptr;
@@ -1211,6 +1338,33 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
         case 6: return dispatch_out<6, 512>(p, out_kind, st);
     }
     return set_error(IDL_EUNSUPPORTED, "idl_profiles: unsupported k%s", "");
+}
+
+int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
+                 const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
+                 int64_t seq_id0, int k, const idl_variant* variants, int n_variants, const int32_t* d_sel,
+                 int S, uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits, int out_kind,
+                 void* d_out, const int64_t* out_off, int64_t out_stride, int pseudocount, int accumulate,
+                 const float* d_mean, const float* d_scale, int32_t* d_status, void* d_workspace,
+                 size_t workspace_bytes, void* stream) {
+    if (out_kind < IDL_OUT_COUNTS_I32 || out_kind > IDL_OUT_FREQ_F64) return set_error(IDL_EINVAL, "idl_profiles: unknown out_kind%s %lld", "", out_kind);
+    return profiles_impl(d_codes, d_nmask, d_chunk_off, d_len, n_seqs_total, d_sidx, n_items, seq_id0, k, variants, n_variants, d_sel, S,
+                         seed, d_edit_off, d_edits, out_kind, d_out, out_off, out_stride, pseudocount, accumulate, d_mean, d_scale,
+                         d_status, d_workspace, workspace_bytes, stream, nullptr, nullptr, nullptr);
+}
+
+int idl_profile_stats(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off, const int32_t* d_len,
+                      int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items, int64_t seq_id0, int k,
+                      const idl_variant* variant, uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits, int pseudocount,
+                      double* d_partials, double* d_part_n, int max_parts, int* n_parts, int32_t* d_status, void* d_workspace,
+                      size_t workspace_bytes, void* stream) {
+    if (!d_partials || !d_part_n || !n_parts || !variant) return set_error(IDL_EINVAL, "idl_profile_stats: null pointer%s", "");
+    if (max_parts < sm_count() * 8) return set_error(IDL_EINVAL, "idl_profile_stats: max_parts too small%s (need %lld)", "", (long long)sm_count() * 8);
+    *n_parts = 0;
+    if (n_items <= 0) return IDL_OK;
+    return profiles_impl(d_codes, d_nmask, d_chunk_off, d_len, n_seqs_total, d_sidx, n_items, seq_id0, k, variant, 1, nullptr, 1, seed,
+                         d_edit_off, d_edits, OUT_STATS, nullptr, nullptr, 0, pseudocount, 0, nullptr, nullptr, d_status, d_workspace,
+                         workspace_bytes, stream, d_partials, d_part_n, n_parts);
 }
 
 int idl_kmer_counts(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,

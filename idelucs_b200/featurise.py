@@ -130,6 +130,33 @@ def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_o
     return out
 
 
+def profile_stats(seqset, k, variant, seed=0, seq_id0=0, edit_lists=None, group=None, pseudocount=1):
+    """Scaler statistics of one variant's float32 frequency profiles over the whole SeqSet, computed
+    inside the featurisation kernel (no [N, 4^k] matrix is written or re-read).  Equivalent to
+    ``Scaler.fit(profiles(seqset, k, [variant], OUT_FREQ_F32)[0], group)``."""
+    lib = _lib.load()
+    device = seqset.device
+    F = 4 ** k
+    max_parts = 2048
+    parts = torch.empty((max_parts, 2, F), dtype=torch.float64, device=device)
+    part_n = torch.zeros((max_parts,), dtype=torch.float64, device=device)
+    varr = _variant_array([variant])
+    n_parts = ctypes.c_int(0)
+    d_eoff, d_ent = (None, None) if edit_lists is None else edit_lists
+    with torch.cuda.device(device):
+        ws = _workspace(device, lib.idl_profiles_workspace_bytes(), "prof")
+        _lib.check(lib.idl_profile_stats(_lib.ptr(seqset.codes), _lib.ptr(seqset.nmask), _lib.ptr(seqset.chunk_off), _lib.ptr(seqset.len),
+                                         seqset.n, None, seqset.n, int(seq_id0), k, varr, ctypes.c_uint64(seed & (2 ** 64 - 1)),
+                                         _lib.ptr(d_eoff), _lib.ptr(d_ent), int(pseudocount), _lib.ptr(parts), _lib.ptr(part_n),
+                                         max_parts, ctypes.byref(n_parts), None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    parts, part_n = parts[: n_parts.value].contiguous(), part_n[: n_parts.value].contiguous()
+    if seqset.n == 0:
+        parts, part_n = torch.zeros((1, 2, F), dtype=torch.float64, device=device), torch.zeros((1,), dtype=torch.float64, device=device)
+    if group is not None:
+        parts, part_n = gather_partials(parts, part_n, group)
+    return Scaler.from_partials(parts, part_n)
+
+
 def kmer_counts_batch(seqset, k, counts=None):
     """int32 counts [n, 4^k] of every sequence (idelucs/kmers.pyx:2-50 per sequence)."""
     lib = _lib.load()

@@ -168,9 +168,7 @@ def augment_device(ss, n_mimics, k=6, seed=None, group=None, seq_id0=0):
     t_norm, slot j = mimic j — standardised with the t_norm statistics, and the Scaler)."""
     seed = _draw_seed() if seed is None else seed
     variants = ft.mimic_schedule(n_mimics)
-    t_norm = ft.profiles(ss, k, variants[:1], out_kind=ft.OUT_FREQ_F32, seed=seed, seq_id0=seq_id0)[0]
-    sc = ft.Scaler.fit(t_norm, group=group)
-    del t_norm
+    sc = ft.profile_stats(ss, k, variants[0], seed=seed, seq_id0=seq_id0, group=group)   # t_norm statistics, never materialised
     out = ft.profiles(ss, k, variants, out_kind=ft.OUT_STD_F32, seed=seed, mean=sc.mean32, scale=sc.scale32, seq_id0=seq_id0)
     return out, sc, seed
 
@@ -223,9 +221,7 @@ class PairBatchLoader(object):
         if len(self.variants) * ss.n * F * 4 <= materialize_bytes:
             self.profiles, self.scaler, _ = augment_device(ss, n_mimics, k, seed=self.seed, group=group, seq_id0=seq_id0)
         else:
-            t_norm = ft.profiles(ss, k, self.variants[:1], out_kind=ft.OUT_FREQ_F32, seed=self.seed, seq_id0=seq_id0)[0]
-            self.scaler = ft.Scaler.fit(t_norm, group=group)
-            del t_norm
+            self.scaler = ft.profile_stats(ss, k, self.variants[0], seed=self.seed, seq_id0=seq_id0, group=group)
             self.profiles = None
 
     def __len__(self):

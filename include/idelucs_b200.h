@@ -114,6 +114,18 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
                  const float* d_mean, const float* d_scale, int32_t* d_status, void* d_workspace,
                  size_t workspace_bytes, void* stream);
 
+/* Column statistics of ONE variant's float32 frequency profiles without materialising them —
+ * replaces the t_norm pass + StandardScaler.fit of AugmentFasta (idelucs/utils.py:330, 354-359):
+ * every CTA accumulates shifted float64 column sums of the rows it produces and emits one
+ * (count, mean, M2) part; feed d_partials / d_part_n / *n_parts to idl_scaler_finalize (after
+ * all-gathering the parts of every rank when sharded).  d_partials double[max_parts][2][4^k],
+ * d_part_n double[max_parts]; max_parts >= 8 x number of SMs. */
+int idl_profile_stats(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off, const int32_t* d_len,
+                      int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items, int64_t seq_id0, int k,
+                      const idl_variant* variant, uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits,
+                      int pseudocount, double* d_partials, double* d_part_n, int max_parts, int* n_parts,
+                      int32_t* d_status, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Convenience form of the above for kmer_counts (idelucs/kmers.pyx:2-50): raw int32 counts
  * of every sequence into d_counts[n, 4^k] (accumulating when accumulate != 0). */
 int idl_kmer_counts(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,

@@ -351,3 +351,36 @@ def test_pc_kernel_equals_generic(ft, SeqSet):
             orc.kmer_counts(mut, 6, cnt)
             assert np.array_equal(c[v, i], cnt), (i, v)
             assert np.array_equal(f32[v, i], ((cnt + 1) / (cnt + 1).sum()).astype(np.float32)), (i, v)
+
+
+def test_profile_stats_equals_matrix_fit(golden_dir, fasta_files, ft, SeqSet):
+    """in-kernel statistics (idl_profile_stats) == colstats over the materialised profiles, for
+    rng-mode Bernoulli, Random_N, clean and explicit (reference mutations) variants; and the
+    AugmentFasta x_train built from them is still bit-identical to the reference"""
+    ss = SeqSet.from_fasta(fasta_files["Influenza-A"])
+    for k, spec in ((6, ft.VariantSpec(ft.KIND_BOTH, 1e-2, 0.5e-2, rng_id=0)), (5, ft.VariantSpec(ft.KIND_RANDOM_N, n_bp=20, rng_id=3)),
+                    (6, ft.VariantSpec(ft.KIND_CLEAN)), (4, ft.VariantSpec(ft.KIND_TRANSVERSION, p2=0.3, rng_id=2))):
+        x = ft.profiles(ss, k, [spec], out_kind=ft.OUT_FREQ_F32, seed=17)[0]
+        a, b = ft.Scaler.fit(x), ft.profile_stats(ss, k, spec, seed=17)
+        assert torch.allclose(a.mean64, b.mean64, rtol=1e-13, atol=0)
+        assert torch.allclose(a.scale64, b.scale64, rtol=1e-9, atol=0)
+        assert float(((a.mean32 - b.mean32).abs() / a.mean32.abs()).max()) < 2e-7      # at most a last-ulp flip of the cast
+        c = ft.profile_stats(ss, k, spec, seed=17)
+        assert torch.equal(b.mean64, c.mean64) and torch.equal(b.scale64, c.scale64)  # run-to-run identical
+    g = _golden(golden_dir)["files"]["Influenza-A"]["augment_seed0_nmimics3"]
+    ed = np.load(os.path.join(golden_dir, "influenza_edits_seed0.npz"))
+    n, offs, k, F = ss.n, ed["offsets"], 5, 1024
+    lut = np.full(256, 4, np.int64)
+    for i, ch in enumerate(b"ACGT"):
+        lut[ch] = i
+    explicit = [[(ed["pos"][offs[p * n + i]:offs[p * n + i + 1]], lut[ed["newbyte"][offs[p * n + i]:offs[p * n + i + 1]]])
+                 for i in range(n)] for p in range(4)]
+    lists = ft.pack_edit_lists(explicit, n, ss.device)
+    variants = [ft.VariantSpec(ft.KIND_EXPLICIT, explicit_idx=p) for p in range(4)]
+    sc = ft.profile_stats(ss, k, variants[0], edit_lists=lists)
+    x = torch.empty((3 * n, 2, F), dtype=torch.float32, device=ss.device)
+    ft.profiles(ss, k, variants, out_kind=ft.OUT_STD_F32, edit_lists=lists, mean=sc.mean32, scale=sc.scale32,
+                out=x, out_off=[0] + [((j * n) * 2 + 1) * F for j in range(3)], out_stride=2 * F)
+    x[n:2 * n, 0] = x[:n, 0]
+    x[2 * n:, 0] = x[:n, 0]
+    assert sha(x.cpu().numpy()) == g["k5"]["x_train_sha256"]
