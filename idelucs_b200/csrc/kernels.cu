@@ -71,6 +71,7 @@ struct ProfParams {
     int only_deferred;                // generic kernel: redo only the items the producer/consumer kernel flagged (status bit 1)
     double* stats_partials;           // OUT_STATS: per-CTA (mean, M2) [gridDim][2][4^k]
     double* stats_n;                  // OUT_STATS: per-CTA row count [gridDim]
+    int dbg;                          // development switches of the producer/consumer kernel (IDL_PC_DBG)
 };
 
 constexpr int OUT_STATS = 4;          // internal out kind: column statistics of slot 0's float32 frequencies, nothing is written per row
@@ -1291,6 +1292,7 @@ static int profiles_impl(const uint32_t* d_codes, const uint32_t* d_nmask, const
     static const bool want_prof = getenv("IDL_PHASE_PROF") != nullptr;
     p.phase_prof = want_prof ? reinterpret_cast<unsigned long long*>(ws + WS_PROF) : nullptr;
     p.only_deferred = 0;
+    { const char* e = getenv("IDL_PC_DBG"); p.dbg = e ? atoi(e) : 0; }
     p.stats_partials = d_stats_partials; p.stats_n = d_stats_n;
     if (out_kind == OUT_STATS) {
         switch (k) {
@@ -1310,10 +1312,13 @@ static int profiles_impl(const uint32_t* d_codes, const uint32_t* d_nmask, const
         for (int v = 0; v < n_variants; ++v) {
             const VarDesc& d = h_vars[v];
             if (d.kind == IDL_KIND_EXPLICIT) pc_ok = false;
-            else if (d.kind == IDL_KIND_RANDOM_N) { if (d.n_bp > 32) pc_ok = false; else if (d.n_bp > 0) n_ent += d.n_bp; }
+            else if (d.kind == IDL_KIND_RANDOM_N) { if (d.n_bp * PC_K > 127) pc_ok = false; else if (d.n_bp > 0) n_ent += d.n_bp; }
             else if (d.kind != IDL_KIND_CLEAN) ++n_bern;
         }
         if (n_bern > PC_MAXB || n_ent > LIST_CAP || n_ent * PC_K > PC_REM) pc_ok = false;
+        // TMA bulk copies: 16-byte aligned rows
+        if (((uintptr_t)d_out & 15) || (out_stride & 3) || ((uintptr_t)d_codes & 15) || ((uintptr_t)d_nmask & 15)) pc_ok = false;
+        for (int v = 0; v < S && pc_ok; ++v) if (out_off[v] & 3) pc_ok = false;
     }
     if (pc_ok) {
         auto kern = out_kind == IDL_OUT_STD_F32 ? profiles_pc_kernel<IDL_OUT_STD_F32> : profiles_pc_kernel<IDL_OUT_FREQ_F32>;

@@ -1,14 +1,27 @@
 // idelucs_b200 — producer/consumer variant of the profiles kernel (k = 6, float outputs).
 //
-// One CTA of 1024 threads per SM.  Warps 16..31 (PRODUCERS) prepare sequence i+1 — count the
-// clean histogram, pack it to uint16, precompute the Random_N removal lists of every slot and
-// the +-1 delta list of the Bernoulli slots — into one of two shared-memory contexts while
-// warps 0..15 (CONSUMERS) stream the 51 profiles of sequence i from the other context:
-// 8 private uint16 copies in two sets of 4; the consumers subtract the removals of the next
-// half-group with fire-and-forget shared atomics, stream the current half-group (restoring
-// its copies on the way) and meet at a consumer-only named barrier once per 4 variants.
-// Producers and consumers meet at ONE CTA-wide barrier per sequence.  The counting, RNG and
-// delta work therefore overlaps with the HBM-bound streaming instead of alternating with it.
+// One persistent CTA of 1024 threads per SM, four roles that only meet through mbarriers:
+//
+//  * PRODUCERS (warps 16..31) prepare sequence i+1 into one of two shared-memory contexts: count
+//    the clean histogram, pack it to uint16, precompute the Random_N removal lists of every slot
+//    and the +-1 delta list of the Bernoulli slots, the per-slot window totals, output rows and
+//    the JOB ORDER (dense slots first, then the sparse slots sorted by window total).
+//  * BUILDERS (warps 0..7) write finished 16 KB float rows into a ring of PC_NBUF shared-memory
+//    row buffers (job j uses buffer j mod PC_NBUF).  A Random_N mimic differs from the clean
+//    histogram in <= 120 of 4096 bins and every untouched bin of every variant with the same
+//    window total T has the SAME output value, so a buffer is only rebuilt when the job's T
+//    differs from the T of the job that used it last (the jobs are sorted by T); a Bernoulli
+//    slot changes most granules and always gets its own dense row (clean + delta scratch).
+//  * FIX warps (one per row buffer) make the buffer's row the job's row: they undo the <= 120
+//    changed bins of the previous job and write those of the new one (4-byte shared-memory
+//    stores).  The changed bins are found through a zero-based delta scratch (packed biased
+//    uint8): removals are subtracted with shared atomics, then a lane claims a scratch word
+//    with atomicExch (which also resets it), so duplicate k-mers in the removal list are harmless.
+//  * The STORE thread writes each job's row with ONE TMA bulk copy
+//    (cp.async.bulk.global.shared::cta, 16 KB): the 83 GB of output never pass through the
+//    LSU instruction queue (the shared-memory traffic of the other roles is not stuck behind
+//    back-pressured global stores), every global write is a full line, and nothing is ever
+//    re-read or partially overwritten in L2.  It also dispatches the items (atomic counter).
 //
 // Items this kernel cannot take (longer than 20 480 bases, > FAST_CAP hits in a 64-base block,
 // delta list overflow) are flagged in d_status (bit 1) and redone by the generic kernel.
@@ -18,11 +31,19 @@
 namespace idl {
 
 constexpr int PC_NT = 1024, PC_HALF = 512;
-constexpr int PC_K = 6, PC_F = 4096, PC_VEC = 1024, PC_VPT = 2, PC_PRIVW = 2048;
-constexpr int PC_G = 8, PC_HG = 4;
+constexpr int PC_K = 6, PC_F = 4096, PC_VEC = 1024, PC_PRIVW = 2048;
+constexpr int PC_NBLD = 256;       // builder threads (warps 0..7)
+constexpr int PC_NFIX = 224;       // fix threads (warps 8..14); warp 15 lane 0 is the store thread
+constexpr int PC_NBUF = 3;         // 16 KB row buffers
+constexpr int PC_FIXW = PC_NFIX / 32;   // fix warps: each owns a 4 KB scratch (biased uint8 deltas) and handles whole jobs
+constexpr int PC_SCRW = 1024;      // words of one fix-warp scratch (four bins per word)
+constexpr uint32_t PC_BIAS4 = 0x80808080u;
+constexpr int PC_SSEQ_W = SSEQ_CW + SSEQ_MW + 6;   // staged sequence: codes | mask (+ 16-byte alignment shift and round-up)
+constexpr int PC_QRING = 8;        // dispatched items buffered ahead of the producers
+constexpr uint32_t PC_BIAS2 = 0x80008000u;
 constexpr int PC_MAXS = 64;        // variant slots per sequence
-constexpr int PC_REM = 6144;       // removed k-mers of all Random_N slots of one sequence (51 x 20 x 6 = 6120)
-constexpr int PC_DELTA = 6144;     // Bernoulli +-1 deltas of one sequence
+constexpr int PC_REM = 5888;       // removed k-mers of all Random_N slots of one sequence (51 x 20 x 6 = 6120)
+constexpr int PC_DELTA = 5120;     // Bernoulli +-1 deltas of one sequence
 constexpr int PC_MAXB = 8;         // Bernoulli slots per sequence
 
 struct alignas(16) PcCtx {
@@ -30,6 +51,12 @@ struct alignas(16) PcCtx {
     uint16_t rem[PC_REM];          // Random_N: removed k-mers, slot s at [rem_off[s]*K, +nbp*K), 0xFFFF = unused
     uint16_t delta[PC_DELTA];      // Bernoulli: kmer | ordinal << 12 | (add ? 0x8000 : 0)
     int dtot[PC_MAXS];             // change of the counted-window total per slot
+    float2 gy[PC_MAXS];            // per slot: (float total, RN(1/total))
+    long long grow[PC_MAXS];       // per slot: byte offset of the output row
+    unsigned long long job_dst[PC_MAXS];   // job j: byte offset of its output row | 1 when the job needs a new row
+    unsigned char job_slot[PC_MAXS];   // job j -> slot: dense slots first (slot order), then sparse/clean slots by total
+    unsigned char job_build[PC_MAXS];  // job j needs a rebuilt row (dense, or its total differs from job j - PC_NBUF's)
+    int n_dense;
     int n_delta;
     int defer;                     // item must be redone by the generic kernel
     int base_total;
@@ -38,16 +65,22 @@ struct alignas(16) PcCtx {
 
 struct PcSmem {
     PcCtx ctx[2];
+    alignas(16) float rowbuf[PC_NBUF][PC_F];
+    // scaler statistics (launch constants; global loads take ~3k cycles under the saturated write stream)
+    alignas(16) float smean[PC_F];
+    alignas(16) float sscale[PC_F];
+    alignas(16) float srscale[PC_F];
     // producer scratch
-    alignas(16) int hist[PC_F];
-    alignas(16) uint32_t sseq[SSEQ_CW + SSEQ_MW];
+    alignas(16) uint32_t sseq[2][PC_SSEQ_W];   // double-buffered: the TMA load of item i+1 lands while item i is prepared
     alignas(16) uint32_t list[LIST_CAP + 8];
     uint32_t gtabs[STABS][RNG_BLOCK];
     int scan[PC_HALF / 32 + 2];
     int seg_off[PC_MAXB + 1];
     int nvalid;
     int any_over;
-    long long next_item;
+    long long q_item[PC_QRING], q_seq[PC_QRING], q_c0[PC_QRING];   // dispatch ring written by the store thread: item, sequence, first chunk, length
+    int q_len[PC_QRING];
+    int q_head;                    // entries published so far
     // launch-uniform slot tables (built once)
     VarDesc svars[PC_MAXS];
     long long sout_off[PC_MAXS];
@@ -58,10 +91,65 @@ struct PcSmem {
     int bern_slot[PC_MAXB];        // slot of ordinal
     int n_bern, n_ent;
     // consumer side
-    alignas(16) uint32_t priv[PC_G * PC_PRIVW];
-    float2 gy[PC_MAXS];
-    long long grow[PC_MAXS];
+    alignas(16) uint32_t dscratch[PC_PRIVW];            // dense slots (builders): biased uint16 deltas, two bins per word
+    alignas(16) uint32_t sscratch[PC_FIXW * PC_SCRW];   // sparse jobs: one scratch per fix warp
+    // mbarriers.  Per row buffer: free (its last bulk copy has been read) -> built (builders, only when rebuilt)
+    // -> full (fix warp: the row is the job's row) -> bulk copy -> free
+    alignas(8) unsigned long long ctx_full[2], ctx_empty[2], row_free[PC_NBUF], row_built[PC_NBUF], row_full[PC_NBUF], seq_full[2];
 };
+
+// ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_hint(void* gdst, const void* ssrc, uint32_t bytes, unsigned long long policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ int ld_acquire_smem(const int* ptr) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(ptr)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_smem(int* ptr, int v) {
+    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(ptr)), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -96,55 +184,80 @@ template <int OUT>
 __device__ __noinline__ void pc_producer(PcSmem& sm, const ProfParams& p) {
     constexpr int K = PC_K;
     const int ptid = threadIdx.x - PC_HALF, lane = ptid & 31;
-    int b = 0;
     long long t_prev = p.phase_prof ? clock64() : 0;
     auto tick = [&](int id) {
         if (p.phase_prof && ptid == 0) { const long long t = clock64(); atomicAdd(p.phase_prof + id, (unsigned long long)(t - t_prev)); t_prev = t; }
     };
-    for (;;) {
+    // Items are dispatched by the store thread into a small ring (index, first chunk, length) and the
+    // packed words of item A_{i+1} are TMA-loaded into the other half of sseq while A_i is prepared:
+    // no global-load latency (~3k cycles under the saturated write stream) and no long-lived
+    // scoreboard sits on the producers' critical path.
+    auto half_count = [](int L) { return ((L + CHUNK_BASES - 1) / CHUNK_BASES) * 2; };
+    auto loads_seq = [&](long long item, int L) { const int nh = half_count(L); return item < p.n_items && nh <= 2 * SSEQ_CHUNKS && nh > 0; };
+    auto issue_seq_load = [&](int buf, long long item, long long c0, int L) {   // thread 0
+        const int nh = half_count(L);
+        if (!loads_seq(item, L)) return;
+        const uint32_t shift = (uint32_t)(c0 & 1);                              // mask words start 8 bytes into a 16-byte unit
+        const uint32_t cbytes = (uint32_t)nh * 8u, mbytes = ((uint32_t)nh * 4u + shift * 8u + 15u) & ~15u;
+        fence_proxy_async_all();                                                // earlier generic reads of this buffer are done
+        mbar_expect_tx(&sm.seq_full[buf], cbytes + mbytes);
+        bulk_load(sm.sseq[buf], p.codes + c0 * 4, cbytes, &sm.seq_full[buf]);
+        bulk_load(sm.sseq[buf] + SSEQ_CW, p.nmask + c0 * 2 - shift * 2, mbytes, &sm.seq_full[buf]);
+    };
+    long long cur_item, cur_seq, cur_c0;
+    int cur_L;
+    int n_loads[2] = {0, 0};       // TMA loads issued into each half of sseq (mbarrier phase bookkeeping)
+    while (ld_acquire_smem(&sm.q_head) < 1) __nanosleep(32);
+    cur_item = sm.q_item[0]; cur_seq = sm.q_seq[0]; cur_c0 = sm.q_c0[0]; cur_L = sm.q_len[0];
+    if (ptid == 0) issue_seq_load(0, cur_item, cur_c0, cur_L);
+    int cur_phase = 0;
+    if (loads_seq(cur_item, cur_L)) ++n_loads[0];
+    for (int it = 0;; ++it) {
+        const int b = it & 1;
         PcCtx& cx = sm.ctx[b];
-        if (ptid == 0) sm.next_item = (long long)atomicAdd(p.work_counter, 1ull);
-        bar_named(1, PC_HALF);
-        const long long item = sm.next_item;
+        while (ld_acquire_smem(&sm.q_head) < it + 2) __nanosleep(32);
+        const int qs = (it + 1) & (PC_QRING - 1);
+        const long long nx_item = sm.q_item[qs], nx_seq = sm.q_seq[qs], nx_c0 = sm.q_c0[qs];
+        const int nx_L = sm.q_len[qs];
+        if (ptid == 0) issue_seq_load(b ^ 1, nx_item, nx_c0, nx_L);            // A_{i+1}: lands during this iteration
+        const int nx_phase = n_loads[b ^ 1];
+        if (loads_seq(nx_item, nx_L)) ++n_loads[b ^ 1];
+        mbar_wait(&sm.ctx_empty[b], ((it >> 1) & 1) ^ 1);   // every consumer role is done with the previous occupant
+        tick(5);
+        const long long item = cur_item;
         if (item >= p.n_items) {
-            if (ptid == 0) cx.item = -1;
-            __syncthreads();
+            if (ptid == 0) { cx.item = -1; mbar_arrive(&sm.ctx_full[b]); }
             return;
         }
-        const long long seq = p.sidx ? (long long)p.sidx[item] : item;
-        const int L = p.len[seq];
-        const long long c0 = p.chunk_off[seq];
-        const uint32_t* gcodes = p.codes + c0 * 4;
-        const uint32_t* gnmask = p.nmask + c0 * 2;
+        const long long seq = cur_seq;
+        const int L = cur_L;
         const uint32_t seq_id = (uint32_t)(p.seq_id0 + seq);
-        const int nhalf = ((L + CHUNK_BASES - 1) / CHUNK_BASES) * 2;
+        const int nhalf = half_count(L);
         const bool fits = nhalf <= 2 * SSEQ_CHUNKS;
         if (ptid == 0) { cx.item = item; cx.defer = fits ? 0 : 1; cx.n_delta = 0; sm.nvalid = 0; sm.any_over = 0; }
         for (int i = ptid; i < PC_MAXS; i += PC_HALF) cx.dtot[i] = 0;
+        uint32_t* cw = reinterpret_cast<uint32_t*>(cx.clean16);   // two uint16 counters per word (counts <= 20 480)
         if (fits) {
-            // ---- count + stage the sequence ----
-            for (int i = ptid; i < PC_VEC; i += PC_HALF) reinterpret_cast<int4*>(sm.hist)[i] = make_int4(0, 0, 0, 0);
+            // ---- the staged sequence (TMA) -> count from shared memory ----
+            uint32_t* codes_w = sm.sseq[b];
+            uint32_t* nmask_w = sm.sseq[b] + SSEQ_CW + (int)(cur_c0 & 1) * 2;
+            reinterpret_cast<uint4*>(cw)[ptid] = make_uint4(0u, 0u, 0u, 0u);
+            if (nhalf > 0) mbar_wait(&sm.seq_full[b], cur_phase & 1);
+            if (ptid < 4) codes_w[nhalf * 2 + ptid] = 0u;
+            if (ptid < 2) nmask_w[nhalf + ptid] = 0xFFFFFFFFu;
             bar_named(1, PC_HALF);
+            const uint32_t* codes = codes_w;
+            const uint32_t* nmask = nmask_w;
             int nv = 0;
             for (int h = ptid; h < nhalf; h += PC_HALF) {
-                const uint2 w = __ldg(reinterpret_cast<const uint2*>(gcodes) + h);
-                reinterpret_cast<uint2*>(sm.sseq)[h] = w;
-                sm.sseq[SSEQ_CW + h] = gnmask[h];
-                nv += count_half<K>(gcodes, gnmask, h, w.x, w.y, [&](uint32_t kmer) { atomicAdd(&sm.hist[kmer], 1); });
+                const uint2 w = reinterpret_cast<const uint2*>(codes)[h];
+                nv += count_half<K>(codes, nmask, h, w.x, w.y, [&](uint32_t kmer) { atomicAdd(&cw[kmer >> 1], 1u << ((kmer & 1u) * 16u)); });
             }
-            if (ptid < 4) sm.sseq[nhalf * 2 + ptid] = 0u;
-            if (ptid < 2) sm.sseq[SSEQ_CW + nhalf + ptid] = 0xFFFFFFFFu;
             nv = warp_sum(nv);
             if (lane == 0 && nv) atomicAdd(&sm.nvalid, nv);
             bar_named(1, PC_HALF);
-            const uint32_t* codes = sm.sseq;
-            const uint32_t* nmask = sm.sseq + SSEQ_CW;
             tick(2);
             if (ptid == 0) cx.base_total = PC_F * p.pseudocount + sm.nvalid;
-            for (int vec = ptid; vec < PC_VEC; vec += PC_HALF) {
-                const int4 h = reinterpret_cast<const int4*>(sm.hist)[vec];
-                cx.clean16[vec] = make_uint2((uint32_t)h.x | ((uint32_t)h.y << 16), (uint32_t)h.z | ((uint32_t)h.w << 16));
-            }
             // ---- Random_N slots: draws (thread <-> slot, philox call) in rounds of LIST_CAP draws ----
             const int n_ent = sm.n_ent;   // <= LIST_CAP (host-checked)
             {
@@ -269,100 +382,335 @@ __device__ __noinline__ void pc_producer(PcSmem& sm, const ProfParams& p) {
             if (ptid == 0 && cx.n_delta > PC_DELTA) cx.defer = 1;
         }
         if (ptid == 0 && cx.defer) { atomicOr(p.status + item, 2); atomicAdd(p.work_counter + 1, 1ull); }
+        // ---- per-slot totals, output rows and the job order (dense slots first, then by window total) ----
+        const int S = p.S;
+        auto job_key = [&](int s) -> unsigned { return sm.kind_class[s] == 2 ? 0u : 0x40000000u | (unsigned)(cx.base_total + cx.dtot[s]); };
+        if (ptid < S) {
+            const int s = ptid;
+            const float ft2 = (float)(cx.base_total + cx.dtot[s]);
+            cx.gy[s] = make_float2(ft2, 1.0f / ft2);
+            cx.grow[s] = 4LL * (sm.sout_off[s] + item * p.out_stride);
+            const unsigned ks = job_key(s);
+            int rank = 0;
+            for (int t = 0; t < S; ++t) {
+                const unsigned kt = job_key(t);
+                rank += (kt < ks || (kt == ks && t < s)) ? 1 : 0;
+            }
+            cx.job_slot[rank] = (unsigned char)s;
+        }
+        if (ptid == 0) cx.n_dense = sm.n_bern;
+        bar_named(1, PC_HALF);
+        if (ptid < S) {
+            const int j = ptid, s = cx.job_slot[j];
+            const int nb = (j < PC_NBUF || sm.kind_class[s] == 2 || job_key(cx.job_slot[j - PC_NBUF]) != job_key(s)) ? 1 : 0;
+            cx.job_build[j] = (unsigned char)nb;
+            cx.job_dst[j] = (unsigned long long)cx.grow[s] | (unsigned long long)nb;
+        }
+        cur_item = nx_item; cur_seq = nx_seq; cur_c0 = nx_c0; cur_L = nx_L; cur_phase = nx_phase;
         tick(4);
-        __syncthreads();   // hand the context over to the consumers
-        tick(5);
-        b ^= 1;
+        bar_named(1, PC_HALF);
+        if (ptid == 0) mbar_arrive(&sm.ctx_full[b]);   // release: hand the context over to the consumers
     }
 }
 
+// the 4 finished output floats of one granule whose bins hold the exact float counts c01 / c23
+template <bool STD>
+__device__ __forceinline__ float4 finish_granule2(float2 c01, float2 c23, float2 fy, const Stats2& st) {
+    const float2 yy = make_float2(fy.y, fy.y), nt = make_float2(-fy.x, -fy.x);
+    float2 q01 = __fmul2_rn(c01, yy), q23 = __fmul2_rn(c23, yy);
+    const float2 r01 = __ffma2_rn(q01, nt, c01), r23 = __ffma2_rn(q23, nt, c23);
+    q01 = __ffma2_rn(r01, yy, q01); q23 = __ffma2_rn(r23, yy, q23);             // RN(count / total)
+    if (STD) {
+        const float2 d01 = __fadd2_rn(q01, st.nm01), d23 = __fadd2_rn(q23, st.nm23);
+        const float2 t01 = __fmul2_rn(d01, st.rs01), t23 = __fmul2_rn(d23, st.rs23);
+        const float2 e01 = __ffma2_rn(t01, st.ns01, d01), e23 = __ffma2_rn(t23, st.ns23, d23);
+        q01 = __ffma2_rn(e01, st.rs01, t01); q23 = __ffma2_rn(e23, st.rs23, t23);   // RN((q - mean) / scale)
+    }
+    return make_float4(q01.x, q01.y, q23.x, q23.y);
+}
+__device__ __forceinline__ void cvt_granule(uint2 pk, float magic, float2& c01, float2& c23) {
+    const float2 nmag = make_float2(-magic, -magic);
+    c01 = make_float2(__uint_as_float(__byte_perm(pk.x, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(pk.x, 0x4B000000u, 0x7432)));
+    c23 = make_float2(__uint_as_float(__byte_perm(pk.y, 0x4B000000u, 0x7410)), __uint_as_float(__byte_perm(pk.y, 0x4B000000u, 0x7432)));
+    c01 = __fadd2_rn(c01, nmag); c23 = __fadd2_rn(c23, nmag);                    // exact count + pseudocount
+}
+
+// development aid (IDL_PHASE_PROF=1): one thread of a role attributes its elapsed cycles to phases
+struct PcClock {
+    unsigned long long* base;
+    long long t_prev;
+    __device__ __forceinline__ void start(unsigned long long* b) { base = b; t_prev = b ? clock64() : 0; }
+    __device__ __forceinline__ void tick(int id) {
+        if (base) { const long long t = clock64(); atomicAdd(base + id, (unsigned long long)(t - t_prev)); t_prev = t; }
+    }
+};
+
+// scaler statistics of one granule from shared memory, ready for the packed ops
+template <bool STD>
+__device__ __forceinline__ Stats2 smem_stats2(const PcSmem& sm, int vec) {
+    Stats2 s;
+    s.nm01 = s.nm23 = make_float2(0.f, 0.f);
+    s.ns01 = s.ns23 = make_float2(-1.f, -1.f);
+    s.rs01 = s.rs23 = make_float2(1.f, 1.f);
+    if (STD) {
+        const float4 m = reinterpret_cast<const float4*>(sm.smean)[vec];
+        const float4 sc = reinterpret_cast<const float4*>(sm.sscale)[vec];
+        const float4 rs = reinterpret_cast<const float4*>(sm.srscale)[vec];
+        s.nm01 = make_float2(-m.x, -m.y); s.nm23 = make_float2(-m.z, -m.w);
+        s.ns01 = make_float2(-sc.x, -sc.y); s.ns23 = make_float2(-sc.z, -sc.w);
+        s.rs01 = make_float2(rs.x, rs.y); s.rs23 = make_float2(rs.z, rs.w);
+    }
+    return s;
+}
+
+// BUILDERS (warps 0..7): finished rows into the ring of row buffers
 template <int OUT>
-__device__ __forceinline__ void pc_consumer(PcSmem& sm, const ProfParams& p) {
-    constexpr int K = PC_K, VEC = PC_VEC, VPT = PC_VPT, NT = PC_HALF, HG = PC_HG, PRIVW = PC_PRIVW;
-    constexpr int ESZ = 4;
-    constexpr int TPH = NT / HG;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+__device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
+    constexpr int NB = PC_NBLD, GPT = PC_VEC / NB;   // granules per thread
+    constexpr bool STD = OUT == IDL_OUT_STD_F32;
+    const int tid = threadIdx.x;
     const float magic = 8388608.0f - (float)p.pseudocount;
-    uint32_t* priv = sm.priv;
-    // scaler statistics of this thread's two granules: fixed for the whole launch, kept in registers
-    Stats2 st[VPT];
-#pragma unroll
-    for (int vv = 0; vv < VPT; ++vv) st[vv] = load_stats2(p.mean, p.scale, p.rscale, tid + vv * NT, OUT == IDL_OUT_STD_F32);
-    int b = 0;
-    long long t_prev = p.phase_prof ? clock64() : 0;
-    auto tick = [&](int id) {
-        if (p.phase_prof && tid == 0) { const long long t = clock64(); atomicAdd(p.phase_prof + id, (unsigned long long)(t - t_prev)); t_prev = t; }
-    };
-    for (;;) {
-        tick(1);
-        __syncthreads();   // context b is ready
-        tick(0);
+    int gj0 = 0;                                     // jobs of the previous sequences (CTA lifetime)
+    PcClock clk;
+    clk.start(tid == 0 ? p.phase_prof : nullptr);
+    for (int it = 0;; ++it) {
+        const int b = it & 1;
+        clk.tick(13);
+        mbar_wait(&sm.ctx_full[b], (it >> 1) & 1);
+        clk.tick(12);
         PcCtx& cx = sm.ctx[b];
-        b ^= 1;
         const long long item = cx.item;
         if (item < 0) return;
-        if (cx.defer) continue;
-        const int S = p.S;
-        const int base_total = cx.base_total;
-        // per-slot totals / output rows, private copies
-        for (int s = tid; s < S; s += NT) {
-            const float ft2 = (float)(base_total + cx.dtot[s]);
-            sm.gy[s] = make_float2(ft2, 1.0f / ft2);
-            sm.grow[s] = (long long)ESZ * (sm.sout_off[s] + item * p.out_stride);
-        }
+        if (!cx.defer) {
+            const int S = p.S;
+            uint2 ck[GPT];
+            float2 c01[GPT], c23[GPT];               // exact float counts (+ pseudocount) of this thread's bins
 #pragma unroll
-        for (int vv = 0; vv < VPT; ++vv) {
-            const int vec = tid + vv * NT;
-            const uint2 pk = cx.clean16[vec];
+            for (int j = 0; j < GPT; ++j) {
+                ck[j] = cx.clean16[tid + j * NB];
+                cvt_granule(ck[j], magic, c01[j], c23[j]);
+            }
+            const int n_delta = cx.n_delta;
+            for (int j = 0; j < S; ++j) {
+                const int buf = (gj0 + j) % PC_NBUF, use = (gj0 + j) / PC_NBUF;
+                if (!cx.job_build[j]) {
+                    // nothing to build, but every use of the buffer is followed: a parity wait can only tell adjacent phases apart
+                    mbar_wait(&sm.row_free[buf], (use & 1) ^ 1);
+                    continue;
+                }
+                const int s = cx.job_slot[j];
+                const float2 fy = cx.gy[s];
+                const bool dense = sm.kind_class[s] == 2;
+                if (dense) {
+                    // patch this slot's deltas into the scratch (previous readers are past their barrier)
+                    const uint32_t ord = (uint32_t)sm.bern_ord[s];
+                    bar_named(2, NB);
+                    for (int r = tid; r < n_delta; r += NB) {
+                        const uint32_t e = cx.delta[r];
+                        if (((e >> 12) & 7u) == ord) upd16(sm.dscratch, e & 0xFFFu, (e & 0x8000u) ? 1 : -1);
+                    }
+                    bar_named(2, NB);
+                }
+                clk.tick(13);
+                mbar_wait(&sm.row_free[buf], (use & 1) ^ 1);   // the bulk copy of the buffer's previous job has been read
+                clk.tick(14);
+                float4* row = reinterpret_cast<float4*>(sm.rowbuf[buf]);
 #pragma unroll
-            for (int c = 0; c < PC_G; ++c) reinterpret_cast<uint2*>(priv + c * PRIVW)[vec] = pk;
+                for (int g = 0; g < GPT; ++g) {
+                    const int vec = tid + g * NB;
+                    float2 d01 = c01[g], d23 = c23[g];
+                    if (dense) {   // own bins = clean + delta; the scratch is reset on the way
+                        uint2* scr = reinterpret_cast<uint2*>(sm.dscratch);
+                        const uint2 w = scr[vec];
+                        scr[vec] = make_uint2(PC_BIAS2, PC_BIAS2);
+                        cvt_granule(make_uint2(ck[g].x + w.x - PC_BIAS2, ck[g].y + w.y - PC_BIAS2), magic, d01, d23);
+                    }
+                    row[vec] = finish_granule2<STD>(d01, d23, fy, smem_stats2<STD>(sm, vec));
+                }
+                fence_proxy_async_smem();              // generic-proxy writes -> visible to the TMA engine
+                mbar_arrive(&sm.row_built[buf]);
+            }
+            gj0 += S;
         }
-        bar_named(2, NT);
-        const int n_delta = cx.n_delta;
-        auto patch_half = [&](int h0, int hs, int set) {
-            const int c = tid / TPH;
-            if (c < hs && sm.kind_class[h0 + c] == 1) {
-                const int n = sm.nbp[h0 + c] * K;
-                const uint16_t* rl = cx.rem + sm.rem_off[h0 + c] * K;
-                uint32_t* privc = priv + (set * HG + c) * PRIVW;
-                for (int r = tid - c * TPH; r < n; r += TPH) {
-                    const uint32_t km = rl[r];
-                    if (km != 0xFFFFu) upd16(privc, km, -1);
+        mbar_arrive(&sm.ctx_empty[b]);
+    }
+}
+
+// STORE thread (warp 15, lane 0): dispatches the items and writes each job's row with one TMA bulk copy
+__device__ __forceinline__ void pc_store(PcSmem& sm, const ProfParams& p) {
+    int gj = 0;
+    const unsigned long long pol_ef = policy_evict_first();
+    // ---- dispatcher.  The atomic and the dependent loads of (sequence, length, first chunk) are two global
+    // round trips; they are issued one iteration before their results are needed, and a stall here is absorbed
+    // by the rows the other roles have already finished.
+    auto load_info = [&](long long item, long long& seq, long long& c0, int& L) {
+        seq = item; c0 = 0; L = 0;
+        if (item < p.n_items) {
+            if (p.sidx) seq = (long long)p.sidx[item];
+            L = p.len[seq];
+            c0 = p.chunk_off[seq];
+        }
+    };
+    auto publish = [&](int idx, long long item, long long seq, long long c0, int L) {
+        const int qs = idx & (PC_QRING - 1);
+        sm.q_item[qs] = item; sm.q_seq[qs] = seq; sm.q_c0[qs] = c0; sm.q_len[qs] = L;
+        st_release_smem(&sm.q_head, idx + 1);
+    };
+    {
+        long long it4[4], sq4[4], c4[4];
+        int l4[4];
+        for (int i = 0; i < 4; ++i) it4[i] = (long long)atomicAdd(p.work_counter, 1ull);
+        for (int i = 0; i < 4; ++i) load_info(it4[i], sq4[i], c4[i], l4[i]);
+        for (int i = 0; i < 4; ++i) publish(i, it4[i], sq4[i], c4[i], l4[i]);
+    }
+    long long a_item = (long long)atomicAdd(p.work_counter, 1ull);   // index 4
+    long long b_item = 0, b_seq = 0, b_c0 = 0;
+    int b_L = 0;
+    PcClock clk;
+    clk.start(p.phase_prof);
+    for (int it = 0;; ++it) {
+        const int b = it & 1;
+        if (it >= 1) publish(it + 3, b_item, b_seq, b_c0, b_L);      // loaded during the previous iteration
+        b_item = a_item;
+        load_info(b_item, b_seq, b_c0, b_L);                          // index it + 4
+        a_item = (long long)atomicAdd(p.work_counter, 1ull);          // index it + 5
+        clk.tick(6);
+        mbar_wait(&sm.ctx_full[b], (it >> 1) & 1);
+        clk.tick(0);
+        PcCtx& cx = sm.ctx[b];
+        const long long item = cx.item;
+        if (item < 0) break;
+        if (!cx.defer) {
+            const int S = p.S;
+            unsigned long long jd_next = cx.job_dst[0];
+            for (int j = 0; j < S; ++j, ++gj) {
+                const unsigned long long jd = jd_next;
+                if (j + 1 < S) jd_next = cx.job_dst[j + 1];
+                const int buf = gj % PC_NBUF;
+                clk.tick(6);
+                mbar_wait(&sm.row_full[buf], (gj / PC_NBUF) & 1);
+                clk.tick(1);
+                unsigned char* dst = reinterpret_cast<unsigned char*>(p.out) + (jd & ~15ull);
+                if (p.dbg & 4) bulk_store_hint(dst, sm.rowbuf[buf], PC_F * 4, pol_ef);
+                else bulk_store(dst, sm.rowbuf[buf], PC_F * 4);
+                bulk_commit();
+                if (gj > 0) {
+                    bulk_wait_read<1>();               // everything but the copy just issued has left shared memory
+                    clk.tick(7);
+                    mbar_arrive(&sm.row_free[(gj - 1) % PC_NBUF]);
                 }
             }
-            // Bernoulli deltas of slots that live in this half-group
-            bool any = false;
-            for (int c2 = 0; c2 < hs; ++c2) any = any || sm.kind_class[h0 + c2] == 2;
-            if (any) {
-                for (int r = tid; r < n_delta; r += NT) {
-                    const uint32_t e = cx.delta[r];
-                    const int slot = sm.bern_slot[(e >> 12) & 7u];
-                    if (slot >= h0 && slot < h0 + hs) upd16(priv + (set * HG + slot - h0) * PRIVW, e & 0xFFFu, (e & 0x8000u) ? 1 : -1);
-                }
-            }
-        };
-        const int nh = (S + HG - 1) / HG;
-        patch_half(0, S < HG ? S : HG, 0);
-        bar_named(2, NT);
-        for (int h = 0; h < nh; ++h) {
-            const int cur = h & 1, h0 = h * HG;
-            const int hs = S - h0 < HG ? S - h0 : HG;
-            if (h + 1 < nh) patch_half(h0 + HG, S - h0 - HG < HG ? S - h0 - HG : HG, cur ^ 1);
-            const uint2 clean0 = cx.clean16[tid], clean1 = cx.clean16[tid + NT];
-#pragma unroll 2
-            for (int c = 0; c < hs; ++c) {
-                const float2 fy = sm.gy[h0 + c];
-                unsigned char* row = reinterpret_cast<unsigned char*>(p.out) + sm.grow[h0 + c];
-                uint2* src = reinterpret_cast<uint2*>(priv + (cur * HG + c) * PRIVW);
-                const uint2 pk0 = src[tid], pk1 = src[tid + NT];
-                src[tid] = clean0;
-                src[tid + NT] = clean1;
-                emit_granule_u16x2<OUT == IDL_OUT_STD_F32>(row, tid, pk0, magic, fy, st[0]);
-                emit_granule_u16x2<OUT == IDL_OUT_STD_F32>(row, tid + NT, pk1, magic, fy, st[1]);
-            }
-            bar_named(2, NT);
         }
-        (void)lane; (void)wid;
+        mbar_arrive(&sm.ctx_empty[b]);
+    }
+    bulk_wait_read<0>();
+    bulk_wait<0>();
+}
+
+// FIX warps (warps 8 .. 8+PC_NBUF-1, one per row buffer): make the buffer's row the job's row.  Subtract the
+// job's removals into the warp's scratch (shared atomics on biased uint8 fields), claim each touched scratch
+// word with atomicExch (the first visitor owns its four bins and resets it — duplicate k-mers in the removal
+// list are harmless); once the buffer's previous bulk copy has been read, put the template value back into the
+// bins the previous job changed (unless the builders rebuilt the row) and write this job's changed bins.
+template <int OUT>
+__device__ __forceinline__ void pc_fix(PcSmem& sm, const ProfParams& p) {
+    constexpr int K = PC_K;
+    constexpr bool STD = OUT == IDL_OUT_STD_F32;
+    constexpr int RPL = 4;                             // removal entries per lane (<= 127 removals per job, host-checked)
+    const int ftid = threadIdx.x - PC_NBLD, fw = ftid >> 5, lane = ftid & 31;
+    if (fw >= PC_NBUF) {                               // spare warps: only the context hand-shake
+        for (int it = 0;; ++it) {
+            const int b = it & 1;
+            mbar_wait(&sm.ctx_full[b], (it >> 1) & 1);
+            if (sm.ctx[b].item < 0) return;
+            mbar_arrive(&sm.ctx_empty[b]);
+        }
+    }
+    uint32_t* scr = sm.sscratch + fw * PC_SCRW;
+    float* row = sm.rowbuf[fw];
+    int gj0 = 0, n_built = 0;                          // CTA lifetime: jobs of the previous sequences, rebuilds of this buffer
+    uint32_t km_prev[RPL];                             // the bins the previous job of this buffer changed (0xFFFF: none)
+#pragma unroll
+    for (int u = 0; u < RPL; ++u) km_prev[u] = 0xFFFFu;
+    PcClock clk;
+    clk.start(ftid == 0 ? p.phase_prof : nullptr);
+    for (int it = 0;; ++it) {
+        const int b = it & 1;
+        clk.tick(11);
+        mbar_wait(&sm.ctx_full[b], (it >> 1) & 1);
+        clk.tick(8);
+        PcCtx& cx = sm.ctx[b];
+        const long long item = cx.item;
+        if (item < 0) return;
+        if (!cx.defer) {
+            const int S = p.S;
+            const uint16_t* clean_h = reinterpret_cast<const uint16_t*>(cx.clean16);
+            // output value of one bin whose clean count changes by d (every lane owns exactly its own entries, so the
+            // RPL evaluations of a lane are independent and the warp does not diverge)
+            auto value = [&](uint32_t bin, int d, float2 fy) -> float {
+                float q = div_rn((float)((int)clean_h[bin] + d + p.pseudocount), fy.x, fy.y);
+                if (STD) q = div_rn(q - sm.smean[bin], sm.sscale[bin], sm.srscale[bin]);
+                return q;
+            };
+            int j = (fw - gj0 % PC_NBUF + PC_NBUF) % PC_NBUF;      // first job of this sequence that lands in this buffer
+            for (; j < S; j += PC_NBUF) {
+                const int use = (gj0 + j) / PC_NBUF;
+                const int s = cx.job_slot[j];
+                const int n = sm.nbp[s] * K;           // 0 for clean and dense slots
+                const uint16_t* rl = cx.rem + sm.rem_off[s] * K;
+                const float2 fy = cx.gy[s];
+                const bool rebuilt = cx.job_build[j] != 0;
+                uint32_t km[RPL];
+                int d[RPL];
+#pragma unroll
+                for (int u = 0; u < RPL; ++u) {
+                    const int r = lane + 32 * u;
+                    km[u] = r < n ? (uint32_t)rl[r] : 0xFFFFu;
+                }
+                // multiplicity of each removed k-mer within this job: subtract into the scratch, read back, reset
+#pragma unroll
+                for (int u = 0; u < RPL; ++u)
+                    if (km[u] != 0xFFFFu) atomicSub(scr + (km[u] >> 2), 1u << ((km[u] & 3u) * 8u));
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < RPL; ++u)
+                    d[u] = km[u] != 0xFFFFu ? (int)((scr[km[u] >> 2] >> ((km[u] & 3u) * 8u)) & 0xFFu) - 0x80 : 0;
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < RPL; ++u)
+                    if (km[u] != 0xFFFFu) scr[km[u] >> 2] = PC_BIAS4;
+                float vnew[RPL];
+#pragma unroll
+                for (int u = 0; u < RPL; ++u) vnew[u] = km[u] != 0xFFFFu ? value(km[u], d[u], fy) : 0.f;
+                clk.tick(9);
+                if (rebuilt) {
+                    mbar_wait(&sm.row_built[fw], n_built & 1);     // the builders wrote a fresh row (they waited for row_free)
+                    ++n_built;
+                } else {
+                    // same window total as the buffer's previous job: put the template value back where that job changed it
+                    float vold[RPL];
+#pragma unroll
+                    for (int u = 0; u < RPL; ++u) vold[u] = km_prev[u] != 0xFFFFu ? value(km_prev[u], 0, fy) : 0.f;
+                    mbar_wait(&sm.row_free[fw], (use & 1) ^ 1);    // the bulk copy of the buffer's previous job has been read
+#pragma unroll
+                    for (int u = 0; u < RPL; ++u)
+                        if (km_prev[u] != 0xFFFFu) row[km_prev[u]] = vold[u];
+                    __syncwarp();
+                }
+                clk.tick(10);
+#pragma unroll
+                for (int u = 0; u < RPL; ++u)
+                    if (km[u] != 0xFFFFu) row[km[u]] = vnew[u];
+#pragma unroll
+                for (int u = 0; u < RPL; ++u) km_prev[u] = km[u];
+                fence_proxy_async_smem();              // generic-proxy writes -> visible to the TMA engine
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.row_full[fw]);
+                clk.tick(11);
+            }
+            gj0 += S;
+        }
+        mbar_arrive(&sm.ctx_empty[b]);
     }
 }
 
@@ -375,6 +723,10 @@ __global__ void __launch_bounds__(PC_NT, 1) profiles_pc_kernel(const ProfParams 
     for (int i = tid; i < p.n_vars; i += PC_NT) sm.svars[i] = p.vars[i];
     for (int i = tid; i < p.S; i += PC_NT) sm.sout_off[i] = p.out_off[i];
     for (int i = tid; i < STABS * RNG_BLOCK; i += PC_NT) (&sm.gtabs[0][0])[i] = i < p.n_tabs * RNG_BLOCK ? p.gtab[i] : 0u;
+    if (OUT == IDL_OUT_STD_F32)
+        for (int i = tid; i < PC_F; i += PC_NT) { sm.smean[i] = p.mean[i]; sm.sscale[i] = p.scale[i]; sm.srscale[i] = p.rscale[i]; }
+    for (int i = tid; i < PC_PRIVW; i += PC_NT) sm.dscratch[i] = PC_BIAS2;
+    for (int i = tid; i < PC_FIXW * PC_SCRW; i += PC_NT) sm.sscratch[i] = PC_BIAS4;
     __syncthreads();
     if (tid == 0) {
         int ent = 0, nb = 0;
@@ -392,10 +744,18 @@ __global__ void __launch_bounds__(PC_NT, 1) profiles_pc_kernel(const ProfParams 
         }
         sm.n_ent = ent;
         sm.n_bern = nb;
+        sm.q_head = 0;
+        for (int i = 0; i < 2; ++i) mbar_init(&sm.seq_full[i], 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.ctx_full[i], 1); mbar_init(&sm.ctx_empty[i], PC_NBLD + PC_NFIX + 1); }
+        for (int i = 0; i < PC_NBUF; ++i) { mbar_init(&sm.row_free[i], 1); mbar_init(&sm.row_built[i], PC_NBLD); mbar_init(&sm.row_full[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (tid >= PC_HALF) pc_producer<OUT>(sm, p);
-    else pc_consumer<OUT>(sm, p);
+    else if (tid < PC_NBLD) pc_builder<OUT>(sm, p);
+    else if (tid < PC_NBLD + PC_NFIX) pc_fix<OUT>(sm, p);
+    else if (tid == PC_NBLD + PC_NFIX) pc_store(sm, p);
 }
 
 }  // namespace idl
+static_assert(sizeof(idl::PcSmem) <= 232448, "PcSmem exceeds the 227 KB dynamic shared memory limit");
