@@ -65,6 +65,7 @@ struct alignas(16) PcCtx {
 
 struct PcSmem {
     PcCtx ctx[2];
+    ProfParams params;             // the producers (an out-of-line function) read the launch parameters from here, not from a local-memory copy
     alignas(16) float rowbuf[PC_NBUF][PC_F];
     // scaler statistics (launch constants; global loads take ~3k cycles under the saturated write stream)
     alignas(16) float smean[PC_F];
@@ -181,7 +182,8 @@ __device__ __forceinline__ int pc_exscan(int v, int* scratch, int* total, int pt
 }
 
 template <int OUT>
-__device__ __noinline__ void pc_producer(PcSmem& sm, const ProfParams& p) {
+__device__ __noinline__ void pc_producer(PcSmem& sm) {
+    const ProfParams& p = sm.params;
     constexpr int K = PC_K;
     const int ptid = threadIdx.x - PC_HALF, lane = ptid & 31;
     long long t_prev = p.phase_prof ? clock64() : 0;
@@ -199,19 +201,19 @@ __device__ __noinline__ void pc_producer(PcSmem& sm, const ProfParams& p) {
         if (!loads_seq(item, L)) return;
         const uint32_t shift = (uint32_t)(c0 & 1);                              // mask words start 8 bytes into a 16-byte unit
         const uint32_t cbytes = (uint32_t)nh * 8u, mbytes = ((uint32_t)nh * 4u + shift * 8u + 15u) & ~15u;
-        fence_proxy_async_all();                                                // earlier generic reads of this buffer are done
+        fence_proxy_async_smem();                                               // earlier generic reads of this buffer are done
         mbar_expect_tx(&sm.seq_full[buf], cbytes + mbytes);
         bulk_load(sm.sseq[buf], p.codes + c0 * 4, cbytes, &sm.seq_full[buf]);
         bulk_load(sm.sseq[buf] + SSEQ_CW, p.nmask + c0 * 2 - shift * 2, mbytes, &sm.seq_full[buf]);
     };
     long long cur_item, cur_seq, cur_c0;
     int cur_L;
-    int n_loads[2] = {0, 0};       // TMA loads issued into each half of sseq (mbarrier phase bookkeeping)
+    int n_loads0 = 0, n_loads1 = 0; // TMA loads issued into each half of sseq (mbarrier phase bookkeeping)
     while (ld_acquire_smem(&sm.q_head) < 1) __nanosleep(32);
     cur_item = sm.q_item[0]; cur_seq = sm.q_seq[0]; cur_c0 = sm.q_c0[0]; cur_L = sm.q_len[0];
     if (ptid == 0) issue_seq_load(0, cur_item, cur_c0, cur_L);
     int cur_phase = 0;
-    if (loads_seq(cur_item, cur_L)) ++n_loads[0];
+    if (loads_seq(cur_item, cur_L)) ++n_loads0;
     for (int it = 0;; ++it) {
         const int b = it & 1;
         PcCtx& cx = sm.ctx[b];
@@ -220,8 +222,8 @@ __device__ __noinline__ void pc_producer(PcSmem& sm, const ProfParams& p) {
         const long long nx_item = sm.q_item[qs], nx_seq = sm.q_seq[qs], nx_c0 = sm.q_c0[qs];
         const int nx_L = sm.q_len[qs];
         if (ptid == 0) issue_seq_load(b ^ 1, nx_item, nx_c0, nx_L);            // A_{i+1}: lands during this iteration
-        const int nx_phase = n_loads[b ^ 1];
-        if (loads_seq(nx_item, nx_L)) ++n_loads[b ^ 1];
+        const int nx_phase = b ? n_loads0 : n_loads1;
+        if (loads_seq(nx_item, nx_L)) { if (b) ++n_loads0; else ++n_loads1; }
         mbar_wait(&sm.ctx_empty[b], ((it >> 1) & 1) ^ 1);   // every consumer role is done with the previous occupant
         tick(5);
         const long long item = cur_item;
@@ -385,18 +387,25 @@ __device__ __noinline__ void pc_producer(PcSmem& sm, const ProfParams& p) {
         // ---- per-slot totals, output rows and the job order (dense slots first, then by window total) ----
         const int S = p.S;
         auto job_key = [&](int s) -> unsigned { return sm.kind_class[s] == 2 ? 0u : 0x40000000u | (unsigned)(cx.base_total + cx.dtot[s]); };
-        if (ptid < S) {
-            const int s = ptid;
-            const float ft2 = (float)(cx.base_total + cx.dtot[s]);
-            cx.gy[s] = make_float2(ft2, 1.0f / ft2);
-            cx.grow[s] = 4LL * (sm.sout_off[s] + item * p.out_stride);
-            const unsigned ks = job_key(s);
+        {   // rank of every slot in the job order: 8 lanes per slot
+            const int s = ptid >> 3, part = ptid & 7;
+            const bool on = s < S;
+            const unsigned ks = on ? job_key(s) : 0u;
             int rank = 0;
-            for (int t = 0; t < S; ++t) {
-                const unsigned kt = job_key(t);
-                rank += (kt < ks || (kt == ks && t < s)) ? 1 : 0;
+            if (on)
+                for (int t = part; t < S; t += 8) {
+                    const unsigned kt = job_key(t);
+                    rank += (kt < ks || (kt == ks && t < s)) ? 1 : 0;
+                }
+            rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+            rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+            rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+            if (on && part == 0) {
+                const float ft2 = (float)(cx.base_total + cx.dtot[s]);
+                cx.gy[s] = make_float2(ft2, 1.0f / ft2);
+                cx.grow[s] = 4LL * (sm.sout_off[s] + item * p.out_stride);
+                cx.job_slot[rank] = (unsigned char)s;
             }
-            cx.job_slot[rank] = (unsigned char)s;
         }
         if (ptid == 0) cx.n_dense = sm.n_bern;
         bar_named(1, PC_HALF);
@@ -472,7 +481,7 @@ __device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
     const float magic = 8388608.0f - (float)p.pseudocount;
     int gj0 = 0;                                     // jobs of the previous sequences (CTA lifetime)
     PcClock clk;
-    clk.start(tid == 0 ? p.phase_prof : nullptr);
+    clk.start(tid == 0 && (p.dbg & 16) ? p.phase_prof : nullptr);
     for (int it = 0;; ++it) {
         const int b = it & 1;
         clk.tick(13);
@@ -567,7 +576,7 @@ __device__ __forceinline__ void pc_store(PcSmem& sm, const ProfParams& p) {
     long long b_item = 0, b_seq = 0, b_c0 = 0;
     int b_L = 0;
     PcClock clk;
-    clk.start(p.phase_prof);
+    clk.start((p.dbg & 48) ? p.phase_prof : nullptr);
     for (int it = 0;; ++it) {
         const int b = it & 1;
         if (it >= 1) publish(it + 3, b_item, b_seq, b_c0, b_L);      // loaded during the previous iteration
@@ -633,7 +642,7 @@ __device__ __forceinline__ void pc_fix(PcSmem& sm, const ProfParams& p) {
 #pragma unroll
     for (int u = 0; u < RPL; ++u) km_prev[u] = 0xFFFFu;
     PcClock clk;
-    clk.start(ftid == 0 ? p.phase_prof : nullptr);
+    clk.start(ftid == 0 && (p.dbg & 16) ? p.phase_prof : nullptr);
     for (int it = 0;; ++it) {
         const int b = it & 1;
         clk.tick(11);
@@ -719,6 +728,7 @@ __global__ void __launch_bounds__(PC_NT, 1) profiles_pc_kernel(const ProfParams 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PcSmem& sm = *reinterpret_cast<PcSmem*>(smem_raw);
     const int tid = threadIdx.x;
+    if (tid == 0) sm.params = p;
     // launch-uniform slot tables
     for (int i = tid; i < p.n_vars; i += PC_NT) sm.svars[i] = p.vars[i];
     for (int i = tid; i < p.S; i += PC_NT) sm.sout_off[i] = p.out_off[i];
@@ -751,7 +761,7 @@ __global__ void __launch_bounds__(PC_NT, 1) profiles_pc_kernel(const ProfParams 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid >= PC_HALF) pc_producer<OUT>(sm, p);
+    if (tid >= PC_HALF) pc_producer<OUT>(sm);
     else if (tid < PC_NBLD) pc_builder<OUT>(sm, p);
     else if (tid < PC_NBLD + PC_NFIX) pc_fix<OUT>(sm, p);
     else if (tid == PC_NBLD + PC_NFIX) pc_store(sm, p);
