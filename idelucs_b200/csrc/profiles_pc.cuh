@@ -500,6 +500,10 @@ __device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
                 cvt_granule(ck[j], magic, c01[j], c23[j]);
             }
             const int n_delta = cx.n_delta;
+            unsigned key_cur = 0u;                   // window total (float bits) the register row val[] holds; 0: none
+            float4 val[GPT];
+#pragma unroll
+            for (int g = 0; g < GPT; ++g) val[g] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int j = 0; j < S; ++j) {
                 const int buf = (gj0 + j) % PC_NBUF, use = (gj0 + j) / PC_NBUF;
                 if (!cx.job_build[j]) {
@@ -520,22 +524,30 @@ __device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
                     }
                     bar_named(2, NB);
                 }
+                // The row's values are computed BEFORE the buffer is free (only the stores sit on the buffer's critical
+                // path) and kept in registers: consecutive rebuilds with the same window total cost four stores per thread.
+                const unsigned key_j = dense ? 0u : __float_as_uint(fy.x);
+                if (dense || key_j != key_cur) {
+                    key_cur = key_j;
+#pragma unroll
+                    for (int g = 0; g < GPT; ++g) {
+                        const int vec = tid + g * NB;
+                        float2 d01 = c01[g], d23 = c23[g];
+                        if (dense) {   // own bins = clean + delta; the scratch is reset on the way
+                            uint2* scr = reinterpret_cast<uint2*>(sm.dscratch);
+                            const uint2 w = scr[vec];
+                            scr[vec] = make_uint2(PC_BIAS2, PC_BIAS2);
+                            cvt_granule(make_uint2(ck[g].x + w.x - PC_BIAS2, ck[g].y + w.y - PC_BIAS2), magic, d01, d23);
+                        }
+                        val[g] = finish_granule2<STD>(d01, d23, fy, smem_stats2<STD>(sm, vec));
+                    }
+                }
                 clk.tick(13);
                 mbar_wait(&sm.row_free[buf], (use & 1) ^ 1);   // the bulk copy of the buffer's previous job has been read
                 clk.tick(14);
                 float4* row = reinterpret_cast<float4*>(sm.rowbuf[buf]);
 #pragma unroll
-                for (int g = 0; g < GPT; ++g) {
-                    const int vec = tid + g * NB;
-                    float2 d01 = c01[g], d23 = c23[g];
-                    if (dense) {   // own bins = clean + delta; the scratch is reset on the way
-                        uint2* scr = reinterpret_cast<uint2*>(sm.dscratch);
-                        const uint2 w = scr[vec];
-                        scr[vec] = make_uint2(PC_BIAS2, PC_BIAS2);
-                        cvt_granule(make_uint2(ck[g].x + w.x - PC_BIAS2, ck[g].y + w.y - PC_BIAS2), magic, d01, d23);
-                    }
-                    row[vec] = finish_granule2<STD>(d01, d23, fy, smem_stats2<STD>(sm, vec));
-                }
+                for (int g = 0; g < GPT; ++g) row[tid + g * NB] = val[g];
                 fence_proxy_async_smem();              // generic-proxy writes -> visible to the TMA engine
                 mbar_arrive(&sm.row_built[buf]);
             }
