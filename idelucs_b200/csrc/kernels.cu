@@ -1315,7 +1315,7 @@ static int profiles_impl(const uint32_t* d_codes, const uint32_t* d_nmask, const
             else if (d.kind == IDL_KIND_RANDOM_N) { if (d.n_bp * PC_K > 127) pc_ok = false; else if (d.n_bp > 0) n_ent += d.n_bp; }
             else if (d.kind != IDL_KIND_CLEAN) ++n_bern;
         }
-        if (n_bern > PC_MAXB || n_ent > LIST_CAP || n_ent * PC_K > PC_REM) pc_ok = false;
+        if (n_bern > PC_DENSE || n_ent > LIST_CAP || n_ent * PC_K > PC_REM) pc_ok = false;
         // TMA bulk copies: 16-byte aligned rows
         if (((uintptr_t)d_out & 15) || (out_stride & 3) || ((uintptr_t)d_codes & 15) || ((uintptr_t)d_nmask & 15)) pc_ok = false;
         for (int v = 0; v < S && pc_ok; ++v) if (out_off[v] & 3) pc_ok = false;

@@ -44,12 +44,12 @@ constexpr uint32_t PC_BIAS2 = 0x80008000u;
 constexpr int PC_MAXS = 64;        // variant slots per sequence
 constexpr int PC_REM = 5888;       // removed k-mers of all Random_N slots of one sequence (51 x 20 x 6 = 6120)
 constexpr int PC_DELTA = 5120;     // Bernoulli +-1 deltas of one sequence
-constexpr int PC_MAXB = 8;         // Bernoulli slots per sequence
+constexpr int PC_MAXB = 8;         // Bernoulli slots per sequence (producer tables)
+constexpr int PC_DENSE = 3;        // ... of which the builders can take (one delta scratch each; the reference schedule has 3)
 
 struct alignas(16) PcCtx {
     uint2 clean16[PC_VEC];         // packed clean histogram
     uint16_t rem[PC_REM];          // Random_N: removed k-mers, slot s at [rem_off[s]*K, +nbp*K), 0xFFFF = unused
-    uint16_t delta[PC_DELTA];      // Bernoulli: kmer | ordinal << 12 | (add ? 0x8000 : 0)
     int dtot[PC_MAXS];             // change of the counted-window total per slot
     float2 gy[PC_MAXS];            // per slot: (float total, RN(1/total))
     long long grow[PC_MAXS];       // per slot: byte offset of the output row
@@ -70,10 +70,13 @@ struct PcSmem {
     // scaler statistics (launch constants; global loads take ~3k cycles under the saturated write stream)
     alignas(16) float smean[PC_F];
     alignas(16) float sscale[PC_F];
-    alignas(16) float srscale[PC_F];
+    signed char srcorr[PC_F];      // RN(1/scale) = bits(MUFU.RCP(scale)) + srcorr (ulps): the exact reciprocal in 1 byte instead of 4
+    int rcorr_bad;                 // a correction did not fit (never seen): every item is deferred to the generic kernel
     // producer scratch
     alignas(16) uint32_t sseq[2][PC_SSEQ_W];   // double-buffered: the TMA load of item i+1 lands while item i is prepared
     alignas(16) uint32_t list[LIST_CAP + 8];
+    uint16_t delta[PC_DELTA];      // Bernoulli deltas of the sequence being prepared / consumed: kmer | ordinal << 12 | (add ? 0x8000 : 0)
+    int delta_free;                // iterations whose deltas the builders have consumed (single buffer, release / acquire)
     uint32_t gtabs[STABS][RNG_BLOCK];
     int scan[PC_HALF / 32 + 2];
     int seg_off[PC_MAXB + 1];
@@ -92,7 +95,7 @@ struct PcSmem {
     int bern_slot[PC_MAXB];        // slot of ordinal
     int n_bern, n_ent;
     // consumer side
-    alignas(16) uint32_t dscratch[PC_PRIVW];            // dense slots (builders): biased uint16 deltas, two bins per word
+    alignas(16) uint32_t dscratch[PC_DENSE][PC_PRIVW];  // dense slots (builders): biased uint16 deltas, two bins per word, one array per Bernoulli ordinal
     alignas(16) uint32_t sscratch[PC_FIXW * PC_SCRW];   // sparse jobs: one scratch per fix warp
     // mbarriers.  Per row buffer: free (its last bulk copy has been read) -> built (builders, only when rebuilt)
     // -> full (fix warp: the row is the job's row) -> bulk copy -> free
@@ -235,7 +238,7 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
         const int L = cur_L;
         const uint32_t seq_id = (uint32_t)(p.seq_id0 + seq);
         const int nhalf = half_count(L);
-        const bool fits = nhalf <= 2 * SSEQ_CHUNKS;
+        const bool fits = nhalf <= 2 * SSEQ_CHUNKS && !sm.rcorr_bad;
         if (ptid == 0) { cx.item = item; cx.defer = fits ? 0 : 1; cx.n_delta = 0; sm.nvalid = 0; sm.any_over = 0; }
         for (int i = ptid; i < PC_MAXS; i += PC_HALF) cx.dtot[i] = 0;
         uint32_t* cw = reinterpret_cast<uint32_t*>(cx.clean16);   // two uint16 counters per word (counts <= 20 480)
@@ -347,6 +350,7 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
                         if (active && blk == 0) sm.seg_off[j] = off;
                         if (ptid == 0) sm.seg_off[nbs] = total;
                         if (active && f.cnt) fast_block_write(f, blk, codes, sm.list + off);
+                        while (ld_acquire_smem(&sm.delta_free) < it) __nanosleep(32);   // the builders have consumed the previous deltas
                         bar_named(1, PC_HALF);
                         for (int i0 = 0; i0 < total; i0 += PC_HALF) {   // uniform trip count: warp collectives inside
                             const int i = i0 + ptid;
@@ -372,7 +376,7 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
                             if (cnt && wbase + wtot <= PC_DELTA) {
                                 const uint32_t tag = (uint32_t)jj << 12;
                                 const int d = apply_entry<K>(codes, nmask, L, sm.list + so, sm.seg_off[jj + 1] - so, i - so, [&](uint32_t kmer, int dd) {
-                                    cx.delta[slot++] = (uint16_t)(kmer | tag | (dd > 0 ? 0x8000u : 0u));
+                                    sm.delta[slot++] = (uint16_t)(kmer | tag | (dd > 0 ? 0x8000u : 0u));
                                 });
                                 if (d) atomicAdd(&cx.dtot[sm.bern_slot[jj]], d);
                             }
@@ -454,6 +458,14 @@ struct PcClock {
     }
 };
 
+// RN(1/x) from the hardware approximation and the per-bin ulp correction computed in the kernel prologue
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_exact(float x, int corr) { return __int_as_float(__float_as_int(rcp_approx(x)) + corr); }
+
 // scaler statistics of one granule from shared memory, ready for the packed ops
 template <bool STD>
 __device__ __forceinline__ Stats2 smem_stats2(const PcSmem& sm, int vec) {
@@ -464,7 +476,8 @@ __device__ __forceinline__ Stats2 smem_stats2(const PcSmem& sm, int vec) {
     if (STD) {
         const float4 m = reinterpret_cast<const float4*>(sm.smean)[vec];
         const float4 sc = reinterpret_cast<const float4*>(sm.sscale)[vec];
-        const float4 rs = reinterpret_cast<const float4*>(sm.srscale)[vec];
+        const char4 rc = reinterpret_cast<const char4*>(sm.srcorr)[vec];
+        const float4 rs = make_float4(rcp_exact(sc.x, rc.x), rcp_exact(sc.y, rc.y), rcp_exact(sc.z, rc.z), rcp_exact(sc.w, rc.w));
         s.nm01 = make_float2(-m.x, -m.y); s.nm23 = make_float2(-m.z, -m.w);
         s.ns01 = make_float2(-sc.x, -sc.y); s.ns23 = make_float2(-sc.z, -sc.w);
         s.rs01 = make_float2(rs.x, rs.y); s.rs23 = make_float2(rs.z, rs.w);
@@ -490,6 +503,7 @@ __device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
         PcCtx& cx = sm.ctx[b];
         const long long item = cx.item;
         if (item < 0) return;
+        if (cx.defer && tid == 0) st_release_smem(&sm.delta_free, it + 1);
         if (!cx.defer) {
             const int S = p.S;
             uint2 ck[GPT];
@@ -499,7 +513,18 @@ __device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
                 ck[j] = cx.clean16[tid + j * NB];
                 cvt_granule(ck[j], magic, c01[j], c23[j]);
             }
+            // all Bernoulli deltas of the sequence into the per-ordinal scratch arrays in ONE scan; the producers may
+            // then write the next sequence's deltas
             const int n_delta = cx.n_delta;
+            if (cx.n_dense > 0) {
+                bar_named(2, NB);                    // every builder is done with the previous sequence's dense rows (own-bin resets)
+                for (int r = tid; r < n_delta; r += NB) {
+                    const uint32_t e = sm.delta[r];
+                    upd16(sm.dscratch[(e >> 12) & 7u], e & 0xFFFu, (e & 0x8000u) ? 1 : -1);
+                }
+                bar_named(2, NB);
+            }
+            if (tid == 0) st_release_smem(&sm.delta_free, it + 1);
             unsigned key_cur = 0u;                   // window total (float bits) the register row val[] holds; 0: none
             float4 val[GPT];
 #pragma unroll
@@ -514,16 +539,6 @@ __device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
                 const int s = cx.job_slot[j];
                 const float2 fy = cx.gy[s];
                 const bool dense = sm.kind_class[s] == 2;
-                if (dense) {
-                    // patch this slot's deltas into the scratch (previous readers are past their barrier)
-                    const uint32_t ord = (uint32_t)sm.bern_ord[s];
-                    bar_named(2, NB);
-                    for (int r = tid; r < n_delta; r += NB) {
-                        const uint32_t e = cx.delta[r];
-                        if (((e >> 12) & 7u) == ord) upd16(sm.dscratch, e & 0xFFFu, (e & 0x8000u) ? 1 : -1);
-                    }
-                    bar_named(2, NB);
-                }
                 // The row's values are computed BEFORE the buffer is free (only the stores sit on the buffer's critical
                 // path) and kept in registers: consecutive rebuilds with the same window total cost four stores per thread.
                 const unsigned key_j = dense ? 0u : __float_as_uint(fy.x);
@@ -534,7 +549,7 @@ __device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
                         const int vec = tid + g * NB;
                         float2 d01 = c01[g], d23 = c23[g];
                         if (dense) {   // own bins = clean + delta; the scratch is reset on the way
-                            uint2* scr = reinterpret_cast<uint2*>(sm.dscratch);
+                            uint2* scr = reinterpret_cast<uint2*>(sm.dscratch[sm.bern_ord[s]]);
                             const uint2 w = scr[vec];
                             scr[vec] = make_uint2(PC_BIAS2, PC_BIAS2);
                             cvt_granule(make_uint2(ck[g].x + w.x - PC_BIAS2, ck[g].y + w.y - PC_BIAS2), magic, d01, d23);
@@ -670,7 +685,7 @@ __device__ __forceinline__ void pc_fix(PcSmem& sm, const ProfParams& p) {
             // RPL evaluations of a lane are independent and the warp does not diverge)
             auto value = [&](uint32_t bin, int d, float2 fy) -> float {
                 float q = div_rn((float)((int)clean_h[bin] + d + p.pseudocount), fy.x, fy.y);
-                if (STD) q = div_rn(q - sm.smean[bin], sm.sscale[bin], sm.srscale[bin]);
+                if (STD) { const float sc = sm.sscale[bin]; q = div_rn(q - sm.smean[bin], sc, rcp_exact(sc, sm.srcorr[bin])); }
                 return q;
             };
             int j = (fw - gj0 % PC_NBUF + PC_NBUF) % PC_NBUF;      // first job of this sequence that lands in this buffer
@@ -740,14 +755,20 @@ __global__ void __launch_bounds__(PC_NT, 1) profiles_pc_kernel(const ProfParams 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PcSmem& sm = *reinterpret_cast<PcSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    if (tid == 0) sm.params = p;
+    if (tid == 0) { sm.params = p; sm.rcorr_bad = 0; sm.delta_free = 0; }
+    __syncthreads();
     // launch-uniform slot tables
     for (int i = tid; i < p.n_vars; i += PC_NT) sm.svars[i] = p.vars[i];
     for (int i = tid; i < p.S; i += PC_NT) sm.sout_off[i] = p.out_off[i];
     for (int i = tid; i < STABS * RNG_BLOCK; i += PC_NT) (&sm.gtabs[0][0])[i] = i < p.n_tabs * RNG_BLOCK ? p.gtab[i] : 0u;
     if (OUT == IDL_OUT_STD_F32)
-        for (int i = tid; i < PC_F; i += PC_NT) { sm.smean[i] = p.mean[i]; sm.sscale[i] = p.scale[i]; sm.srscale[i] = p.rscale[i]; }
-    for (int i = tid; i < PC_PRIVW; i += PC_NT) sm.dscratch[i] = PC_BIAS2;
+        for (int i = tid; i < PC_F; i += PC_NT) {
+            const float sc = p.scale[i];
+            const int corr = __float_as_int(p.rscale[i]) - __float_as_int(rcp_approx(sc));
+            sm.smean[i] = p.mean[i]; sm.sscale[i] = sc; sm.srcorr[i] = (signed char)corr;
+            if (corr < -64 || corr > 64) sm.rcorr_bad = 1;
+        }
+    for (int i = tid; i < PC_DENSE * PC_PRIVW; i += PC_NT) (&sm.dscratch[0][0])[i] = PC_BIAS2;
     for (int i = tid; i < PC_FIXW * PC_SCRW; i += PC_NT) sm.sscratch[i] = PC_BIAS4;
     __syncthreads();
     if (tid == 0) {
