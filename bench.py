@@ -222,7 +222,7 @@ def run_ours(args):
     alg_bytes = n * ((SEQ_LEN + 3) // 4) + n * V * F * 4
     peak, peak_src = measured_peak()
     traffic = recorded_traffic()
-    roofline = {"bound": "hbm", "kernel": "profiles_pc_kernel<STD_F32> (producer/consumer; + deferred-item pass of profiles_kernel<6,512,STD_F32>)", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "profiles_pc_kernel<STD_F32> (TMA producer/builder/fix/store pipeline; + deferred-item pass of profiles_kernel<6,512,STD_F32>)", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": alg_bytes / (kms * 1e-3) / 1e9 / peak, "peak_source": peak_src + " — of measured",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kms,
                 "traffic": traffic["dram_bytes_per_sequence"] * n if traffic else None,

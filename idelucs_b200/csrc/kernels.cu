@@ -610,6 +610,7 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ProfSmem<K, NT>& sm = *reinterpret_cast<ProfSmem<K, NT>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (p.only_deferred && p.work_counter[1] == 0ull) return;   // the producer/consumer kernel took every item (stream order: its count is final)
 
     const float magic = 8388608.0f - (float)p.pseudocount;
     const bool cached = p.n_vars <= SVARS && p.S <= SVARS;
