@@ -34,7 +34,8 @@ constexpr int PC_NT = 1024, PC_HALF = 512;
 constexpr int PC_K = 6, PC_F = 4096, PC_VEC = 1024, PC_PRIVW = 2048;
 constexpr int PC_NBLD = 256;       // builder threads (warps 0..7)
 constexpr int PC_NFIX = 224;       // fix threads (warps 8..14); warp 15 lane 0 is the store thread
-constexpr int PC_NBUF = 3;         // 16 KB row buffers
+constexpr int PC_NBUF = 4;         // 16 KB row buffers
+constexpr int PC_INFL = PC_NBUF - 2;   // bulk copies kept in flight (of the other two buffers one is being fixed, one is ready)
 constexpr int PC_FIXW = PC_NFIX / 32;   // fix warps: each owns a 4 KB scratch (biased uint8 deltas) and handles whole jobs
 constexpr int PC_SCRW = 1024;      // words of one fix-warp scratch (four bins per word)
 constexpr uint32_t PC_BIAS4 = 0x80808080u;
@@ -96,7 +97,7 @@ struct PcSmem {
     int n_bern, n_ent;
     // consumer side
     alignas(16) uint32_t dscratch[PC_DENSE][PC_PRIVW];  // dense slots (builders): biased uint16 deltas, two bins per word, one array per Bernoulli ordinal
-    alignas(16) uint32_t sscratch[PC_FIXW * PC_SCRW];   // sparse jobs: one scratch per fix warp
+    alignas(16) uint32_t sscratch[PC_NBUF * PC_SCRW];   // sparse jobs: one scratch per active fix warp (= per row buffer)
     // mbarriers.  Per row buffer: free (its last bulk copy has been read) -> built (builders, only when rebuilt)
     // -> full (fix warp: the row is the job's row) -> bulk copy -> free
     alignas(8) unsigned long long ctx_full[2], ctx_empty[2], row_free[PC_NBUF], row_built[PC_NBUF], row_full[PC_NBUF], seq_full[2];
@@ -630,10 +631,10 @@ __device__ __forceinline__ void pc_store(PcSmem& sm, const ProfParams& p) {
                 if (p.dbg & 4) bulk_store_hint(dst, sm.rowbuf[buf], PC_F * 4, pol_ef);
                 else bulk_store(dst, sm.rowbuf[buf], PC_F * 4);
                 bulk_commit();
-                if (gj > 0) {
-                    bulk_wait_read<1>();               // everything but the copy just issued has left shared memory
+                if (gj >= PC_INFL) {
+                    bulk_wait_read<PC_INFL>();         // all but the PC_INFL most recent copies have left shared memory
                     clk.tick(7);
-                    mbar_arrive(&sm.row_free[(gj - 1) % PC_NBUF]);
+                    mbar_arrive(&sm.row_free[(gj - PC_INFL) % PC_NBUF]);
                 }
             }
         }
@@ -769,7 +770,7 @@ __global__ void __launch_bounds__(PC_NT, 1) profiles_pc_kernel(const ProfParams 
             if (corr < -64 || corr > 64) sm.rcorr_bad = 1;
         }
     for (int i = tid; i < PC_DENSE * PC_PRIVW; i += PC_NT) (&sm.dscratch[0][0])[i] = PC_BIAS2;
-    for (int i = tid; i < PC_FIXW * PC_SCRW; i += PC_NT) sm.sscratch[i] = PC_BIAS4;
+    for (int i = tid; i < PC_NBUF * PC_SCRW; i += PC_NT) sm.sscratch[i] = PC_BIAS4;
     __syncthreads();
     if (tid == 0) {
         int ent = 0, nb = 0;
