@@ -35,6 +35,7 @@ constexpr int PC_K = 6, PC_F = 4096, PC_VEC = 1024, PC_PRIVW = 2048;
 constexpr int PC_NBLD = 256;       // builder threads (warps 0..7)
 constexpr int PC_NFIX = 224;       // fix threads (warps 8..14); warp 15 lane 0 is the store thread
 constexpr int PC_NBUF = 4;         // 16 KB row buffers
+constexpr int PC_NOTH = 1;         // row buffers that take the "other" jobs (dense rows, minority window totals) while the rest stream the main total
 constexpr int PC_INFL = PC_NBUF - 2;   // bulk copies kept in flight (of the other two buffers one is being fixed, one is ready)
 constexpr int PC_FIXW = PC_NFIX / 32;   // fix warps: each owns a 4 KB scratch (biased uint8 deltas) and handles whole jobs
 constexpr int PC_SCRW = 1024;      // words of one fix-warp scratch (four bins per word)
@@ -77,6 +78,9 @@ struct PcSmem {
     alignas(16) uint32_t sseq[2][PC_SSEQ_W];   // double-buffered: the TMA load of item i+1 lands while item i is prepared
     alignas(16) uint32_t list[LIST_CAP + 8];
     uint16_t delta[PC_DELTA];      // Bernoulli deltas of the sequence being prepared / consumed: kmer | ordinal << 12 | (add ? 0x8000 : 0)
+    unsigned char m_sorted[PC_MAXS];   // slots sorted by job key (dense first, then window total)
+    unsigned char m_lt[PC_MAXS], m_eq[PC_MAXS];   // per slot: slots with a smaller key / with the same key
+    unsigned m_exh[2];             // ballots of "the list this position wants is exhausted"
     int delta_free;                // iterations whose deltas the builders have consumed (single buffer, release / acquire)
     uint32_t gtabs[STABS][RNG_BLOCK];
     int scan[PC_HALF / 32 + 2];
@@ -101,6 +105,8 @@ struct PcSmem {
     // mbarriers.  Per row buffer: free (its last bulk copy has been read) -> built (builders, only when rebuilt)
     // -> full (fix warp: the row is the job's row) -> bulk copy -> free
     alignas(8) unsigned long long ctx_full[2], ctx_empty[2], row_free[PC_NBUF], row_built[PC_NBUF], row_full[PC_NBUF], seq_full[2];
+    int free_count[PC_NBUF];       // uses of each buffer whose bulk copy has been read.  The builders look ahead and skip the uses that
+                                   // need no rebuild; an mbarrier parity wait alone can only tell adjacent phases apart
 };
 
 // ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) ----
@@ -116,6 +122,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         "{\n.reg .pred p;\nWAIT_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one (hardware-suspended, time-limited) wait attempt: a sleeping primitive for loops that re-check a counter
+__device__ __forceinline__ void mbar_try_once(unsigned long long* bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity) {
     uint32_t ok;
@@ -213,6 +223,7 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
     long long cur_item, cur_seq, cur_c0;
     int cur_L;
     int n_loads0 = 0, n_loads1 = 0; // TMA loads issued into each half of sseq (mbarrier phase bookkeeping)
+    int gj0 = 0;                    // jobs of the previous (not deferred) sequences: the consumers' buffer rotation
     while (ld_acquire_smem(&sm.q_head) < 1) __nanosleep(32);
     cur_item = sm.q_item[0]; cur_seq = sm.q_seq[0]; cur_c0 = sm.q_c0[0]; cur_L = sm.q_len[0];
     if (ptid == 0) issue_seq_load(0, cur_item, cur_c0, cur_L);
@@ -392,27 +403,79 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
         // ---- per-slot totals, output rows and the job order (dense slots first, then by window total) ----
         const int S = p.S;
         auto job_key = [&](int s) -> unsigned { return sm.kind_class[s] == 2 ? 0u : 0x40000000u | (unsigned)(cx.base_total + cx.dtot[s]); };
-        {   // rank of every slot in the job order: 8 lanes per slot
+        {   // slots sorted by key (8 lanes per slot): rank = smaller keys + equal keys with a smaller slot index
             const int s = ptid >> 3, part = ptid & 7;
             const bool on = s < S;
             const unsigned ks = on ? job_key(s) : 0u;
-            int rank = 0;
+            int lt = 0, eqb = 0, eq = 0;
             if (on)
                 for (int t = part; t < S; t += 8) {
                     const unsigned kt = job_key(t);
-                    rank += (kt < ks || (kt == ks && t < s)) ? 1 : 0;
+                    lt += kt < ks ? 1 : 0;
+                    eq += kt == ks ? 1 : 0;
+                    eqb += (kt == ks && t < s) ? 1 : 0;
                 }
-            rank += __shfl_xor_sync(0xffffffffu, rank, 1);
-            rank += __shfl_xor_sync(0xffffffffu, rank, 2);
-            rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                lt += __shfl_xor_sync(0xffffffffu, lt, o);
+                eq += __shfl_xor_sync(0xffffffffu, eq, o);
+                eqb += __shfl_xor_sync(0xffffffffu, eqb, o);
+            }
             if (on && part == 0) {
                 const float ft2 = (float)(cx.base_total + cx.dtot[s]);
                 cx.gy[s] = make_float2(ft2, 1.0f / ft2);
                 cx.grow[s] = 4LL * (sm.sout_off[s] + item * p.out_stride);
-                cx.job_slot[rank] = (unsigned char)s;
+                sm.m_sorted[lt + eqb] = (unsigned char)s;
+                sm.m_lt[s] = (unsigned char)lt;
+                sm.m_eq[s] = (unsigned char)eq;
             }
         }
-        if (ptid == 0) cx.n_dense = sm.n_bern;
+        const int n_dense = sm.n_bern;
+        if (ptid == 0) cx.n_dense = n_dense;
+        bar_named(1, PC_HALF);
+        // ---- job order.  The MAIN jobs (the window total of the median sparse slot: usually > 2/3 of the slots)
+        // stream from PC_NBUF - PC_NOTH row buffers that never need a rebuild; the OTHER jobs (dense rows, minority
+        // totals: each needs the builders) take turns in the remaining PC_NOTH buffers, so a rebuild is hidden behind
+        // the main jobs' bulk copies instead of stalling the store thread.  Position p uses buffer (gj0 + p) mod PC_NBUF.
+        int M = 0, R0 = S;
+        if (S > n_dense) {
+            const int smid = sm.m_sorted[n_dense + (S - n_dense) / 2];
+            M = sm.m_eq[smid]; R0 = sm.m_lt[smid];
+        }
+        const int O = S - M, a = gj0 % PC_NBUF;
+        // (the first round of buffers is all main: the main row is the cheapest to have ready at the start of a sequence)
+        auto lane_type = [&](int q) { return (a + q) % PC_NBUF >= PC_NBUF - PC_NOTH; };
+        auto other_type = [&](int q) { return q >= PC_NBUF && lane_type(q); };
+        auto lanes_before = [&](int q) {
+            int f = (q / PC_NBUF) * PC_NOTH;
+            for (int r = q - q % PC_NBUF; r < q; ++r) f += lane_type(r) ? 1 : 0;
+            return f;
+        };
+        auto others_before = [&](int q) { return q <= PC_NBUF ? 0 : lanes_before(q) - lanes_before(PC_NBUF); };   // other-type positions in [0, q)
+        if (ptid < 64) {
+            const int q = ptid;
+            const int f = others_before(q);
+            const bool exh = q < S && (other_type(q) ? f >= O : q - f >= M);
+            const unsigned bal = __ballot_sync(0xffffffffu, exh);
+            if (lane == 0) sm.m_exh[ptid >> 5] = bal;
+        }
+        bar_named(1, PC_HALF);
+        if (ptid < S) {
+            const int q = ptid;
+            const unsigned b0 = sm.m_exh[0], b1 = sm.m_exh[1];
+            const int E = b0 ? __ffs(b0) - 1 : (b1 ? 32 + __ffs(b1) - 1 : S);   // first position whose list is exhausted
+            int rank;
+            if (q < E) {
+                const int f = others_before(q);
+                if (other_type(q)) rank = f < R0 ? f : f + M;          // other index f -> sorted rank
+                else rank = R0 + (q - f);                              // main index q - f
+            } else {
+                const int fE = others_before(E);
+                if (other_type(E)) rank = R0 + (E - fE) + (q - E);     // the others ran out: the rest are main jobs
+                else { const int o = fE + (q - E); rank = o < R0 ? o : o + M; }
+            }
+            cx.job_slot[q] = sm.m_sorted[rank];
+        }
         bar_named(1, PC_HALF);
         if (ptid < S) {
             const int j = ptid, s = cx.job_slot[j];
@@ -420,6 +483,7 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
             cx.job_build[j] = (unsigned char)nb;
             cx.job_dst[j] = (unsigned long long)cx.grow[s] | (unsigned long long)nb;
         }
+        if (!cx.defer) gj0 += S;
         cur_item = nx_item; cur_seq = nx_seq; cur_c0 = nx_c0; cur_L = nx_L; cur_phase = nx_phase;
         tick(4);
         bar_named(1, PC_HALF);
@@ -532,11 +596,7 @@ __device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
             for (int g = 0; g < GPT; ++g) val[g] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int j = 0; j < S; ++j) {
                 const int buf = (gj0 + j) % PC_NBUF, use = (gj0 + j) / PC_NBUF;
-                if (!cx.job_build[j]) {
-                    // nothing to build, but every use of the buffer is followed: a parity wait can only tell adjacent phases apart
-                    mbar_wait(&sm.row_free[buf], (use & 1) ^ 1);
-                    continue;
-                }
+                if (!cx.job_build[j]) continue;
                 const int s = cx.job_slot[j];
                 const float2 fy = cx.gy[s];
                 const bool dense = sm.kind_class[s] == 2;
@@ -559,7 +619,8 @@ __device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
                     }
                 }
                 clk.tick(13);
-                mbar_wait(&sm.row_free[buf], (use & 1) ^ 1);   // the bulk copy of the buffer's previous job has been read
+                // the bulk copy of the buffer's previous job has been read (counter = truth, the mbarrier is only the way to sleep)
+                while (ld_acquire_smem(&sm.free_count[buf]) < use) mbar_try_once(&sm.row_free[buf], (use & 1) ^ 1);
                 clk.tick(14);
                 float4* row = reinterpret_cast<float4*>(sm.rowbuf[buf]);
 #pragma unroll
@@ -634,6 +695,7 @@ __device__ __forceinline__ void pc_store(PcSmem& sm, const ProfParams& p) {
                 if (gj >= PC_INFL) {
                     bulk_wait_read<PC_INFL>();         // all but the PC_INFL most recent copies have left shared memory
                     clk.tick(7);
+                    st_release_smem(&sm.free_count[(gj - PC_INFL) % PC_NBUF], (gj - PC_INFL) / PC_NBUF + 1);
                     mbar_arrive(&sm.row_free[(gj - PC_INFL) % PC_NBUF]);
                 }
             }
@@ -791,7 +853,7 @@ __global__ void __launch_bounds__(PC_NT, 1) profiles_pc_kernel(const ProfParams 
         sm.q_head = 0;
         for (int i = 0; i < 2; ++i) mbar_init(&sm.seq_full[i], 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&sm.ctx_full[i], 1); mbar_init(&sm.ctx_empty[i], PC_NBLD + PC_NFIX + 1); }
-        for (int i = 0; i < PC_NBUF; ++i) { mbar_init(&sm.row_free[i], 1); mbar_init(&sm.row_built[i], PC_NBLD); mbar_init(&sm.row_full[i], 1); }
+        for (int i = 0; i < PC_NBUF; ++i) { mbar_init(&sm.row_free[i], 1); mbar_init(&sm.row_built[i], PC_NBLD); mbar_init(&sm.row_full[i], 1); sm.free_count[i] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
