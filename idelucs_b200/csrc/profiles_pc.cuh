@@ -444,10 +444,11 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
         }
         const int O = S - M, a = gj0 % PC_NBUF;
         // (the first round of buffers is all main: the main row is the cheapest to have ready at the start of a sequence)
-        auto lane_type = [&](int q) { return (a + q) % PC_NBUF >= PC_NBUF - PC_NOTH; };
+        const int noth = (p.dbg & 64) ? 0 : PC_NOTH;
+        auto lane_type = [&](int q) { return (a + q) % PC_NBUF >= PC_NBUF - noth; };
         auto other_type = [&](int q) { return q >= PC_NBUF && lane_type(q); };
         auto lanes_before = [&](int q) {
-            int f = (q / PC_NBUF) * PC_NOTH;
+            int f = (q / PC_NBUF) * noth;
             for (int r = q - q % PC_NBUF; r < q; ++r) f += lane_type(r) ? 1 : 0;
             return f;
         };
@@ -728,9 +729,10 @@ __device__ __forceinline__ void pc_fix(PcSmem& sm, const ProfParams& p) {
     uint32_t* scr = sm.sscratch + fw * PC_SCRW;
     float* row = sm.rowbuf[fw];
     int gj0 = 0, n_built = 0;                          // CTA lifetime: jobs of the previous sequences, rebuilds of this buffer
-    uint32_t km_prev[RPL];                             // the bins the previous job of this buffer changed (0xFFFF: none)
+    uint32_t km_prev[RPL];                             // the bins the previous job of this buffer changed (0xFFFF: none) ...
+    float vt_prev[RPL];                                // ... and the template values it found there
 #pragma unroll
-    for (int u = 0; u < RPL; ++u) km_prev[u] = 0xFFFFu;
+    for (int u = 0; u < RPL; ++u) { km_prev[u] = 0xFFFFu; vt_prev[u] = 0.f; }
     PcClock clk;
     clk.start(ftid == 0 && (p.dbg & 16) ? p.phase_prof : nullptr);
     for (int it = 0;; ++it) {
@@ -760,48 +762,55 @@ __device__ __forceinline__ void pc_fix(PcSmem& sm, const ProfParams& p) {
                 const float2 fy = cx.gy[s];
                 const bool rebuilt = cx.job_build[j] != 0;
                 uint32_t km[RPL];
-                int d[RPL];
-#pragma unroll
-                for (int u = 0; u < RPL; ++u) {
-                    const int r = lane + 32 * u;
-                    km[u] = r < n ? (uint32_t)rl[r] : 0xFFFFu;
-                }
-                // multiplicity of each removed k-mer within this job: subtract into the scratch, read back, reset
-#pragma unroll
-                for (int u = 0; u < RPL; ++u)
-                    if (km[u] != 0xFFFFu) atomicSub(scr + (km[u] >> 2), 1u << ((km[u] & 3u) * 8u));
-                __syncwarp();
-#pragma unroll
-                for (int u = 0; u < RPL; ++u)
-                    d[u] = km[u] != 0xFFFFu ? (int)((scr[km[u] >> 2] >> ((km[u] & 3u) * 8u)) & 0xFFu) - 0x80 : 0;
-                __syncwarp();
-#pragma unroll
-                for (int u = 0; u < RPL; ++u)
-                    if (km[u] != 0xFFFFu) scr[km[u] >> 2] = PC_BIAS4;
                 float vnew[RPL];
 #pragma unroll
-                for (int u = 0; u < RPL; ++u) vnew[u] = km[u] != 0xFFFFu ? value(km[u], d[u], fy) : 0.f;
+                for (int u = 0; u < RPL; ++u) { km[u] = 0xFFFFu; vnew[u] = 0.f; }
+                if (n > 0) {                           // (warp-uniform) nothing to prepare for clean and dense slots
+                    int d[RPL];
+#pragma unroll
+                    for (int u = 0; u < RPL; ++u) {
+                        const int r = lane + 32 * u;
+                        km[u] = r < n ? (uint32_t)rl[r] : 0xFFFFu;
+                    }
+                    // multiplicity of each removed k-mer within this job: subtract into the scratch, read back, reset
+#pragma unroll
+                    for (int u = 0; u < RPL; ++u)
+                        if (km[u] != 0xFFFFu) atomicSub(scr + (km[u] >> 2), 1u << ((km[u] & 3u) * 8u));
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < RPL; ++u)
+                        d[u] = km[u] != 0xFFFFu ? (int)((scr[km[u] >> 2] >> ((km[u] & 3u) * 8u)) & 0xFFu) - 0x80 : 0;
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < RPL; ++u)
+                        if (km[u] != 0xFFFFu) scr[km[u] >> 2] = PC_BIAS4;
+#pragma unroll
+                    for (int u = 0; u < RPL; ++u)
+                        if (km[u] != 0xFFFFu) vnew[u] = value(km[u], d[u], fy);
+                }
                 clk.tick(9);
                 if (rebuilt) {
                     mbar_wait(&sm.row_built[fw], n_built & 1);     // the builders wrote a fresh row (they waited for row_free)
                     ++n_built;
                 } else {
-                    // same window total as the buffer's previous job: put the template value back where that job changed it
-                    float vold[RPL];
-#pragma unroll
-                    for (int u = 0; u < RPL; ++u) vold[u] = km_prev[u] != 0xFFFFu ? value(km_prev[u], 0, fy) : 0.f;
                     mbar_wait(&sm.row_free[fw], (use & 1) ^ 1);    // the bulk copy of the buffer's previous job has been read
+                    // same window total as the buffer's previous job: put the template values back where that job changed them
 #pragma unroll
                     for (int u = 0; u < RPL; ++u)
-                        if (km_prev[u] != 0xFFFFu) row[km_prev[u]] = vold[u];
+                        if (km_prev[u] != 0xFFFFu) row[km_prev[u]] = vt_prev[u];
                     __syncwarp();
                 }
                 clk.tick(10);
+                // the row now holds the template: remember its values at this job's bins (the next job's undo list), then overwrite
+#pragma unroll
+                for (int u = 0; u < RPL; ++u) {
+                    km_prev[u] = km[u];
+                    if (km[u] != 0xFFFFu) vt_prev[u] = row[km[u]];
+                }
+                __syncwarp();
 #pragma unroll
                 for (int u = 0; u < RPL; ++u)
                     if (km[u] != 0xFFFFu) row[km[u]] = vnew[u];
-#pragma unroll
-                for (int u = 0; u < RPL; ++u) km_prev[u] = km[u];
                 fence_proxy_async_smem();              // generic-proxy writes -> visible to the TMA engine
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.row_full[fw]);
