@@ -109,6 +109,8 @@ struct PcSmem {
                                    // need no rebuild; an mbarrier parity wait alone can only tell adjacent phases apart
 };
 
+constexpr uint32_t PC_SUSPEND_NS = 2000u;   // upper bound of one hardware-suspended mbarrier wait (a completed phase wakes the thread at once):
+                                            // long enough that waiting warps do not eat issue slots with retries
 // ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX; SASS: SYNCS.*, UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
@@ -120,12 +122,12 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     asm volatile(
         "{\n.reg .pred p;\nWAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity), "r"(PC_SUSPEND_NS) : "memory");
 }
 // one (hardware-suspended, time-limited) wait attempt: a sleeping primitive for loops that re-check a counter
 __device__ __forceinline__ void mbar_try_once(unsigned long long* bar, uint32_t parity) {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n}" ::"r"(smem_u32(bar)), "r"(parity), "r"(PC_SUSPEND_NS) : "memory");
 }
 __device__ __forceinline__ bool mbar_test(unsigned long long* bar, uint32_t parity) {
     uint32_t ok;
