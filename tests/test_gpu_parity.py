@@ -384,3 +384,57 @@ def test_profile_stats_equals_matrix_fit(golden_dir, fasta_files, ft, SeqSet):
     x[n:2 * n, 0] = x[:n, 0]
     x[2 * n:, 0] = x[:n, 0]
     assert sha(x.cpu().numpy()) == g["k5"]["x_train_sha256"]
+
+
+def test_pc_kernel_repetitive_and_degenerate_sequences(ft, SeqSet):
+    """fast kernel == generic kernel on inputs that stress its sparse fix-up logic: homopolymers and short tandem
+    repeats (every Random_N removal of a variant hits the same few bins: multiplicities up to 120 in the biased
+    uint8 scratch), all-N and N-rich sequences (window totals near the pseudocount floor, many equal totals),
+    and lengths around the 64-base chunk / 128-base mask alignment boundaries"""
+    rng = np.random.default_rng(5)
+    seqs = []
+    for i in range(640):
+        L = int(rng.integers(1, 4000))
+        kind = i % 8
+        if kind == 0:
+            s = b"A" * L
+        elif kind == 1:
+            s = (b"ACG" * (L // 3 + 1))[:L]
+        elif kind == 2:
+            s = b"N" * L
+        elif kind == 3:
+            a = np.frombuffer(b"ACGTNNNN", dtype=np.uint8)
+            s = a[rng.integers(0, a.size, size=L)].tobytes()
+        elif kind == 4:
+            s = (b"AT" * (L // 2 + 1))[:L]
+        elif kind == 5:
+            s = b"G" * int(rng.choice([63, 64, 65, 127, 128, 129, 191, 192, 193]))
+        else:
+            a = np.frombuffer(b"ACGT", dtype=np.uint8)
+            s = a[rng.integers(0, 4, size=L)].tobytes()
+        seqs.append(s)
+    ss = SeqSet.from_sequences(seqs)
+    variants = ft.mimic_schedule(50)
+    mean = torch.rand(4096, device="cuda") * 1e-3
+    scale = torch.rand(4096, device="cuda") * 1e-4 + 1e-6
+    outs = {}
+    for mode in ("pc", "generic"):
+        if mode == "generic":
+            os.environ["IDL_NO_PC"] = "1"
+        try:
+            outs[mode] = ft.profiles(ss, 6, variants, out_kind=ft.OUT_STD_F32, seed=3, mean=mean, scale=scale)
+        finally:
+            os.environ.pop("IDL_NO_PC", None)
+    assert torch.equal(outs["pc"], outs["generic"])
+    # mimic counts of a homopolymer against the oracle's mutate-and-recount
+    c = ft.profiles(ss, 6, variants, out_kind=ft.OUT_COUNTS_I32, seed=3).cpu().numpy()
+    for i in (0, 8, 1, 3):
+        for v in (0, 1, 2, 3, 50):
+            spec = variants[v]
+            edits = orc.rng_variant_edits(3, i, v, spec.kind, orc.codes_of_seq(seqs[i]), len(seqs[i]), spec.p1, spec.p2, spec.n_bp)
+            mut = bytearray(seqs[i])
+            for pos, val in edits:
+                mut[pos] = b"ACGTN"[val]
+            cnt = np.zeros(4096, np.int32)
+            orc.kmer_counts(mut, 6, cnt)
+            assert np.array_equal(c[v, i], cnt), (i, v)

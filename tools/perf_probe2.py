@@ -33,6 +33,15 @@ def main():
             ts.append(a.elapsed_time(b))
         by = nv * n * F * 4 + n * L / 4
         print("%-20s dbg=%s best %.3f ms  %.1f GB/s" % (name, os.environ.get("IDL_PC_DBG", "0"), min(ts), by / min(ts) / 1e6))
+        if name.startswith("all") and not os.environ.get("IDL_PHASE_PROF"):
+            fs = lambda: ft.profile_stats(ss, k, variants[0], seed=1)
+            fs(); torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fs(); b.record(); torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            print("%-20s best %.3f ms" % ("stats pass (slot 0)", min(ts)))
         if os.environ.get("IDL_PHASE_PROF"):
             ws = list(ft._workspaces.values())[0]
             prof = ws[-128:].view(torch.int64)
