@@ -36,6 +36,10 @@ PROTOTYPES = {
     "idl_profile_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, ctypes.POINTER(Variant),
                                   c_u64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, ctypes.POINTER(c_int), c_void_p, c_void_p,
                                   c_size_t, c_void_p]),
+    "idl_cgr_map": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p]),
+    "idl_revcomp_canonical": (c_int, [c_int, c_void_p]),
+    "idl_revcomp_fold": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "idl_normalize_counts": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
     "idl_kmer_counts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "idl_colstats_parts": (c_int, [c_i64]),
     "idl_colstats": (c_int, [c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p]),

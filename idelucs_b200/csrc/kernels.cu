@@ -1115,6 +1115,65 @@ static int sm_count() {
     return g_sm_count;
 }
 
+// ---------------------------------------------------------------------------------------
+// K6: index maps of a count matrix: FCGR order (kmers.pyx:53-123),
+// canonical (reverse-complement) folding (utils.py:191-221), normalisation of integer counts
+// ---------------------------------------------------------------------------------------
+// kmers.pyx:110-123: base t of a window (t = 0 oldest) contributes bit t of cgr_i / cgr_j with
+// (i, j)(A, C, G, T) = (1,0) (0,0) (0,1) (1,1); the cell is (cgr_i << k) + cgr_j
+IDL_HD uint32_t cgr_index(uint32_t m, int k) {
+    uint32_t ci = 0, cj = 0;
+    for (int t = 0; t < k; ++t) {
+        const uint32_t d = (m >> (2 * (k - 1 - t))) & 3u;   // A0 C1 G2 T3, oldest base most significant
+        ci |= ((~(d ^ (d >> 1))) & 1u) << t;
+        cj |= (d >> 1) << t;
+    }
+    return (ci << k) | cj;
+}
+// utils.py:191-206: index of the reverse complement of k-mer m
+IDL_HD uint32_t revcomp_index(uint32_t m, int k) {
+    uint32_t x = ~m & ((k < 16 ? (1u << (2 * k)) : 0u) - 1u), r = 0;
+    for (int t = 0; t < k; ++t) { r = (r << 2) | (x & 3u); x >>= 2; }
+    return r;
+}
+
+__global__ void cgr_map_kernel(const int32_t* __restrict__ counts, int32_t* __restrict__ cgr, long long total, int k, int accumulate) {
+    const long long F = 1ll << (2 * k);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i >> (2 * k);
+        const long long dst = row * F + cgr_index((uint32_t)(i & (F - 1)), k);
+        cgr[dst] = (accumulate ? cgr[dst] : 0) + counts[i];
+    }
+}
+// utils.py:208-221 on an integer vector: canonical k-mers (kmer <= revcomp) in increasing order, value
+// int((c[kmer] + c[revcomp]) * 0.5) — the in-place float product is truncated back into the int32 array
+__global__ void revcomp_fold_kernel(const int32_t* __restrict__ counts, int32_t* __restrict__ out, long long n, int k,
+                                    const int32_t* __restrict__ canon, int R) {
+    const long long F = 1ll << (2 * k);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * R; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / R;
+        const uint32_t kmer = (uint32_t)canon[i - row * R], rc = revcomp_index(kmer, k);
+        const int a = counts[row * F + kmer], b = counts[row * F + rc];
+        out[i] = (int)((double)(a + b) * 0.5);
+    }
+}
+// counts / np.sum(counts) (utils.py:250, 272) for an int32 [n, R] matrix: one warp per row, float64 and / or float32 output
+__global__ void normalize_counts_kernel(const int32_t* __restrict__ counts, long long n, int R, double* __restrict__ out64, float* __restrict__ out32) {
+    const int lane = threadIdx.x & 31;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    long long sum = 0;
+    for (int c = lane; c < R; c += 32) sum += counts[row * R + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const double tot = (double)sum;
+    for (int c = lane; c < R; c += 32) {
+        const double q = (double)counts[row * R + c] / tot;
+        if (out64) out64[row * R + c] = q;
+        if (out32) out32[row * R + c] = (float)q;
+    }
+}
+
 __global__ void rscale_kernel(const float* __restrict__ scale, float* __restrict__ rscale, int F) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < F) rscale[i] = 1.0f / scale[i];  // IEEE division: the correctly rounded reciprocal div_rn needs
@@ -1415,6 +1474,46 @@ int idl_standardize_f32(const float* d_x, float* d_out, int64_t n, int F, const 
     const long long cap = (long long)sm_count() * 16;
     if (grid > cap) grid = cap;
     standardize_f32_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_out, n4, F / 4, d_mean32, d_scale32);
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
+}
+
+int idl_cgr_map(const int32_t* d_counts, int64_t n, int k, int32_t* d_cgr, int accumulate, void* stream) {
+    if (!d_counts || !d_cgr || n < 0 || k < 1 || k > 12) return set_error(IDL_EINVAL, "idl_cgr_map: bad argument%s", "");
+    const long long total = n << (2 * k);
+    if (total == 0) return IDL_OK;
+    long long grid = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (grid > cap) grid = cap;
+    cgr_map_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_counts, d_cgr, total, k, accumulate);
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
+}
+
+int idl_revcomp_canonical(int k, int32_t* h_index) {
+    if (k < 1 || k > 12) return -1;
+    int R = 0;
+    for (uint32_t m = 0; m < (1u << (2 * k)); ++m)
+        if (m <= revcomp_index(m, k)) { if (h_index) h_index[R] = (int32_t)m; ++R; }
+    return R;
+}
+
+int idl_revcomp_fold(const int32_t* d_counts, int64_t n, int k, const int32_t* d_canon, int R, int32_t* d_out, void* stream) {
+    if (!d_counts || !d_out || !d_canon || n < 0 || k < 1 || k > 12 || R < 1) return set_error(IDL_EINVAL, "idl_revcomp_fold: bad argument%s", "");
+    if (n == 0) return IDL_OK;
+    long long grid = (n * R + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (grid > cap) grid = cap;
+    revcomp_fold_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_counts, d_out, n, k, d_canon, R);
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
+}
+
+int idl_normalize_counts(const int32_t* d_counts, int64_t n, int R, double* d_out64, float* d_out32, void* stream) {
+    if (!d_counts || (!d_out64 && !d_out32) || n < 0 || R < 1) return set_error(IDL_EINVAL, "idl_normalize_counts: bad argument%s", "");
+    if (n == 0) return IDL_OK;
+    const long long grid = (n * 32 + 255) / 256;
+    normalize_counts_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_counts, n, R, d_out64, d_out32);
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }

@@ -171,6 +171,66 @@ def kmer_counts_batch(seqset, k, counts=None):
     return counts
 
 
+def cgr_batch(counts, k, cgr=None):
+    """FCGR cell counts [n, 4^k] (idelucs/kmers.pyx:53-123) from the k-mer counts of the same windows: a fixed
+    permutation of the count vector (idl_cgr_map); accumulates into ``cgr`` when given."""
+    lib = _lib.load()
+    accumulate = cgr is not None
+    if cgr is None:
+        cgr = torch.empty_like(counts)
+    assert counts.dtype == torch.int32 and counts.is_contiguous() and cgr.is_contiguous()
+    with torch.cuda.device(counts.device):
+        _lib.check(lib.idl_cgr_map(_lib.ptr(counts), counts.shape[0], k, _lib.ptr(cgr), 1 if accumulate else 0, _lib.stream_ptr()))
+    return cgr
+
+
+_canon_cache = {}
+
+
+def canonical_index(k, device):
+    """int32 device tensor of the canonical k-mers of kmer_rev_comp (idelucs/utils.py:208-221), increasing"""
+    key = (k, str(device))
+    if key not in _canon_cache:
+        lib = _lib.load()
+        import numpy as np
+        h = np.empty(4 ** k, np.int32)
+        R = lib.idl_revcomp_canonical(k, ctypes.c_void_p(h.ctypes.data))
+        _canon_cache[key] = torch.from_numpy(h[:R].copy()).to(device)
+    return _canon_cache[key]
+
+
+def revcomp_fold(counts, k):
+    """kmer_rev_comp on int32 counts [..., 4^k] (pseudocount included) -> int32 [..., R] (idl_revcomp_fold)"""
+    lib = _lib.load()
+    canon = canonical_index(k, counts.device)
+    flat = counts.reshape(-1, 4 ** k).contiguous()
+    out = torch.empty((flat.shape[0], canon.numel()), dtype=torch.int32, device=counts.device)
+    with torch.cuda.device(counts.device):
+        _lib.check(lib.idl_revcomp_fold(_lib.ptr(flat), flat.shape[0], k, _lib.ptr(canon), canon.numel(), _lib.ptr(out), _lib.stream_ptr()))
+    return out.reshape(tuple(counts.shape[:-1]) + (canon.numel(),))
+
+
+def normalize_counts(counts, want64=True, want32=False):
+    """counts / np.sum(counts) per row of an int32 [..., R] tensor (idelucs/utils.py:250, 272): float64 and / or
+    float32(float64) (idl_normalize_counts)"""
+    lib = _lib.load()
+    R = counts.shape[-1]
+    flat = counts.reshape(-1, R).contiguous()
+    o64 = torch.empty(flat.shape, dtype=torch.float64, device=counts.device) if want64 else None
+    o32 = torch.empty(flat.shape, dtype=torch.float32, device=counts.device) if want32 else None
+    with torch.cuda.device(counts.device):
+        _lib.check(lib.idl_normalize_counts(_lib.ptr(flat), flat.shape[0], R, _lib.ptr(o64), _lib.ptr(o32), _lib.stream_ptr()))
+    res = tuple(t.reshape(counts.shape) for t in (o64, o32) if t is not None)
+    return res[0] if len(res) == 1 else res
+
+
+def reduced_profiles(seqset, k, variants, seed=0, edit_lists=None, seq_id0=0, want64=True, want32=False):
+    """reduce=True path of kmersFasta (idelucs/utils.py:246-250): +1-pseudocount counts of every variant ->
+    canonical folding -> counts / sum.  Returns [V, N, R] float64 and / or float32."""
+    c = profiles(seqset, k, variants, out_kind=OUT_COUNTS_I32, seed=seed, edit_lists=edit_lists, seq_id0=seq_id0, pseudocount=1)
+    return normalize_counts(revcomp_fold(c, k), want64=want64, want32=want32)
+
+
 class Scaler(object):
     """StandardScaler statistics on the device (idelucs/utils.py:358-359, 404-405)."""
 

@@ -32,5 +32,19 @@ def kmer_counts(seq, k, counts):
 
 
 def cgr(seq, k, CGR):
-    """idelucs/kmers.pyx:53-123 (FCGR index order) — a 'next' row of the scope table."""
-    raise NotImplementedError("cgr() is outside the round-1 hot path (SURVEY §8f rank 4)")
+    """idelucs/kmers.pyx:53-123: accumulates the FCGR cell counts of ``seq`` INTO ``CGR`` (contiguous int32[4**k]);
+    same windows and alphabet as ``kmer_counts``, cell (cgr_i << k) + cgr_j.  Computed on the GPU as the counting
+    kernel followed by the index map (``featurise.cgr_batch``)."""
+    mv = memoryview(seq)
+    if mv.readonly:
+        raise BufferError("Object is not writable.")
+    c = np.asarray(CGR) if not isinstance(CGR, np.ndarray) else CGR
+    if c.dtype != np.int32:
+        raise ValueError("Buffer dtype mismatch, expected 'int' but got '%s'" % c.dtype.name)
+    if c.ndim != 1 or not c.flags["C_CONTIGUOUS"]:
+        raise ValueError("ndarray is not C-contiguous")
+    if c.size < 4 ** k:
+        raise ValueError("CGR must hold 4**k entries")
+    ss = SeqSet.from_sequences([bytes(mv)], alphabet="strict")
+    got = featurise.cgr_batch(featurise.kmer_counts_batch(ss, k), k)[0].cpu().numpy()
+    c[: 4 ** k] += got

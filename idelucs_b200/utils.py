@@ -149,9 +149,8 @@ def _explicit_lists_from_callable(fname, ss, transform):
 
 
 def kmersFasta(fname, k=6, transform=None, reduce=False):
-    """idelucs/utils.py:224-277 -> (names, float64[N, 4^k]) with the +1 pseudocount."""
-    if reduce:
-        raise NotImplementedError("reduce=True (canonical k-mer folding) is outside the round-1 hot path")
+    """idelucs/utils.py:224-277 -> (names, float64[N, 4^k]) with the +1 pseudocount (reduce=True: float64
+    [N, R] over the canonical k-mers, utils.py:246-247)."""
     ss = load_seqset(fname)
     if transform is None:
         variants, lists, seed = [ft.VariantSpec(ft.KIND_CLEAN)], None, 0
@@ -159,15 +158,24 @@ def kmersFasta(fname, k=6, transform=None, reduce=False):
         variants, lists, seed = [transform.spec(0)], None, _draw_seed()
     else:
         variants, lists, seed = [ft.VariantSpec(ft.KIND_EXPLICIT, explicit_idx=0)], _explicit_lists_from_callable(fname, ss, transform), 0
-    out = ft.profiles(ss, k, variants, out_kind=ft.OUT_FREQ_F64, seed=seed, edit_lists=lists)
+    if reduce:
+        out = ft.reduced_profiles(ss, k, variants, seed=seed, edit_lists=lists)
+    else:
+        out = ft.profiles(ss, k, variants, out_kind=ft.OUT_FREQ_F64, seed=seed, edit_lists=lists)
     return list(ss.names), out[0].cpu().numpy()
 
 
-def augment_device(ss, n_mimics, k=6, seed=None, group=None, seq_id0=0):
+def augment_device(ss, n_mimics, k=6, seed=None, group=None, seq_id0=0, reduce=False):
     """Device-resident AugmentFasta: returns (profiles float32 [n_mimics+1, N, 4^k] — slot 0 =
-    t_norm, slot j = mimic j — standardised with the t_norm statistics, and the Scaler)."""
+    t_norm, slot j = mimic j — standardised with the t_norm statistics, and the Scaler).
+    reduce=True: the canonical-k-mer profiles [n_mimics+1, N, R] (utils.py:246-247 applied to every pass)."""
     seed = _draw_seed() if seed is None else seed
     variants = ft.mimic_schedule(n_mimics)
+    if reduce:
+        x32 = ft.reduced_profiles(ss, k, variants, seed=seed, seq_id0=seq_id0, want64=False, want32=True)
+        sc = ft.Scaler.fit(x32[0], group=group)
+        V, n, R = x32.shape
+        return sc.transform32(x32.reshape(V * n, R)).reshape(V, n, R), sc, seed
     sc = ft.profile_stats(ss, k, variants[0], seed=seed, seq_id0=seq_id0, group=group)   # t_norm statistics, never materialised
     out = ft.profiles(ss, k, variants, out_kind=ft.OUT_STD_F32, seed=seed, mean=sc.mean32, scale=sc.scale32, seq_id0=seq_id0)
     return out, sc, seed
@@ -176,10 +184,8 @@ def augment_device(ss, n_mimics, k=6, seed=None, group=None, seq_id0=0):
 def AugmentFasta(sequence_file, n_mimics, k=6, reduce=False):
     """idelucs/utils.py:321-368 -> float32 numpy [n_pairs, 2, 4^k], mimic-major, column 0 =
     standardised t_norm, column 1 = standardised mimic (n_pairs = max(n_mimics, 2) * N)."""
-    if reduce:
-        raise NotImplementedError("reduce=True is outside the round-1 hot path")
     ss = load_seqset(sequence_file)
-    prof, _, _ = augment_device(ss, n_mimics, k=k)
+    prof, _, _ = augment_device(ss, n_mimics, k=k, reduce=reduce)
     V, n, F = prof.shape
     x = torch.empty((V - 1, n, 2, F), dtype=torch.float32, device=prof.device)
     x[:, :, 0, :] = prof[0].unsqueeze(0)
@@ -211,14 +217,16 @@ class PairBatchLoader(object):
     packed sequences by the mimic kernel (selection mode), which gives identical values."""
 
     def __init__(self, ss, n_mimics, k=6, batch_size=512, seed=None, materialize_bytes=8 << 30, group=None,
-                 seq_id0=0, drop_last=False):
+                 seq_id0=0, drop_last=False, reduce=False):
         self.ss, self.k, self.batch_size, self.drop_last = ss, k, batch_size, drop_last
         self.variants = ft.mimic_schedule(n_mimics)
         self.n_pairs = (len(self.variants) - 1) * ss.n
         self.seed = _draw_seed() if seed is None else seed
         self.seq_id0 = seq_id0
         F = 4 ** k
-        if len(self.variants) * ss.n * F * 4 <= materialize_bytes:
+        if reduce:   # canonical-k-mer profiles (model_size 'small'): always materialised
+            self.profiles, self.scaler, _ = augment_device(ss, n_mimics, k, seed=self.seed, group=group, seq_id0=seq_id0, reduce=True)
+        elif len(self.variants) * ss.n * F * 4 <= materialize_bytes:
             self.profiles, self.scaler, _ = augment_device(ss, n_mimics, k, seed=self.seed, group=group, seq_id0=seq_id0)
         else:
             self.scaler = ft.profile_stats(ss, k, self.variants[0], seed=self.seed, seq_id0=seq_id0, group=group)
@@ -247,9 +255,7 @@ class PairBatchLoader(object):
 
 def create_dataloader(sequence_file, n_mimics, k=6, batch_size=512, GT_file=None, reduce=False):
     """idelucs/utils.py:422-429 -> iterable of {'true','modified'} batches (shuffled every epoch)."""
-    if reduce:
-        raise NotImplementedError("reduce=True is outside the round-1 hot path")
-    return PairBatchLoader(load_seqset(sequence_file), n_mimics, k=k, batch_size=batch_size)
+    return PairBatchLoader(load_seqset(sequence_file), n_mimics, k=k, batch_size=batch_size, reduce=reduce)
 
 
 def SummaryFasta(fname, GT_file=None):
@@ -274,14 +280,14 @@ class SequenceDataset(torch.utils.data.Dataset):
     trainer feeds to the network (models.py:163 casts to float32)."""
 
     def __init__(self, fasta_file, k=6, transform=None, GT_file=None, reduce=False, group=None):
-        if reduce:
-            raise NotImplementedError("reduce=True is outside the round-1 hot path")
         self.names, self.lengths, self.GT, self.cluster_dis = SummaryFasta(fasta_file, GT_file)
         ss = load_seqset(fasta_file)
-        if transform is None:
+        if transform is None and not reduce:
             f64 = ft.profiles(ss, k, [ft.VariantSpec(ft.KIND_CLEAN)], out_kind=ft.OUT_FREQ_F64)[0]
+        elif transform is None:
+            f64 = ft.reduced_profiles(ss, k, [ft.VariantSpec(ft.KIND_CLEAN)])[0]
         else:
-            f64 = torch.from_numpy(kmersFasta(fasta_file, k, transform)[1]).to(ss.device)
+            f64 = torch.from_numpy(kmersFasta(fasta_file, k, transform, reduce=reduce)[1]).to(ss.device)
         sc = ft.Scaler.fit(f64, group=group)
         self._k64 = sc.transform64(f64)
         self.kmers32 = sc.transform64(f64, want32=True)

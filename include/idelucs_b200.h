@@ -154,6 +154,22 @@ int idl_standardize_f32(const float* d_x, float* d_out, int64_t n, int F, const 
 int idl_standardize_f64(const double* d_x, double* d_out64, float* d_out32, int64_t n, int F,
                         const double* d_mean64, const double* d_scale64, void* stream);
 
+/* K6 — index maps of an int32 count matrix [n, 4^k].
+ * idl_cgr_map: replaces cgr() (idelucs/kmers.pyx:53-123): d_cgr[row, (cgr_i << k) + cgr_j] (+)= d_counts[row, kmer] —
+ *   the FCGR cell of every k-mer (same windows as kmer_counts; verified cgr[cgr_index(m)] == kmer_counts[m]).
+ * idl_revcomp_canonical: the canonical k-mer list of kmer_rev_comp (idelucs/utils.py:208-221: kmer <= reverse
+ *   complement, increasing) into a HOST array of >= 4^k ints (NULL: only count); returns its length R.
+ * idl_revcomp_fold: replaces kmer_rev_comp on the integer count vector the reference applies it to
+ *   (utils.py:246-247, 268-269): d_out[row, r] = int((c[kmer_r] + c[revcomp(kmer_r)]) * 0.5) — the reference's
+ *   in-place float product is truncated back into its int32 array.
+ * idl_normalize_counts: counts / np.sum(counts) (utils.py:250, 272) per row of an int32 [n, R] matrix, float64
+ *   and / or float32(float64) output. */
+int idl_cgr_map(const int32_t* d_counts, int64_t n, int k, int32_t* d_cgr, int accumulate, void* stream);
+int idl_revcomp_canonical(int k, int32_t* h_index);
+int idl_revcomp_fold(const int32_t* d_counts, int64_t n, int k, const int32_t* d_canon, int R, int32_t* d_out,
+                     void* stream);
+int idl_normalize_counts(const int32_t* d_counts, int64_t n, int R, double* d_out64, float* d_out32, void* stream);
+
 /* K5 — replaces IID_loss / compute_joint (idelucs/LossFunctions.py:20-62), forward and
  * backward in one launch.  d_z1, d_z2: float32 [B, C] row-major.  Outputs (each optional,
  * NULL to skip): d_loss float32[1]; d_joint float32[C, C] (symmetrised, normalised,

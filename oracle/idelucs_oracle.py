@@ -186,16 +186,69 @@ def profile_from_seq(seq, k: int) -> np.ndarray:
     return counts / np.sum(counts)
 
 
+def cgr(seq, k: int, CGR: np.ndarray) -> None:
+    """idelucs/kmers.pyx:53-123: FCGR cell counts.  Strict alphabet (A, C, G, T; everything else resets);
+    a base appended at bit n_bp of cgr_i / cgr_j with (i, j)(A, C, G, T) = (1,0) (0,0) (0,1) (1,1) (:55-88 tables);
+    when k bases are held the cell (cgr_i << k) + cgr_j is incremented and the oldest base (bit 0) dropped
+    (:110-123)."""
+    enc = {ord("A"): (1, 0), ord("C"): (0, 0), ord("G"): (0, 1), ord("T"): (1, 1)}
+    ci = cj = n_bp = 0
+    for b in bytes(seq):
+        e = enc.get(b)
+        if e is None:
+            n_bp = 0; ci = 0; cj = 0
+        else:
+            ci |= e[0] << n_bp
+            cj |= e[1] << n_bp
+            n_bp += 1
+        if n_bp == k:
+            CGR[(ci << k) + cj] += 1
+            ci >>= 1; cj >>= 1
+            n_bp -= 1
+
+
+def reverse_complement(x: int, k: int) -> int:
+    """idelucs/utils.py:191-206: swap the two bits of every base, complement, reverse all 2k bits =
+    reversed order of the complemented bases."""
+    numbits = 2 * k
+    mask = 0xAAAAAAAA
+    x = ((x >> 1) & (mask >> 1)) | ((x << 1) & mask)
+    x = (1 << numbits) - 1 - x
+    rev = 0
+    for _ in range(numbits):
+        rev = (rev << 1) | (x & 1)
+        x >>= 1
+    return rev
+
+
+def kmer_rev_comp(kmer_counts_vec: np.ndarray, k: int) -> np.ndarray:
+    """idelucs/utils.py:208-221, including its in-place semantics: for every canonical k-mer (kmer <= revcomp, in
+    increasing order) ``v[kmer] += v[revcomp]; v[kmer] *= 0.5`` — on the int32 vector the reference passes
+    (:246-247, 268-269) the float product is truncated when stored back — and the canonical entries are returned."""
+    index = []
+    for kmer in range(4 ** k):
+        rc = reverse_complement(kmer, k)
+        if kmer <= rc:
+            index.append(kmer)
+            kmer_counts_vec[kmer] += kmer_counts_vec[rc]
+            kmer_counts_vec[kmer] = kmer_counts_vec[kmer] * 0.5   # element assignment casts back to the array dtype
+    return kmer_counts_vec[index]
+
+
 def kmersFasta(fname, k=6, transform=None, reduce=False):
-    """idelucs/utils.py:224-277 with reduce=False (the default 'linear' model path)."""
-    if reduce:
-        raise NotImplementedError("reduce=True (kmer_rev_comp) is a 'next' row, SURVEY §8f")
+    """idelucs/utils.py:224-277 (reduce=True: canonical folding of the +1-pseudocount int32 counts, :246-247)."""
     names, kmers = [], []
     for seq_id, seq in read_fasta(fname):
         names.append(seq_id)
         if transform:
             transform(seq)
-        kmers.append(profile_from_seq(seq, k))
+        if reduce:
+            counts = np.ones(4 ** k, dtype=np.int32)
+            kmer_counts(seq, k, counts)
+            counts = kmer_rev_comp(counts, k)
+            kmers.append(counts / np.sum(counts))
+        else:
+            kmers.append(profile_from_seq(seq, k))
     return names, np.array(kmers)
 
 
@@ -249,14 +302,14 @@ def mimic_transforms(n_mimics: int):
 
 def AugmentFasta(sequence_file, n_mimics, k=6, reduce=False, return_parts=False):
     """idelucs/utils.py:321-368."""
-    _, t_norm = kmersFasta(sequence_file, k=k, transform=transition_transversion(1e-2, 0.5e-2))
+    _, t_norm = kmersFasta(sequence_file, k=k, transform=transition_transversion(1e-2, 0.5e-2), reduce=reduce)
     feats = []
-    _, t_mut = kmersFasta(sequence_file, k=k, transform=transition(1e-2))
+    _, t_mut = kmersFasta(sequence_file, k=k, transform=transition(1e-2), reduce=reduce)
     feats.append(np.stack((t_norm, t_mut), axis=1))
-    _, t_mut = kmersFasta(sequence_file, k=k, transform=transversion(0.5e-2))
+    _, t_mut = kmersFasta(sequence_file, k=k, transform=transversion(0.5e-2), reduce=reduce)
     feats.append(np.stack((t_norm, t_mut), axis=1))
     for _ in range(n_mimics - 2):
-        _, t_mut = kmersFasta(sequence_file, k=k, transform=Random_N(20))
+        _, t_mut = kmersFasta(sequence_file, k=k, transform=Random_N(20), reduce=reduce)
         feats.append(np.stack((t_norm, t_mut), axis=1))
     x_train = np.concatenate(feats, axis=0).astype("float32")
     x_test = t_norm.astype("float32")

@@ -124,3 +124,29 @@ def test_training_recovers_clusters(golden_dir, fasta_files):
         _, acc = cluster_acc(np.array([labels[c] for c in GT]), y_pred)
         best = max(best, acc)
     assert best >= 0.85, best
+
+
+def test_cgr_and_reduce_match_oracle(fasta_files):
+    """kmers.cgr == the oracle's FCGR loop (bit-exact), kmersFasta(reduce=True) == the oracle's
+    canonical folding incl. its int truncation (bit-exact float64), SequenceDataset / AugmentFasta(reduce=True) shapes"""
+    import idelucs_b200.kmers as km
+    import idelucs_b200.utils as U
+    rng = np.random.default_rng(2)
+    for k in (2, 4, 6):
+        seq = bytearray(rng.integers(60, 90, size=5000, dtype=np.uint8).tobytes())
+        a = np.full(4 ** k, 3, np.int32)
+        b = np.full(4 ** k, 3, np.int32)
+        km.cgr(seq, k, a)
+        orc.cgr(seq, k, b)
+        assert np.array_equal(a, b)
+    for k in (4, 6):
+        n1, x1 = U.kmersFasta(fasta_files["Influenza-A"], k=k, reduce=True)
+        n2, x2 = orc.kmersFasta(fasta_files["Influenza-A"], k=k, reduce=True)
+        assert n1 == n2 and x1.shape == x2.shape and np.array_equal(x1, x2)
+    ds = U.SequenceDataset(fasta_files["Influenza-A"], k=4, reduce=True)
+    _, ref = orc.kmersFasta(fasta_files["Influenza-A"], k=4, reduce=True)
+    m, v, sc = orc.standard_scaler_fit(ref)
+    np.testing.assert_allclose(ds.kmers, (ref - m) / sc, rtol=0, atol=1e-10)
+    x = U.AugmentFasta(fasta_files["Influenza-A"], 3, k=4, reduce=True)
+    assert x.shape == (3 * 949, 2, 136) and x.dtype == np.float32 and np.isfinite(x).all()
+    assert abs(float(x[:949, 0].mean())) < 1e-3      # t_norm column is standardised with its own statistics

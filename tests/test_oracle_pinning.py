@@ -261,3 +261,56 @@ def test_live_iid_loss_and_grad():
         np.testing.assert_allclose(dz2, z2.grad.numpy(), rtol=1e-9, atol=1e-14)
         j = ref.LossFunctions.compute_joint(z1.detach(), z2.detach()).numpy()
         np.testing.assert_allclose(orc.compute_joint(z1.detach().numpy(), z2.detach().numpy()), j, rtol=1e-12)
+
+
+# ---- cgr / kmer_rev_comp ------------------------------------------------------------------
+def test_cgr_is_a_permutation_of_kmer_counts():
+    """the FCGR vector is the k-mer count vector under cgr_index (the map the CUDA kernel applies)"""
+    rng = np.random.default_rng(3)
+    alph = np.frombuffer(b"ACGTACGTACGTN", dtype=np.uint8)
+    for k in (1, 2, 3, 4, 6):
+        seq = alph[rng.integers(0, alph.size, size=700)].tobytes()
+        c = np.zeros(4 ** k, np.int32)
+        g = np.zeros(4 ** k, np.int32)
+        orc.kmer_counts(bytearray(seq), k, c)
+        orc.cgr(bytearray(seq), k, g)
+        idx = np.zeros(4 ** k, np.int64)
+        for m in range(4 ** k):
+            ci = cj = 0
+            for t in range(k):
+                d = (m >> (2 * (k - 1 - t))) & 3
+                ci |= (1 if d in (0, 3) else 0) << t
+                cj |= (d >> 1) << t
+            idx[m] = (ci << k) | cj
+        assert sorted(idx.tolist()) == list(range(4 ** k))
+        assert np.array_equal(g[idx], c)
+
+
+def test_reverse_complement_and_canonical_count():
+    assert orc.reverse_complement(1, 3) == 47                       # AAC -> GTT (SURVEY §8f)
+    for k, n in ((2, 10), (3, 32), (4, 136), (6, 2080)):
+        assert sum(1 for m in range(4 ** k) if m <= orc.reverse_complement(m, k)) == n
+    v = np.arange(1, 17, dtype=np.int32)
+    out = orc.kmer_rev_comp(v.copy(), 2)
+    # AA(0)<->TT(15): int((1 + 16) * 0.5) = 8 (truncated); palindrome AT(3): (4 + 4) * 0.5 = 4
+    assert out[0] == 8 and out.dtype == np.int32 and 4 in out.tolist()
+
+
+@pytest.mark.skipif(not ref_live.available(), reason="reference mount absent")
+def test_live_cgr_and_reduce(fasta_files):
+    """oracle == live reference: cgr() on random bytes, kmer_rev_comp on int32 counts, kmersFasta(reduce=True)"""
+    ref = ref_live.load()
+    from idelucs import kmers as rk, utils as ru
+    rng = np.random.default_rng(11)
+    for k in (2, 4, 6):
+        seq = bytearray(rng.integers(60, 90, size=3000, dtype=np.uint8).tobytes())
+        a = np.zeros(4 ** k, np.int32)
+        b = np.zeros(4 ** k, np.int32)
+        rk.cgr(seq, k, a)
+        orc.cgr(seq, k, b)
+        assert np.array_equal(a, b)
+        v = rng.integers(1, 50, size=4 ** k).astype(np.int32)
+        assert np.array_equal(ru.kmer_rev_comp(v.copy(), k), orc.kmer_rev_comp(v.copy(), k))
+    n1, x1 = ru.kmersFasta(fasta_files["Influenza-A"], k=4, reduce=True)
+    n2, x2 = orc.kmersFasta(fasta_files["Influenza-A"], k=4, reduce=True)
+    assert n1 == n2 and x1.shape == (949, 136) and np.array_equal(x1, x2)
