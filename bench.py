@@ -15,6 +15,8 @@ shard (weak scaling); the scaler statistics are all-gathered over NCCL inside th
 port driving the reference's own compiled Cython k-mer counter from oracle/_ref) on a bounded
 sample, with all host cores.
 """
+import os as _os
+_os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # rank 0 prints ONE JSON line on stdout; nothing else may
 import argparse
 import json
 import multiprocessing as mp
@@ -261,8 +263,8 @@ def run_ours(args):
             e2e_s = float(t.item())
         e2e = {"value": world * ne * V / e2e_s, "unit": "profiles/s", "h2d_bytes_per_step": int(ne * SEQ_LEN + (ne + 1) * 16),
                "d2h_bytes_per_step": int(V * ne * F * 4 + ne * 8), "ms_per_step": e2e_s * 1e3,
-               "sequences_per_step": ne, "api": "SeqSet.from_ascii(pinned host bytes) -> idl_pack/idl_profiles/idl_colstats/"
-               "idl_scaler_finalize -> pinned host float32 [51, n, 4096]"}
+               "sequences_per_step": ne, "api": "SeqSet.from_ascii(pinned host bytes) -> idl_pack / idl_profile_stats / "
+               "idl_scaler_finalize / idl_profiles -> pinned host float32 [51, n, 4096]"}
 
     # ---- secondary metric: training pairs/s (BASELINE configs[3]: 1 M x 2 kb sharded, B=512 per rank) ----
     train = None
