@@ -180,8 +180,9 @@ IDL_HD Window<K> load_window(const uint32_t* codes, const uint32_t* nmask, int q
 // of the number of counted windows.  Equivalent to re-running kmers.pyx:38-50 on the
 // mutated sequence, restricted to the windows the edit touches.
 // ---------------------------------------------------------------------------------------
-template <int K, class Upd>
-IDL_HD int apply_entry(const uint32_t* codes, const uint32_t* nmask, int L, const uint32_t* list, int n, int i,
+// `list` is anything indexable by int (a plain array, or a view that stitches per-block slots together).
+template <int K, class List, class Upd>
+IDL_HD int apply_entry(const uint32_t* codes, const uint32_t* nmask, int L, const List& list, int n, int i,
                        Upd upd) {
     constexpr int W = 2 * K - 1;
     constexpr uint32_t KMASK = (1u << (2 * K)) - 1u;

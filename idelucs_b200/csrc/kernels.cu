@@ -610,7 +610,10 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ProfSmem<K, NT>& sm = *reinterpret_cast<ProfSmem<K, NT>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (p.only_deferred && p.work_counter[1] == 0ull) return;   // the producer/consumer kernel took every item (stream order: its count is final)
+    if (p.only_deferred && p.work_counter[1] == 0ull) {   // the fast kernel took every item (stream order: its count is final)
+        if (OUT == OUT_STATS && tid == 0) p.stats_n[blockIdx.x] = 0.0;   // an empty part
+        return;
+    }
 
     const float magic = 8388608.0f - (float)p.pseudocount;
     const bool cached = p.n_vars <= SVARS && p.S <= SVARS;
@@ -631,6 +634,7 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
     double acc1[VPT][4], acc2[VPT][4];
     float shiftK[VPT][4];
     int n_acc = 0;
+    long long stats_cursor = blockIdx.x;   // thread 0 only
 #pragma unroll
     for (int vv = 0; vv < VPT; ++vv)
 #pragma unroll
@@ -639,7 +643,14 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
         __syncthreads();  // previous item fully done (also protects sm.item)
         if (tid == 0) {
             long long it;
-            if (OUT == OUT_STATS) it = (long long)blockIdx.x + (long long)n_acc * gridDim.x;   // static rows per CTA: reproducible sums
+            if (OUT == OUT_STATS) {   // static rows per CTA: reproducible sums
+                it = stats_cursor;
+                if (p.only_deferred) {    // only what the fast statistics kernel flagged
+                    while (it < p.n_items && !(p.status[it] & 2)) it += gridDim.x;
+                    if (it < p.n_items) atomicAnd(p.status + it, ~2);
+                }
+                stats_cursor = it + gridDim.x;
+            }
             else if (!p.only_deferred) it = (long long)atomicAdd(p.work_counter, 1ull);
             else if (p.work_counter[1] == 0ull) it = p.n_items;   // nothing was deferred
             else {
@@ -1020,6 +1031,7 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
 
 }  // namespace idl
 #include "profiles_pc.cuh"
+#include "stats_fast.cuh"
 namespace idl {
 
 // ---------------------------------------------------------------------------------------
@@ -1365,6 +1377,28 @@ static int profiles_impl(const uint32_t* d_codes, const uint32_t* d_nmask, const
     p.only_deferred = 0;
     { const char* e = getenv("IDL_PC_DBG"); p.dbg = e ? atoi(e) : 0; }
     p.stats_partials = d_stats_partials; p.stats_n = d_stats_n;
+    if (out_kind == OUT_STATS && k == 6 && d_status && getenv("IDL_NO_FAST_STATS") == nullptr &&
+        (h_vars[0].kind == IDL_KIND_CLEAN || h_vars[0].kind == IDL_KIND_TRANSITION || h_vars[0].kind == IDL_KIND_TRANSVERSION ||
+         h_vars[0].kind == IDL_KIND_BOTH || (h_vars[0].kind == IDL_KIND_RANDOM_N && h_vars[0].n_bp <= 0))) {
+        // pipelined register-accumulator kernel, one CTA per SM; what it defers (status bit 1) goes to the generic kernel below,
+        // which appends its own parts
+        static bool configured = false;
+        if (!configured) {
+            IDL_CUDA_CHECK(cudaFuncSetAttribute(stats_fast_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SfSmem)));
+            configured = true;
+        }
+        long long grid = sm_count();
+        if (grid > n_items) grid = n_items;
+        stats_fast_kernel<6><<<(unsigned)grid, SF_NT, sizeof(SfSmem), st>>>(p);
+        IDL_CUDA_CHECK(cudaGetLastError());
+        p.only_deferred = 1;
+        p.stats_partials += (size_t)grid * 2 * F;
+        p.stats_n += grid;
+        int g2 = 0;
+        const int rc = dispatch_out<6, 512>(p, out_kind, st, &g2);
+        if (n_parts_out) *n_parts_out = (int)grid + g2;
+        return rc;
+    }
     if (out_kind == OUT_STATS) {
         switch (k) {
             case 1: return dispatch_out<1, 64>(p, out_kind, st, n_parts_out);

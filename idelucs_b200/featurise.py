@@ -143,12 +143,14 @@ def profile_stats(seqset, k, variant, seed=0, seq_id0=0, edit_lists=None, group=
     varr = _variant_array([variant])
     n_parts = ctypes.c_int(0)
     d_eoff, d_ent = (None, None) if edit_lists is None else edit_lists
+    # bit 1 = "left to the generic kernel" (set and cleared inside the call)
+    status = torch.zeros((max(seqset.n, 1),), dtype=torch.int32, device=device)
     with torch.cuda.device(device):
         ws = _workspace(device, lib.idl_profiles_workspace_bytes(), "prof")
         _lib.check(lib.idl_profile_stats(_lib.ptr(seqset.codes), _lib.ptr(seqset.nmask), _lib.ptr(seqset.chunk_off), _lib.ptr(seqset.len),
                                          seqset.n, None, seqset.n, int(seq_id0), k, varr, ctypes.c_uint64(seed & (2 ** 64 - 1)),
                                          _lib.ptr(d_eoff), _lib.ptr(d_ent), int(pseudocount), _lib.ptr(parts), _lib.ptr(part_n),
-                                         max_parts, ctypes.byref(n_parts), None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+                                         max_parts, ctypes.byref(n_parts), _lib.ptr(status), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     parts, part_n = parts[: n_parts.value].contiguous(), part_n[: n_parts.value].contiguous()
     if seqset.n == 0:
         parts, part_n = torch.zeros((1, 2, F), dtype=torch.float64, device=device), torch.zeros((1,), dtype=torch.float64, device=device)

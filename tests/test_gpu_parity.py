@@ -386,6 +386,49 @@ def test_profile_stats_equals_matrix_fit(golden_dir, fasta_files, ft, SeqSet):
     assert sha(x.cpu().numpy()) == g["k5"]["x_train_sha256"]
 
 
+def test_fast_stats_kernel_equals_generic_and_matrix_fit(ft, SeqSet):
+    """the pipelined statistics kernel (k=6, stats_fast.cuh: register accumulators, prefetched 16-base
+    units, per-block edit slots) against the generic OUT_STATS path and against colstats of the
+    materialised float32 profiles (themselves bit-exact against the oracle): clean and Bernoulli
+    slots, ragged lengths incl. 0 / < k / block and chunk boundaries / deferred long ones, Ns, and
+    rates high enough that blocks overflow the fast generator (deferred to the generic kernel)"""
+    rng = np.random.default_rng(33)
+    alph = np.frombuffer(b"ACGTACGTACGTACGTACGTACGTACGTN", dtype=np.uint8)
+    lens = rng.integers(1, 12000, size=900)
+    lens[[0, 1, 2, 3, 4, 450, 899]] = [0, 3, 5, 6, 16, 16385, 70001]
+    lens[[200, 201, 202, 203, 204, 205]] = [16384, 16400, 33000, 16320, 16321, 16319]
+    lens[[300, 301, 302, 303]] = [63, 64, 65, 128]
+    seqs = [alph[rng.integers(0, alph.size, size=int(L))].tobytes() for L in lens]
+    seqs[7] = b"N" * 500
+    seqs[8] = b"ACGTAC" + b"N" * 40 + b"ACGTACG"
+    ss = SeqSet.from_sequences(seqs)
+    few = SeqSet.from_sequences(seqs[:40])
+    specs = [ft.VariantSpec(ft.KIND_CLEAN), ft.VariantSpec(ft.KIND_BOTH, 1e-2, 0.5e-2, rng_id=0),
+             ft.VariantSpec(ft.KIND_TRANSITION, p1=1e-2, rng_id=1), ft.VariantSpec(ft.KIND_TRANSVERSION, p2=0.5e-2, rng_id=2),
+             ft.VariantSpec(ft.KIND_BOTH, 0.06, 0.05, rng_id=5),      # many blocks with > 6 hits per stream: deferred items
+             ft.VariantSpec(ft.KIND_BOTH, 0.5, 0.4, rng_id=6)]        # every item deferred
+    for spec in specs:
+        x = ft.profiles(ss, 6, [spec], out_kind=ft.OUT_FREQ_F32, seed=17, seq_id0=3)[0]
+        a = ft.Scaler.fit(x)
+        b = ft.profile_stats(ss, 6, spec, seed=17, seq_id0=3)
+        os.environ["IDL_NO_FAST_STATS"] = "1"
+        try:
+            g = ft.profile_stats(ss, 6, spec, seed=17, seq_id0=3)
+        finally:
+            os.environ.pop("IDL_NO_FAST_STATS", None)
+        for other in (a, g):
+            assert torch.allclose(other.mean64, b.mean64, rtol=1e-13, atol=0), spec
+            assert torch.allclose(other.scale64, b.scale64, rtol=1e-9, atol=0), spec
+            assert float(((other.mean32 - b.mean32).abs() / other.mean32.abs()).max()) < 2e-7
+        c = ft.profile_stats(ss, 6, spec, seed=17, seq_id0=3)
+        assert torch.equal(b.mean64, c.mean64) and torch.equal(b.scale64, c.scale64)      # run-to-run identical
+        # float64 sums of the float32 frequencies on a small set
+        s = ft.profile_stats(few, 6, spec, seed=17)
+        xf = ft.profiles(few, 6, [spec], out_kind=ft.OUT_FREQ_F32, seed=17)[0].double().cpu().numpy()
+        np.testing.assert_allclose(s.mean64.cpu().numpy(), xf.mean(axis=0), rtol=1e-13, atol=0)
+        np.testing.assert_allclose(s.var64.cpu().numpy(), xf.var(axis=0), rtol=1e-8, atol=1e-30)
+
+
 def test_pc_kernel_repetitive_and_degenerate_sequences(ft, SeqSet):
     """fast kernel == generic kernel on inputs that stress its sparse fix-up logic: homopolymers and short tandem
     repeats (every Random_N removal of a variant hits the same few bins: multiplicities up to 120 in the biased
