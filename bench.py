@@ -95,14 +95,54 @@ def cpu_reference(n_seq_per_core, cores):
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 20 ms during the timed region."""
+    """SM clock / throttle reasons sampled every ~5 ms during the timed region, in-process through NVML
+    (a `nvidia-smi -lms` child needs longer to start than the timed region lasts); nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, False, None
+        self.sm, self.smax, self.reasons = [], None, set()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
+
+    def _sample(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.smax = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -115,6 +155,17 @@ class ClockSampler(object):
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            if not self.sm:
+                try:
+                    self._sample()
+                except Exception:
+                    pass
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is not None:
             self.proc.terminate()
         sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
@@ -126,7 +177,7 @@ class ClockSampler(object):
                         reasons.add(name)
         smax = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peak():
@@ -183,7 +234,7 @@ def run_ours(args):
         k_ev[1].record()
         return sc
 
-    launches_per_step = 5  # pass A: profiles_kernel<STATS>, scaler_finalize; pass B: rscale, profiles_pc + deferred-item pass
+    launches_per_step = 6  # pass A: stats_fast_kernel + deferred-item pass of profiles_kernel<STATS>, scaler_finalize; pass B: rscale, profiles_pc + deferred-item pass
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -266,6 +317,28 @@ def run_ours(args):
                "sequences_per_step": ne, "api": "SeqSet.from_ascii(pinned host bytes) -> idl_pack / idl_profile_stats / "
                "idl_scaler_finalize / idl_profiles -> pinned host float32 [51, n, 4096]"}
 
+    # ---- FASTA ingest: native scanner vs the reference-style Python line loop, same file ----
+    ingest = None
+    if rank == 0 and not args.no_ingest:
+        import tempfile
+        from idelucs_b200.seqset import read_fasta_native, read_fasta_raw
+        ni = min(n, 20000)
+        rows = ascii_dev[: ni * SEQ_LEN].view(ni, SEQ_LEN // 100, 100).cpu().numpy()      # 100-column FASTA lines
+        with tempfile.NamedTemporaryFile(suffix=".fa", delete=False) as fh:
+            nl = np.full((SEQ_LEN // 100, 1), 10, np.uint8)
+            for i in range(ni):
+                fh.write(b">seq_%d synthetic\n" % i)
+                fh.write(np.concatenate([rows[i], nl], axis=1).tobytes())
+            fpath = fh.name
+        fbytes = os.path.getsize(fpath)
+        read_fasta_native(fpath)
+        t0 = time.perf_counter(); names_n, flat_n, off_n = read_fasta_native(fpath); t_nat = time.perf_counter() - t0
+        t0 = time.perf_counter(); names_p, seqs_p = read_fasta_raw(fpath); t_py = time.perf_counter() - t0
+        assert names_n == names_p and flat_n.numpy().tobytes() == b"".join(seqs_p)
+        os.unlink(fpath)
+        ingest = {"file_bytes": fbytes, "records": ni, "native_GBps": fbytes / t_nat / 1e9, "python_line_loop_GBps": fbytes / t_py / 1e9,
+                  "api": "read_fasta_native: file -> host image -> idl_fasta_scan / idl_fasta_extract -> pinned flat bytes + offsets (one thread)"}
+
     # ---- secondary metric: training pairs/s (BASELINE configs[3]: 1 M x 2 kb sharded, B=512 per rank) ----
     train = None
     if args.train_steps > 0:
@@ -320,7 +393,7 @@ def run_ours(args):
                        "profiles_per_step": world * n * V, "output": "float32 [51, N, 4096] standardised, %.1f GB per GPU per step"
                                    % (V * n * F * 4 / 1e9), "cache": "inputs+outputs per step exceed L2 (126 MB) by >100x, no flush needed",
                        "mutation_rates": "transition 1e-2, transversion 5e-3, Random_N 20 (idelucs/utils.py:330-349)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "train": train}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu, "train": train, "fasta_ingest": ingest}
     print(json.dumps(line))
 
 
@@ -362,6 +435,7 @@ def main():
     ap.add_argument("--cpu_seqs_per_core", type=int, default=4096)
     ap.add_argument("--ref_seqs_per_core", type=int, default=1024)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_ingest", action="store_true", help="skip the FASTA ingest measurement")
     ap.add_argument("--train_steps", type=int, default=200, help="steps of the secondary training-pairs/s measurement (0 = skip)")
     ap.add_argument("--train_seqs", type=int, default=1000000, help="total sequences of the training workload (configs[3])")
     ap.add_argument("--kernel_timing", action="store_true", help="time the dominant kernel inside the timed loop (adds syncs)")

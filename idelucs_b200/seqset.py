@@ -44,6 +44,32 @@ def read_fasta_raw(fname):
     return names, seqs
 
 
+def read_fasta_native(fname, pinned=None):
+    """The same record iteration by the native scanner (idl_fasta_scan / idl_fasta_extract): the file is mapped
+    once and the stripped sequence lines are concatenated into one flat (pinned, when a GPU is present) uint8
+    tensor.  Returns (names, flat uint8 tensor, byte_off int64[n+1])."""
+    import ctypes
+    import os
+    lib = _lib.load()
+    if pinned is None:
+        pinned = torch.cuda.is_available()
+    size = os.path.getsize(fname)
+    # the file image is the page cache itself (read-only mapping): no copy before the scan
+    bnp = np.memmap(fname, dtype=np.uint8, mode="r") if size else np.zeros(1, np.uint8)
+    buf_ptr = ctypes.c_void_p(bnp.ctypes.data)
+    n_rec, n_seq = ctypes.c_int64(0), ctypes.c_int64(0)
+    _lib.check(lib.idl_fasta_scan(buf_ptr, size, ctypes.byref(n_rec), ctypes.byref(n_seq)))
+    n = n_rec.value
+    flat = torch.empty(max(n_seq.value, 1), dtype=torch.uint8, pin_memory=bool(pinned))
+    byte_off = np.zeros(n + 1, np.int64)
+    hdr_off, hdr_len = np.zeros(n, np.int64), np.zeros(n, np.int64)
+    _lib.check(lib.idl_fasta_extract(buf_ptr, size, n, _lib.ptr(flat), n_seq.value, byte_off.ctypes.data_as(ctypes.c_void_p),
+                                     hdr_off.ctypes.data_as(ctypes.c_void_p), hdr_len.ctypes.data_as(ctypes.c_void_p)))
+    mv = memoryview(bnp)
+    names = [bytes(mv[o:o + l]).decode() for o, l in zip(hdr_off.tolist(), hdr_len.tolist())]
+    return names, flat[: n_seq.value], byte_off
+
+
 class SeqSet(object):
     """n sequences packed on one GPU.  Tensors: codes (int32 words, 2 bit/base), nmask
     (int32 words, 1 bit/base), chunk_off (int64[n+1]), len (int32[n])."""
@@ -155,5 +181,20 @@ class SeqSet(object):
 
     @classmethod
     def from_fasta(cls, fname, device=None):
-        names, seqs = read_fasta_raw(fname)
+        """Parse once with the native scanner, one H2D copy of the flat pinned bytes, pack on the device.  Records
+        whose sequence lines hold interior whitespace (deleted by check_sequence, utils.py:45) take the host
+        compaction path of from_sequences."""
+        names, flat, byte_off = read_fasta_native(fname)
+        header_error = None
+        for i, h in enumerate(names):
+            try:
+                _check_header(h)
+            except ValueError as e:
+                header_error = (i, e)
+                break
+        self = cls.from_ascii(flat, byte_off, names=names, device=device, validate=False)
+        if not self.validate(header_error):
+            return self
+        fl = flat.numpy()
+        seqs = [fl[byte_off[i]:byte_off[i + 1]].tobytes() for i in range(len(names))]
         return cls.from_sequences(seqs, names=names, device=device)

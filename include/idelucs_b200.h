@@ -184,6 +184,19 @@ int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb,
                  float* d_joint, float* d_dz1, float* d_dz2, void* d_workspace, size_t workspace_bytes,
                  void* stream);
 
+/* F1 — FASTA ingest on the host.  Replaces the record loop of kmersFasta
+ * (idelucs/utils.py:229-261), which the reference re-runs on every pass (n_mimics + 1 times per training run,
+ * once more per predict): '#' lines skipped (:230); a '>' line closes the running record only while its id is
+ * non-empty (:233-252), then id = line[1:-1] (:253); other lines contribute line.strip() (:257); the last record
+ * is always closed (:259-261).  Two calls over the file image `buf` (HOST memory):
+ * idl_fasta_scan counts the records and the sequence bytes; idl_fasta_extract writes the concatenated sequence
+ * bytes (seq_out, ideally pinned: it is what idl_pack reads after one H2D copy), byte_off int64[n_records+1],
+ * and the id span of every record inside buf (hdr_off / hdr_len int64[n_records]).  Alphabet handling
+ * (check_sequence, :26-51) stays in idl_pack. */
+int idl_fasta_scan(const uint8_t* buf, int64_t nbytes, int64_t* n_records, int64_t* n_seq_bytes);
+int idl_fasta_extract(const uint8_t* buf, int64_t nbytes, int64_t n_records, uint8_t* seq_out, int64_t seq_cap,
+                      int64_t* byte_off, int64_t* hdr_off, int64_t* hdr_len);
+
 #ifdef __cplusplus
 }
 #endif
