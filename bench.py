@@ -353,7 +353,7 @@ def run_ours(args):
         st._d_ascii = None
         del a
         tr = ShardedTrainer(st, k=K, n_clusters=5, n_mimics=N_MIMICS, batch_sz=512, seed=7, seq_id0=rank * nt, world=world)
-        graphed = tr.enable_cuda_graph() if world == 1 else False   # DDP replicas stay eager in this round
+        graphed = tr.enable_cuda_graph()   # N > 1: the flat-gradient all-reduce is captured with the step
         for _ in range(10):
             tr.step()
         torch.cuda.synchronize()

@@ -5,8 +5,9 @@ Each rank owns a contiguous shard of the packed sequences, regenerates its pair 
 the fly with the mimic kernel (selection mode — the 1.6 TB x_train of the reference never
 exists), runs the reference's training step (idelucs/models.py:113-143: two forwards,
 (1-w) InfoNCE + w IIC loss, backward, RMSprop) with the fused IIC kernel, and all-reduces the
-gradients of the data-parallel MLP replicas over NCCL (torch DDP).  batch_sz is PER RANK (weak
-scaling in the batch, strong in the data set)."""
+gradients of the data-parallel MLP replicas over NCCL: the replicas' .grad tensors are views into ONE flat
+buffer, averaged by a single all-reduce per step (8.5 MB at k=6) that is captured in the step's CUDA graph
+together with everything else.  batch_sz is PER RANK (weak scaling in the batch, strong in the data set)."""
 import torch
 import torch.distributed as dist
 
@@ -29,7 +30,17 @@ class ShardedTrainer(object):
         net = NetLinear(4 ** k, n_clusters)
         net.apply(weights_init)
         net.to(self.dev)
-        self.net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[self.dev.index]) if world > 1 else net
+        self.net = net
+        self._flat_grad = None
+        if world > 1:   # identical replicas (same seed); gradients live in one flat buffer = one NCCL call per step
+            params = [p for p in net.parameters() if p.requires_grad]
+            self._flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=self.dev)
+            o = 0
+            for p in params:
+                p.grad = self._flat_grad[o:o + p.numel()].view_as(p)
+                o += p.numel()
+            for p in params:   # replicas must start identical whatever the RNG state of the rank was
+                dist.broadcast(p.data, src=0)
         self.opt = torch.optim.RMSprop(self.net.parameters(), lr=lr, weight_decay=0.01, capturable=True)
         self.lamb, self.weight, self.batch_sz = lamb, weight, batch_sz
         self.gen = torch.Generator(device=self.dev).manual_seed(seed * 1000003 + seq_id0 + 1)
@@ -49,15 +60,26 @@ class ShardedTrainer(object):
                     self._step_from_ids()
             torch.cuda.current_stream(self.dev).wait_stream(s)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=s):
-                self._loss = self._step_from_ids()
+            if self.world > 1:
+                # the NCCL watchdog thread polls events while this thread captures: only this thread's calls may
+                # invalidate the capture
+                torch.cuda.synchronize(self.dev)
+                with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
+                    self._loss = self._step_from_ids()
+            else:
+                with torch.cuda.graph(g, stream=s):
+                    self._loss = self._step_from_ids()
             self._graph = g
-            return True
         except Exception as e:  # noqa: BLE001 — eager fallback of an optimisation, not of the CUDA path
             self._graph = None
             self._graph_error = repr(e)
             torch.cuda.synchronize(self.dev)
-            return False
+        if self.world > 1:   # all ranks replay the graph or none does (a rank that fell back must not face captured collectives alone)
+            okf = torch.tensor([1.0 if self._graph is not None else 0.0], device=self.dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if float(okf.item()) < 1.0:
+                self._graph = None
+        return self._graph is not None
 
     def step(self):
         """one training step on a random batch of this rank's pairs; returns the loss tensor"""
@@ -69,11 +91,16 @@ class ShardedTrainer(object):
 
     def _step_from_ids(self):
         batch = self.loader.batch(self._ids)
-        self.opt.zero_grad(set_to_none=True)
+        if self._flat_grad is None:
+            self.opt.zero_grad(set_to_none=True)
+        else:
+            self._flat_grad.zero_()
         z1, h1 = self.net(batch["true"])
         z2, h2 = self.net(batch["modified"])
         loss = (1 - self.weight) * info_nce_loss(h1, h2, 0.85) + self.weight * IID_loss(z1, z2, lamb=self.lamb)
         loss.backward()
+        if self._flat_grad is not None:
+            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.AVG)
         self.opt.step()
         return loss.detach()
 
@@ -84,7 +111,7 @@ class ShardedTrainer(object):
         f64 = ft.profiles(seqset, k, [ft.VariantSpec(ft.KIND_CLEAN)], out_kind=ft.OUT_FREQ_F64)[0]
         sc = ft.Scaler.fit(f64, group=dist.group.WORLD if self.world > 1 else None)
         x = sc.transform64(f64, want32=True)
-        net = self.net.module if self.world > 1 else self.net
+        net = self.net
         net.eval()
         preds = torch.cat([torch.max(net(x[b:b + batch])[0], 1)[1] for b in range(0, x.shape[0], batch)])
         net.train()

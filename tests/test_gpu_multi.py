@@ -1,6 +1,7 @@
 """Two-rank NCCL test of the sharded path (needs >= 2 GPUs; skipped otherwise): scaler
 statistics merged over ranks == single-GPU statistics, sharded mimics identical to the
-unsharded ones (global sequence ids in the RNG), DDP training step, all-gathered predictions."""
+unsharded ones (global sequence ids in the RNG), data-parallel training step (eager and CUDA-graphed, flat-gradient
+all-reduce), all-gathered predictions."""
 import os
 import sys
 
@@ -41,12 +42,22 @@ def _worker(rank, world, port, ret):
         ok = ok and torch.allclose(prof, pf[:, lo:hi], rtol=1e-5, atol=1e-5)
         ok = ok and bool((prof == pf[:, lo:hi]).float().mean() > 0.99)
     tr = ShardedTrainer(ss, k=k, n_clusters=4, n_mimics=6, batch_sz=64, seed=3, seq_id0=lo, world=world)
+    graphed = tr.enable_cuda_graph()                            # step + flat-gradient all-reduce in one CUDA graph
     losses = [float(tr.step().item()) for _ in range(4)]
     ok = ok and all(np.isfinite(losses))
     w = next(tr.net.parameters()).detach().clone()
     ws = [torch.empty_like(w) for _ in range(world)]
     dist.all_gather(ws, w)
-    ok = ok and all(torch.equal(ws[0], x) for x in ws)          # replicas stay identical (DDP all-reduce)
+    ok = ok and all(torch.equal(ws[0], x) for x in ws)          # replicas stay identical (averaged gradients)
+    if rank == 0:
+        ret["graph"] = bool(graphed)
+        ret["graph_error"] = getattr(tr, "_graph_error", "")
+    tr._graph = None                                            # the same step eagerly
+    losses = [float(tr.step().item()) for _ in range(3)]
+    ok = ok and all(np.isfinite(losses))
+    w = next(tr.net.parameters()).detach().clone()
+    dist.all_gather(ws, w)
+    ok = ok and all(torch.equal(ws[0], x) for x in ws)
     preds = tr.predict(ss, k=k)
     ok = ok and preds.shape[0] == n
     t = torch.tensor([1.0 if ok else 0.0], device=dev)
@@ -56,6 +67,7 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+@pytest.mark.timeout(240)
 def test_two_gpu_sharding():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -64,3 +76,4 @@ def test_two_gpu_sharding():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, 29700 + os.getpid() % 200, ret), nprocs=2, join=True)
     assert ret["ok"]
+    assert ret["graph"], ret["graph_error"]
