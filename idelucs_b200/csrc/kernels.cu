@@ -207,6 +207,7 @@ struct ProfSmem {
     int scan[NT / 32 + 2];
     int nvalid;
     long long item;
+    unsigned dqmask[NT / 32];         // deferred mode: which of the NT items examined last are flagged
     VarDesc svars[SVARS];             // descriptor cache (first SVARS variants)
     long long sout_off[SVARS];
 };
@@ -634,33 +635,59 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
     double acc1[VPT][4], acc2[VPT][4];
     float shiftK[VPT][4];
     int n_acc = 0;
-    long long stats_cursor = blockIdx.x;   // thread 0 only
+    long long stats_cursor = blockIdx.x;   // OUT_STATS: next own item (thread 0; every thread in deferred mode)
+    long long dq_base = 0;                 // deferred mode: first item of the NT examined last
+    int dq_pos = NT;                       // deferred mode: next bit of sm.dqmask to look at (NT: refill)
 #pragma unroll
     for (int vv = 0; vv < VPT; ++vv)
 #pragma unroll
         for (int e = 0; e < 4; ++e) { acc1[vv][e] = 0.0; acc2[vv][e] = 0.0; shiftK[vv][e] = 0.f; }
     for (;;) {
         __syncthreads();  // previous item fully done (also protects sm.item)
-        if (tid == 0) {
-            long long it;
-            if (OUT == OUT_STATS) {   // static rows per CTA: reproducible sums
-                it = stats_cursor;
-                if (p.only_deferred) {    // only what the fast statistics kernel flagged
-                    while (it < p.n_items && !(p.status[it] & 2)) it += gridDim.x;
-                    if (it < p.n_items) atomicAnd(p.status + it, ~2);
+        long long item;
+        if (p.only_deferred) {
+            // deferred mode: the CTA looks at NT status words at a time (one per thread, ballot masks in shared memory)
+            // instead of one global round trip per item examined.  OUT_STATS: static rows per CTA (its own items in
+            // ascending order -> reproducible sums); otherwise chunks of NT items from a global cursor.
+            for (;;) {
+                item = -1;
+                while (dq_pos < NT) {
+                    const unsigned w = sm.dqmask[dq_pos >> 5] >> (dq_pos & 31);
+                    if (w) {
+                        const int b = dq_pos + __ffs(w) - 1;
+                        dq_pos = b + 1;
+                        item = dq_base + (OUT == OUT_STATS ? (long long)b * gridDim.x : (long long)b);
+                        break;
+                    }
+                    dq_pos = (dq_pos | 31) + 1;
                 }
-                stats_cursor = it + gridDim.x;
+                if (item >= 0) break;
+                __syncthreads();   // everybody is done with the old masks
+                if (OUT == OUT_STATS) { dq_base = stats_cursor; stats_cursor += (long long)NT * gridDim.x; }
+                else {
+                    if (tid == 0) sm.item = (long long)atomicAdd(p.work_counter + 2, (unsigned long long)NT);
+                    __syncthreads();
+                    dq_base = sm.item;
+                }
+                if (dq_base >= p.n_items) { item = p.n_items; break; }
+                const long long it = dq_base + (OUT == OUT_STATS ? (long long)tid * gridDim.x : (long long)tid);
+                const bool hit = it < p.n_items && (p.status[it] & 2);
+                if (hit) atomicAnd(p.status + it, ~2);
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) sm.dqmask[wid] = m;
+                __syncthreads();
+                dq_pos = 0;
             }
-            else if (!p.only_deferred) it = (long long)atomicAdd(p.work_counter, 1ull);
-            else if (p.work_counter[1] == 0ull) it = p.n_items;   // nothing was deferred
-            else {
-                do { it = (long long)atomicAdd(p.work_counter + 2, 1ull); } while (it < p.n_items && !(p.status[it] & 2));
-                if (it < p.n_items) atomicAnd(p.status + it, ~2);
+        } else {
+            if (tid == 0) {
+                long long it;
+                if (OUT == OUT_STATS) { it = stats_cursor; stats_cursor = it + gridDim.x; }   // static rows per CTA: reproducible sums
+                else it = (long long)atomicAdd(p.work_counter, 1ull);
+                sm.item = it;
             }
-            sm.item = it;
+            __syncthreads();
+            item = sm.item;
         }
-        __syncthreads();
-        const long long item = sm.item;
         if (item >= p.n_items) break;
         const long long seq = p.sidx ? (long long)p.sidx[item] : item;
         ItemCtx cx;
