@@ -63,14 +63,25 @@ def compute_joint(x_out, x_tf_out):
     return joint
 
 
+_targets = {}
+
+
+def info_nce_loss_stacked(h, temperature):
+    """info_nce_loss on the two views already stacked as one [2n, d] tensor (rows 0..n-1 = first view)."""
+    n2 = h.shape[0]
+    feats = F.normalize(h.float(), dim=1)
+    logits = (feats @ feats.T) / temperature
+    logits.fill_diagonal_(float("-inf"))      # in place: the division's backward does not need its output
+    key = (n2, logits.device)
+    if key not in _targets:
+        idx = torch.arange(n2, device=logits.device)
+        _targets[key] = (idx + n2 // 2) % n2
+    return F.cross_entropy(logits, _targets[key])
+
+
 def info_nce_loss(z1, z2, temperature):
     """SimCLR NT-Xent (idelucs/LossFunctions.py:65-98).  The reference gathers [positive,
     negatives] per row with boolean masks and takes cross-entropy against label 0; that equals
     the cross-entropy of the self-masked similarity row against the index of the other view,
     which needs no mask gathers (and no host synchronisation)."""
-    n = z1.shape[0]
-    feats = F.normalize(torch.cat((z1, z2), 0).float(), dim=1)
-    logits = (feats @ feats.T) / temperature
-    idx = torch.arange(2 * n, device=logits.device)
-    logits = logits.masked_fill(idx.unsqueeze(0) == idx.unsqueeze(1), float("-inf"))
-    return F.cross_entropy(logits, (idx + n) % (2 * n))
+    return info_nce_loss_stacked(torch.cat((z1, z2), 0), temperature)

@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 from . import featurise as ft
-from .LossFunctions import IID_loss, info_nce_loss
+from .LossFunctions import IID_loss, info_nce_loss, info_nce_loss_stacked
 from .PytorchUtils import NetLinear
 from .models import weights_init
 
@@ -95,9 +95,16 @@ class ShardedTrainer(object):
             self.opt.zero_grad(set_to_none=True)
         else:
             self._flat_grad.zero_()
-        z1, h1 = self.net(batch["true"])
-        z2, h2 = self.net(batch["modified"])
-        loss = (1 - self.weight) * info_nce_loss(h1, h2, 0.85) + self.weight * IID_loss(z1, z2, lamb=self.lamb)
+        if "both" in batch:   # one pass over the stacked [2B, F] batch: same per-row math as the reference's two forwards
+            B = batch["true"].shape[0]   # (models.py:121-122; dropout masks are independent per row either way), half the launches
+            z, h = self.net(batch["both"])
+            nce = info_nce_loss_stacked(h, 0.85)
+            z1, z2 = z[:B], z[B:]
+        else:
+            z1, h1 = self.net(batch["true"])
+            z2, h2 = self.net(batch["modified"])
+            nce = info_nce_loss(h1, h2, 0.85)
+        loss = (1 - self.weight) * nce + self.weight * IID_loss(z1, z2, lamb=self.lamb)
         loss.backward()
         if self._flat_grad is not None:
             dist.all_reduce(self._flat_grad, op=dist.ReduceOp.AVG)

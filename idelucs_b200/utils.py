@@ -245,7 +245,7 @@ class PairBatchLoader(object):
         sel = torch.stack([torch.zeros_like(mim), mim], dim=1).to(torch.int32).contiguous()
         out = ft.profiles(self.ss, self.k, self.variants, out_kind=ft.OUT_STD_F32, seed=self.seed, sidx=sidx.to(torch.int32),
                           sel=sel, mean=self.scaler.mean32, scale=self.scaler.scale32, seq_id0=self.seq_id0)
-        return {"true": out[0], "modified": out[1]}
+        return {"true": out[0], "modified": out[1], "both": out.view(-1, out.shape[-1])}   # 'both' = the two sides stacked, no copy
 
     def __iter__(self):
         perm = torch.randperm(self.n_pairs, device=self.ss.device)

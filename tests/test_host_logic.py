@@ -34,6 +34,10 @@ def test_info_nce_equals_reference_formulation():
         gw = torch.autograd.grad(want, a)[0]
         gg = torch.autograd.grad(got, a)[0]
         assert torch.allclose(gw, gg, atol=1e-6)
+        from idelucs_b200.LossFunctions import info_nce_loss_stacked
+        st = info_nce_loss_stacked(torch.cat((a, b), 0), 0.85)      # the training step's stacked form
+        assert abs(want.item() - st.item()) < 1e-6
+        assert torch.allclose(gw, torch.autograd.grad(st, a)[0], atol=1e-6)
 
 
 def test_check_sequence_shim_matches_oracle():
