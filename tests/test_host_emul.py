@@ -246,3 +246,23 @@ def test_fast_block_generator_equals_generic(emul):
                 if p1 <= 0.01:
                     assert nov.value == 0
     assert total_over > 0  # the high-rate cases do exercise the overflow report
+
+
+def test_block_slot_view_equals_flat_list(emul):
+    """the statistics kernel applies the edits of a 64-base block through a view of three per-block slots
+    (previous block, own block, first entry of the next) instead of the whole sorted list: the histogram
+    deltas must be identical — also at rates where neighbouring edits share windows all the time"""
+    rng = np.random.default_rng(123)
+    checked = 0
+    for L, n_rate, p1, p2 in [(10000, 0.0, 1e-2, 0.5e-2), (2000, 0.01, 1e-2, 0.5e-2), (1409, 0.05, 0.04, 0.03),
+                              (700, 0.1, 0.07, 0.05), (193, 0.0, 0.09, 0.09), (64, 0.2, 0.05, 0.05), (5, 0.0, 0.3, 0.3)]:
+        s = rand_seq(rng, L, n_rate)
+        codes, nmask, _ = pack(emul, s)
+        for kind in (orc.KIND_BOTH, orc.KIND_TRANSITION, orc.KIND_TRANSVERSION):
+            for seq_id in range(8):
+                nov = ctypes.c_int(0)
+                bad = emul.emul_slots_vs_flat(_ptr(codes), _ptr(nmask), L, 6, ctypes.c_ulonglong(99), seq_id, kind, kind,
+                                              ctypes.c_double(p1), ctypes.c_double(p2), ctypes.byref(nov))
+                assert bad == 0, (L, p1, kind, seq_id)
+                checked += 0 if nov.value else 1
+    assert checked > 100
