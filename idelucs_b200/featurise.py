@@ -297,21 +297,37 @@ class Scaler(object):
         return out32 if want32 else out64
 
 
+def _merge_local(parts, part_n):
+    """this rank's parts -> ONE (mean, M2, rows) part, fixed-order Chan merge (idl_scaler_finalize on the device; the
+    same recurrence in torch for host tensors, which only the gloo host-logic tests use)"""
+    if parts.is_cuda:
+        s = Scaler.from_partials(parts, part_n)
+        n = part_n.sum()
+        return s.mean64, s.var64 * n, n
+    F = parts.shape[2]
+    na, ma, M2 = 0.0, torch.zeros(F, dtype=torch.float64), torch.zeros(F, dtype=torch.float64)
+    for g in range(parts.shape[0]):
+        nb = float(part_n[g])
+        if nb <= 0:
+            continue
+        delta = parts[g, 0] - ma
+        nt = na + nb
+        ma = ma + delta * (nb / nt)
+        M2 = M2 + parts[g, 1] + delta * delta * (na * nb / nt)
+        na = nt
+    return ma, M2, torch.tensor(na, dtype=torch.float64)
+
+
 def gather_partials(parts, part_n, group=None):
-    """all-gather variable-length scaler partials over the ranks (padding with empty parts)."""
+    """Scaler partials of the whole group: every rank first merges its own parts into one, then the ranks exchange
+    2·F + 1 doubles each (all-gather, rank order) — no host synchronisation, 64 KB per rank at k = 6 instead of
+    one part per CTA.  Returns ([world, 2, F], [world])."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    P = torch.tensor([parts.shape[0]], dtype=torch.int64, device=parts.device)
-    allP = [torch.zeros_like(P) for _ in range(world)]
-    dist.all_gather(allP, P, group=group)
-    maxP = int(max(int(p.item()) for p in allP))
     F = parts.shape[2]
-    pad = torch.zeros((maxP, 2, F), dtype=torch.float64, device=parts.device)
-    padn = torch.zeros((maxP,), dtype=torch.float64, device=parts.device)
-    pad[: parts.shape[0]] = parts
-    padn[: parts.shape[0]] = part_n
-    gp = [torch.empty_like(pad) for _ in range(world)]
-    gn = [torch.empty_like(padn) for _ in range(world)]
-    dist.all_gather(gp, pad, group=group)
-    dist.all_gather(gn, padn, group=group)
-    return torch.cat(gp, 0).contiguous(), torch.cat(gn, 0).contiguous()
+    mean, M2, n = _merge_local(parts, part_n)
+    packed = torch.cat([mean.reshape(-1), M2.reshape(-1), n.reshape(1)]).contiguous()
+    out = [torch.empty_like(packed) for _ in range(world)]
+    dist.all_gather(out, packed, group=group)
+    out = torch.stack(out, 0)
+    return out[:, : 2 * F].reshape(world, 2, F).contiguous(), out[:, 2 * F].contiguous()
