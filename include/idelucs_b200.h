@@ -104,8 +104,10 @@ size_t idl_profiles_workspace_bytes(void);
  * val 0..3 = set A/C/G/T, 4 = set N; position-sorted and unique per list), n_seqs_total =
  * number of sequences the CSR is indexed over.  d_mean/d_scale: float32[4^k] for
  * IDL_OUT_STD_F32.  accumulate != 0 (COUNTS only) adds into d_out like kmers.pyx does.
- * d_status int32[n_items] (optional): bit 0 set when an item's edit list overflowed the
- * on-chip list (the item's outputs for that variant are then unmutated). */
+ * d_status int32[n_items], zero on entry (optional): bit 0 set when an item's edit list overflowed the
+ * on-chip list (the item's outputs for that variant are then unmutated).  Bit 1 is used inside the call (k = 6 float
+ * outputs: items the producer/consumer kernel hands to the generic kernel) and is clear again when the work is done;
+ * without d_status only the generic kernel runs. */
 int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
                  const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
                  int64_t seq_id0, int k, const idl_variant* variants, int n_variants, const int32_t* d_sel,
@@ -119,7 +121,11 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
  * every CTA accumulates shifted float64 column sums of the rows it produces and emits one
  * (count, mean, M2) part; feed d_partials / d_part_n / *n_parts to idl_scaler_finalize (after
  * all-gathering the parts of every rank when sharded).  d_partials double[max_parts][2][4^k],
- * d_part_n double[max_parts]; max_parts >= 8 x number of SMs. */
+ * d_part_n double[max_parts]; max_parts >= 8 x number of SMs.  Rows are assigned to CTAs statically, so the sums are
+ * run-to-run identical.  d_status int32[n_items], zero on entry (optional): with it, k = 6 and a clean / transition /
+ * transversion / combined variant the pipelined kernel (csrc/stats_fast.cuh) takes the call; it marks the few items it
+ * cannot take (bit 1: longer than 16 320 bases, a 64-base block with more than 6 hits of one mutation stream), the
+ * generic kernel folds those into further parts and clears the bit again.  Bit 0 as in idl_profiles. */
 int idl_profile_stats(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off, const int32_t* d_len,
                       int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items, int64_t seq_id0, int k,
                       const idl_variant* variant, uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits,
