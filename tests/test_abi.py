@@ -148,3 +148,22 @@ def test_native_fasta_scanner_argument_validation():
     assert lib.idl_fasta_extract(buf, 12, 1, out, 4, off, ho, hl) == 1          # record count mismatch
     assert lib.idl_fasta_extract(buf, 12, 2, out, 4, off, ho, hl) == 0
     assert out.raw == b"ACGT" and list(off) == [0, 2, 4] and list(ho) == [1, 7] and list(hl) == [1, 1]
+
+
+def test_native_fasta_scanner_fuzz(tmp_path):
+    """random byte soup made of the bytes that matter to the record loop ('>', '#', newlines, CR, blanks, tabs,
+    vertical tab, bases): the native scanner and the literal reference loop must agree on every file"""
+    from idelucs_b200.seqset import read_fasta_native
+    rng = np.random.default_rng(2024)
+    alphabet = np.frombuffer(b">#\n\n\n\r \t\x0b\x0cACGTNacgtxyz-", dtype=np.uint8)
+    pth = os.path.join(str(tmp_path), "fuzz.fa")
+    for trial in range(300):
+        n = int(rng.integers(0, 200))
+        data = alphabet[rng.integers(0, alphabet.size, size=n)].tobytes()
+        with open(pth, "wb") as fh:
+            fh.write(data)
+        want_names, want_seqs = _ref_loop(pth)
+        names, flat, off = read_fasta_native(pth, pinned=False)
+        flat = flat.numpy()
+        assert names == want_names, data
+        assert [flat[off[i]:off[i + 1]].tobytes() for i in range(len(names))] == want_seqs, data
