@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(SF_NT, 1) stats_fast_kernel(const ProfParams p
     const long long G = gridDim.x;
     const long long n_items = p.n_items;
     const VarDesc vd = p.vars[0];
-    const bool bern = (vd.kind == KIND_TRANSITION || vd.kind == KIND_TRANSVERSION || vd.kind == KIND_BOTH) && !(p.dbg & 1);
-    const bool dbg_s2 = !(p.dbg & 8);
+    const bool bern = (vd.kind == KIND_TRANSITION || vd.kind == KIND_TRANSVERSION || vd.kind == KIND_BOTH) && !(p.dbg & 0x100);   // development switches (IDL_PC_DBG bits 8..11): stages off for timing, results are then wrong
+    const bool dbg_s2 = !(p.dbg & 0x800);
 
 #pragma unroll
     for (int r = 0; r < 4; ++r) reinterpret_cast<int4*>(sm.hist[r])[tid] = make_int4(0, 0, 0, 0);
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(SF_NT, 1) stats_fast_kernel(const ProfParams p
             if (nu > 0) {
                 int nv = 0;
                 if (tid < nu) {
-                    if (!(p.dbg & 2)) nv = sf_count_unit<K>(ua, tid, sm.hist[r]);
+                    if (!(p.dbg & 0x200)) nv = sf_count_unit<K>(ua, tid, sm.hist[r]);
                     sm.codes[r][tid] = ua.w;
                     if (!(tid & 1)) sm.mask[r][tid >> 1] = ua.m;
                 } else if (tid < nu + 4) {   // slack behind the sequence (window reads run one word past the end)
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(SF_NT, 1) stats_fast_kernel(const ProfParams p
                     atomicOr(p.status + ((long long)blockIdx.x + n * G), 2);
                     atomicAdd(p.work_counter + 1, 1ull);
                 }
-            } else if (!(p.dbg & 4)) {
+            } else if (!(p.dbg & 0x400)) {
                 const int total = F * pc + sm.nvalid[(int)n & 7];
                 const float ftot = (float)total;
                 const float y = 1.0f / ftot;

@@ -17,9 +17,9 @@ def main():
     variants = ft.mimic_schedule(50)
     for name, spec, env in (("both fast", variants[0], {}), ("both generic", variants[0], {"IDL_NO_FAST_STATS": "1"}),
                             ("clean fast", ft.VariantSpec(ft.KIND_CLEAN), {}),
-                            ("both fast, no S1/S2", variants[0], {"IDL_PC_DBG": "1"}), ("both fast, no S2", variants[0], {"IDL_PC_DBG": "8"}),
-                            ("both fast, no count", variants[0], {"IDL_PC_DBG": "2"}), ("both fast, no fold", variants[0], {"IDL_PC_DBG": "4"}),
-                            ("both fast, only S1", variants[0], {"IDL_PC_DBG": "14"}), ("nothing", variants[0], {"IDL_PC_DBG": "15"})):
+                            ("both fast, no S1/S2", variants[0], {"IDL_PC_DBG": "256"}), ("both fast, no S2", variants[0], {"IDL_PC_DBG": "2048"}),
+                            ("both fast, no count", variants[0], {"IDL_PC_DBG": "512"}), ("both fast, no fold", variants[0], {"IDL_PC_DBG": "1024"}),
+                            ("both fast, only S1", variants[0], {"IDL_PC_DBG": "3584"}), ("nothing", variants[0], {"IDL_PC_DBG": "3840"})):
         os.environ.update(env)
         fs = lambda: ft.profile_stats(ss, 6, spec, seed=1)
         fs(); torch.cuda.synchronize()
