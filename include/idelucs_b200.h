@@ -197,7 +197,9 @@ int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb,
  * is always closed (:259-261).  Two calls over the file image `buf` (HOST memory):
  * idl_fasta_scan counts the records and the sequence bytes; idl_fasta_extract writes the concatenated sequence
  * bytes (seq_out, ideally pinned: it is what idl_pack reads after one H2D copy), byte_off int64[n_records+1],
- * and the id span of every record inside buf (hdr_off / hdr_len int64[n_records]).  Alphabet handling
+ * and the id span of every record inside buf (hdr_off / hdr_len int64[n_records]).  The image is cut at line
+ * boundaries and walked by up to 32 host threads; an idl_fasta_extract that directly follows idl_fasta_scan on the same
+ * thread and image (which must not change in between) reuses its line index.  Alphabet handling
  * (check_sequence, :26-51) stays in idl_pack. */
 int idl_fasta_scan(const uint8_t* buf, int64_t nbytes, int64_t* n_records, int64_t* n_seq_bytes);
 int idl_fasta_extract(const uint8_t* buf, int64_t nbytes, int64_t n_records, uint8_t* seq_out, int64_t seq_cap,

@@ -123,10 +123,16 @@ def test_native_fasta_scanner_equals_reference_loop(tmp_path, fasta_files):
     paths += [pth, fasta_files["Influenza-A"], fasta_files["Actinopterygii"]]
     for pth in paths:
         want_names, want_seqs = _ref_loop(pth)
-        names, flat, off = read_fasta_native(pth, pinned=False)
-        flat = flat.numpy()
-        assert names == want_names, pth
-        assert [flat[off[i]:off[i + 1]].tobytes() for i in range(len(names))] == want_seqs, pth
+        for env in ({}, {"IDL_FASTA_CHUNK": "64", "IDL_FASTA_THREADS": "5"}, {"IDL_FASTA_CHUNK": "1", "IDL_FASTA_THREADS": "32"}):
+            os.environ.update(env)          # forced: many chunks per file, cut anywhere (the parallel stitching path)
+            try:
+                names, flat, off = read_fasta_native(pth, pinned=False)
+            finally:
+                for k in env:
+                    os.environ.pop(k)
+            flat = flat.numpy()
+            assert names == want_names, (pth, env)
+            assert [flat[off[i]:off[i + 1]].tobytes() for i in range(len(names))] == want_seqs, (pth, env)
         assert (names, want_seqs) == tuple(read_fasta_raw(pth))
     for stem in ("Influenza-A", "Actinopterygii"):      # the oracle's loop (which also runs check_sequence) on the real files
         names, flat, off = read_fasta_native(fasta_files[stem], pinned=False)
@@ -157,13 +163,19 @@ def test_native_fasta_scanner_fuzz(tmp_path):
     rng = np.random.default_rng(2024)
     alphabet = np.frombuffer(b">#\n\n\n\r \t\x0b\x0cACGTNacgtxyz-", dtype=np.uint8)
     pth = os.path.join(str(tmp_path), "fuzz.fa")
-    for trial in range(300):
+    for trial in range(600):
         n = int(rng.integers(0, 200))
         data = alphabet[rng.integers(0, alphabet.size, size=n)].tobytes()
         with open(pth, "wb") as fh:
             fh.write(data)
         want_names, want_seqs = _ref_loop(pth)
-        names, flat, off = read_fasta_native(pth, pinned=False)
+        env = {} if trial % 3 == 0 else {"IDL_FASTA_CHUNK": str(1 + trial % 37), "IDL_FASTA_THREADS": str(2 + trial % 9)}
+        os.environ.update(env)              # two thirds of the trials: several chunks, cut anywhere
+        try:
+            names, flat, off = read_fasta_native(pth, pinned=False)
+        finally:
+            for k in env:
+                os.environ.pop(k)
         flat = flat.numpy()
-        assert names == want_names, data
-        assert [flat[off[i]:off[i + 1]].tobytes() for i in range(len(names))] == want_seqs, data
+        assert names == want_names, (data, env)
+        assert [flat[off[i]:off[i + 1]].tobytes() for i in range(len(names))] == want_seqs, (data, env)
