@@ -11,10 +11,13 @@
 //                  iteration earlier (lengths / offsets two iterations earlier: no global-memory
 //                  latency on the critical path); predicated shared atomics into histogram (j+3)&3;
 //                  the words are also staged in shared memory for S1/S2
-//   S1 (item j+2)  Bernoulli edits: thread <-> 64-base block, register-only generator (fast_block),
-//                  written position-sorted into the block's 12-entry slot (no CTA-wide scan)
-//   S2 (item j+1)  thread <-> block: +-1 histogram deltas of the block's edits (apply_entry on a view
-//                  that stitches the previous block's slot, this slot and the next block's first entry)
+//   S1 (items j+2 .. j+7, every 6th iteration)  Bernoulli edits of SIX sequences at once: thread <-> 64-base
+//                  block, register-only generator (fast_block), written position-sorted into the block's
+//                  12-entry slot of an 8-item ring (no CTA-wide scan).  One sequence at a time this stage is
+//                  5 busy warps and pure latency; six together fill the SM
+//   S2 (item j+1)  thread <-> EDIT: warps 16..31 each list the edits of their 16 blocks (warp scan of the
+//                  per-block counts) and apply them as +-1 shared atomics (apply_entry on a view that stitches
+//                  the previous block's slot, this slot and the next block's first entry)
 //   S3 (item j)    fold: 4 bins per thread -> float32 frequency -> float64 sums; bins zeroed
 //
 // so the LSU/atomic work, the integer RNG work and the FP32/FP64 work of different sequences overlap.
