@@ -314,3 +314,34 @@ def test_live_cgr_and_reduce(fasta_files):
     n1, x1 = ru.kmersFasta(fasta_files["Influenza-A"], k=4, reduce=True)
     n2, x2 = orc.kmersFasta(fasta_files["Influenza-A"], k=4, reduce=True)
     assert n1 == n2 and x1.shape == (949, 136) and np.array_equal(x1, x2)
+
+
+@needs_ref
+def test_live_fasta_record_loop_vs_native_scanner(tmp_path):
+    """the live reference's kmersFasta (idelucs/utils.py:224-277) on files that exercise its record loop — comments,
+    blank and blank-padded lines, CRLF, an empty first id (its lines run into the next record), no trailing newline —
+    against the native scanner (idl_fasta_scan / idl_fasta_extract) followed by the oracle's check_sequence + counting:
+    same names, same float64 profiles"""
+    ref = ref_live.load()
+    from idelucs_b200.seqset import read_fasta_native
+    cases = [
+        b">a\nACGTTGCA\nACGGT\n>b\nGGCATTA\n",
+        b">a\nACGTTGCA\nACGGT\n>b\nGGCATTA",
+        b"# c\n>a desc\n  ACGTAC \t\n#mid\nTTGACA\n\n>b\n\n>c\nACGTNNACGT\n",
+        b">\nACGTAC\n>x\nGTACGT\n>y\nTTTTAC\n",
+        b">a\r\nACGTAC\r\nTTGGCC\r\n>b\r\nGGGGCCAT\r\n",
+        b">a\nacgtacgtRYKM\n>b\nAC-GTACGT\n",
+    ]
+    for i, content in enumerate(cases):
+        pth = os.path.join(str(tmp_path), "live%d.fa" % i)
+        with open(pth, "wb") as fh:
+            fh.write(content)
+        want_names, want = ref.utils.kmersFasta(pth, k=3)
+        names, flat, off = read_fasta_native(pth, pinned=False)
+        flat = flat.numpy()
+        assert names == list(want_names), (i, names, want_names)
+        for r, name in enumerate(names):
+            seq = orc.check_sequence(name, bytearray(flat[off[r]:off[r + 1]].tobytes()))
+            c = np.ones(64, np.int32)
+            orc.kmer_counts(seq, 3, c)
+            assert np.array_equal(c / c.sum(), want[r]), (i, r)
