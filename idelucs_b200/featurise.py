@@ -303,6 +303,8 @@ def _merge_local(parts, part_n):
     if parts.is_cuda:
         s = Scaler.from_partials(parts, part_n)
         n = part_n.sum()
+        # M2 = var * rows: one float64 rounding away from the merge's own M2 (far below the 1e-9 the scale is compared
+        # at); a constant column keeps its exact 0
         return s.mean64, s.var64 * n, n
     F = parts.shape[2]
     na, ma, M2 = 0.0, torch.zeros(F, dtype=torch.float64), torch.zeros(F, dtype=torch.float64)
