@@ -26,6 +26,7 @@ class Variant(ctypes.Structure):
 PROTOTYPES = {
     "idl_abi_version": (c_int, []),
     "idl_last_error": (ctypes.c_char_p, []),
+    "idl_launch_count": (ctypes.c_longlong, []),
     "idl_geometric_table": (c_int, [c_double, c_void_p]),
     "idl_pack": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "idl_profiles_workspace_bytes": (c_size_t, []),
@@ -36,6 +37,13 @@ PROTOTYPES = {
     "idl_profile_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, ctypes.POINTER(Variant),
                                   c_u64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, ctypes.POINTER(c_int), c_void_p, c_void_p,
                                   c_size_t, c_void_p]),
+    "idl_prepare_bytes": (c_size_t, [c_i64]),
+    "idl_profiles_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, ctypes.POINTER(Variant),
+                                     c_int, c_u64, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_int, ctypes.POINTER(c_int), c_void_p,
+                                     c_void_p, c_size_t, c_void_p]),
+    "idl_profiles_prepared": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, ctypes.POINTER(Variant),
+                                      c_int, c_u64, c_int, c_void_p, ctypes.POINTER(c_i64), c_i64, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "idl_cgr_map": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p]),
     "idl_revcomp_canonical": (c_int, [c_int, c_void_p]),
     "idl_revcomp_fold": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
@@ -76,7 +84,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.idl_abi_version() != 1:
+    if lib.idl_abi_version() != 2:
         raise IdelucsB200Error("ABI version mismatch")
     _lib = lib
     return lib

@@ -7,6 +7,8 @@
 namespace idl {
 // records the thread-local error text returned by idl_last_error(); returns `code`
 int set_error(int code, const char* fmt, const char* a = "", long long b = 0);
+// counts the kernels this library has launched (idl_launch_count)
+void note_launch();
 }  // namespace idl
 
 #define IDL_CUDA_CHECK(expr)                                                                             \

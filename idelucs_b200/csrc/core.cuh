@@ -389,120 +389,98 @@ IDL_HD int block_edits(int kind, uint64_t seed, uint32_t seq_id, uint32_t varian
 }
 
 // ---------------------------------------------------------------------------------------
-// FAST block generator: the same edits as block_edits(), produced without data-dependent
-// loops or a second RNG pass, for blocks with at most FAST_CAP hits per stream (the rule
-// at the reference's rates; otherwise the caller falls back to block_edits()).  All arrays
-// are statically indexed so they live in registers.
+// MASK block generator: the same edits as block_edits(), with the hits of each stream kept as a 64-bit
+// mask (bit i = block-relative position i).  Merging the two streams, dropping hits on N and ordering
+// the edits by position are then a handful of logic instructions instead of list merges, and a block
+// may hold any number of hits (the gap loop is data dependent; at the reference's rates a warp leaves
+// it after one Philox call per stream).  Everything stays in registers.
 // ---------------------------------------------------------------------------------------
-constexpr int FAST_CAP = 6;
-
 IDL_HD uint32_t u4_sel(const U4& r, int i) { return i == 0 ? r.x : i == 1 ? r.y : i == 2 ? r.z : r.w; }
 
-// hits of one stream in one block: block-relative positions, ascending, 8 bits each in
-// `pos8` (hit i at bits [8i, 8i+8); 0xFF = no hit), choice bit i in chbits.
-// Returns false when the block has more than FAST_CAP hits (overflow).
+IDL_HD uint32_t brev32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    return (x >> 16) | (x << 16);
+#endif
+}
+IDL_HD int ffs64(uint64_t x) {   // index of the lowest set bit (x != 0)
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+
+// hits of one stream in one block (same word consumption as BernGen: one word per step, or gap + choice)
 template <bool CHOICE>
-IDL_HD bool fast_stream(uint64_t seed, uint32_t seq_id, uint32_t variant, uint32_t stream, int block, int L,
-                        const uint32_t* T, float slope, uint64_t& pos8, uint32_t& chbits) {
-    constexpr int WPS = CHOICE ? 2 : 1;  // words per step
-    int cur = -1;                        // block-relative
+IDL_HD uint64_t stream_mask(uint64_t seed, uint32_t seq_id, uint32_t variant, uint32_t stream, int block, int L,
+                            const uint32_t* T, float slope, uint64_t& choice) {
     int end = L - block * RNG_BLOCK;
     if (end > RNG_BLOCK) end = RNG_BLOCK;
-    bool done = end <= 0;
-    bool overflow = false;
-    pos8 = 0xFFFFFFFFFFFFFFFFull;
-    chbits = 0u;
-    U4 r;
-    r.x = r.y = r.z = r.w = 0u;
+    uint64_t m = 0;
+    choice = 0;
+    if (end <= 0) return 0;
+    int cur = -1;
+    for (uint32_t j = 0;; ++j) {
+        const U4 r = philox4x32_10(j, (uint32_t)block, seq_id, (variant << 2) | stream, (uint32_t)seed, (uint32_t)(seed >> 32));
 #pragma unroll
-    for (int it = 0; it <= FAST_CAP; ++it) {
-        const int wi = it * WPS;
-        if ((wi & 3) == 0 && !done)
-            r = philox4x32_10((uint32_t)(wi >> 2), (uint32_t)block, seq_id, (variant << 2) | stream, (uint32_t)seed, (uint32_t)(seed >> 32));
-        if (!done) {
-            const int g = gap_of(u4_sel(r, wi & 3), T, slope);
-            const uint32_t ch = CHOICE ? (u4_sel(r, (wi & 3) + 1) >> 31) : 0u;
-            if (g == 0 || cur + g >= end) done = true;
-            else {
-                cur += g;
-                if (it < FAST_CAP) {
-                    pos8 = (pos8 & ~(0xFFull << (8 * it))) | ((uint64_t)cur << (8 * it));
-                    chbits |= ch << it;
-                } else overflow = true;
-            }
+        for (int s = 0; s < (CHOICE ? 2 : 4); ++s) {
+            const int g = gap_of(CHOICE ? (s == 0 ? r.x : r.z) : u4_sel(r, s), T, slope);
+            if (g == 0 || cur + g >= end) return m;
+            cur += g;
+            m |= 1ull << cur;
+            if (CHOICE) choice |= (uint64_t)((s == 0 ? r.y : r.w) >> 31) << cur;
         }
     }
-    return !overflow;
 }
 
-struct FastBlock {
-    uint64_t a8, b8;   // transition / transversion hits (block-relative, 8 bits each, 0xFF = none)
-    uint32_t chb;      // transversion choice bits
-    uint32_t keep;     // bit i: transition hit i is emitted; bit FAST_CAP+j: transversion hit j
-    int cnt;           // number of emitted edits
-    bool ok;           // false: overflow, use block_edits()
+struct BlockMasks {
+    uint64_t a;    // bases that take a transition (A<->G, C<->T)
+    uint64_t b;    // bases that take a transversion ...
+    uint64_t ch;   // ... and its choice bit
 };
+IDL_HD int block_masks_count(const BlockMasks& m) { return popc64(m.a | m.b); }
 
-IDL_HD int fast_pos(uint64_t p8, int i) { return (int)((p8 >> (8 * i)) & 0xFFull); }
-
-IDL_HD FastBlock fast_block(int kind, uint64_t seed, uint32_t seq_id, uint32_t variant, int block, int L, const uint32_t* nmask,
-                            const uint32_t* T1, float slope1, const uint32_t* T2, float slope2) {
-    FastBlock f;
-    f.a8 = f.b8 = 0xFFFFFFFFFFFFFFFFull; f.chb = 0u; f.keep = 0u; f.cnt = 0; f.ok = true;
-    uint32_t dummy;
-    if (kind == KIND_TRANSITION || kind == KIND_BOTH)
-        f.ok = fast_stream<false>(seed, seq_id, variant, STREAM_TRANSITION, block, L, T1, slope1, f.a8, dummy);
-    if (kind == KIND_TRANSVERSION || kind == KIND_BOTH)
-        f.ok = fast_stream<true>(seed, seq_id, variant, STREAM_TRANSVERSION, block, L, T2, slope2, f.b8, f.chb) && f.ok;
-    // a transition hit is dropped where a transversion hits the same base; hits on N are dropped
-    const int base = block * RNG_BLOCK;
-#pragma unroll
-    for (int i = 0; i < FAST_CAP; ++i) {
-        const int ai = fast_pos(f.a8, i), bi = fast_pos(f.b8, i);
-        bool ka = ai != 0xFF;
-#pragma unroll
-        for (int j = 0; j < FAST_CAP; ++j) ka = ka && (fast_pos(f.b8, j) != ai);
-        if (ka) ka = !nflag_at(nmask, base + ai);
-        bool kb = bi != 0xFF;
-        if (kb) kb = !nflag_at(nmask, base + bi);
-        f.keep |= (ka ? 1u : 0u) << i;
-        f.keep |= (kb ? 1u : 0u) << (FAST_CAP + i);
-    }
-#if defined(__CUDA_ARCH__)
-    f.cnt = __popc(f.keep);
-#else
-    f.cnt = __builtin_popcount(f.keep);
-#endif
-    return f;
+IDL_HD BlockMasks block_masks(int kind, uint64_t seed, uint32_t seq_id, uint32_t variant, int block, int L, const uint32_t* nmask,
+                              const uint32_t* T1, float slope1, const uint32_t* T2, float slope2) {
+    BlockMasks m;
+    m.a = m.b = m.ch = 0;
+    uint64_t dummy;
+    if (kind == KIND_TRANSITION || kind == KIND_BOTH) m.a = stream_mask<false>(seed, seq_id, variant, STREAM_TRANSITION, block, L, T1, slope1, dummy);
+    if (kind == KIND_TRANSVERSION || kind == KIND_BOTH) m.b = stream_mask<true>(seed, seq_id, variant, STREAM_TRANSVERSION, block, L, T2, slope2, m.ch);
+    // reset flags of the block: nmask bit 31-j of word w = base 32w + j
+    const uint64_t nm = ((uint64_t)brev32(nmask[2 * block + 1]) << 32) | (uint64_t)brev32(nmask[2 * block]);
+    m.b &= ~nm;             // N stays N
+    m.a &= ~(nm | m.b);     // where both streams hit, the transversion decides (it only depends on the purine / pyrimidine class)
+    return m;
 }
 
-// write the block's edits, position-sorted, to dst[0..cnt)
-IDL_HD void fast_block_write(const FastBlock& f, int block, const uint32_t* codes, uint32_t* dst) {
-    const int base = block * RNG_BLOCK;
-#pragma unroll
-    for (int i = 0; i < FAST_CAP; ++i) {
-        if ((f.keep >> i) & 1u) {  // transition hit i: rank = kept transitions before + kept transversions below
-            const int ai = fast_pos(f.a8, i);
-            int rank = 0;
-#pragma unroll
-            for (int t = 0; t < FAST_CAP; ++t) {
-                rank += (t < i && ((f.keep >> t) & 1u)) ? 1 : 0;
-                rank += (((f.keep >> (FAST_CAP + t)) & 1u) && fast_pos(f.b8, t) < ai) ? 1 : 0;
-            }
-            dst[rank] = ((uint32_t)(base + ai) << 3) | (code_at(codes, base + ai) ^ 2u);
-        }
-        if ((f.keep >> (FAST_CAP + i)) & 1u) {
-            const int bi = fast_pos(f.b8, i);
-            int rank = 0;
-#pragma unroll
-            for (int t = 0; t < FAST_CAP; ++t) {
-                rank += (t < i && ((f.keep >> (FAST_CAP + t)) & 1u)) ? 1 : 0;
-                rank += (((f.keep >> t) & 1u) && fast_pos(f.a8, t) < bi) ? 1 : 0;
-            }
-            const uint32_t c = code_at(codes, base + bi);
-            const uint32_t cb = (f.chb >> i) & 1u;
-            dst[rank] = ((uint32_t)(base + bi) << 3) | ((c & 1u) ? (cb << 1) : (1u | ((1u - cb) << 1)));
-        }
+// the edit at block-relative position i (a set bit of m.a | m.b)
+IDL_HD uint32_t block_masks_entry(const BlockMasks& m, int block, const uint32_t* codes, int i) {
+    const int pos = block * RNG_BLOCK + i;
+    const uint32_t c = code_at(codes, pos);
+    uint32_t val;
+    if ((m.b >> i) & 1ull) {
+        const uint32_t cb = (uint32_t)((m.ch >> i) & 1ull);
+        val = (c & 1u) ? (cb << 1) : (1u | ((1u - cb) << 1));
+    } else {
+        val = c ^ 2u;
+    }
+    return ((uint32_t)pos << 3) | val;
+}
+
+// write the block's edits, position-sorted, to dst[0 .. block_masks_count(m))
+IDL_HD void block_masks_write(const BlockMasks& m, int block, const uint32_t* codes, uint32_t* dst) {
+    uint64_t u = m.a | m.b;
+    while (u) {
+        const int i = ffs64(u);
+        u &= u - 1;
+        *dst++ = block_masks_entry(m, block, codes, i);
     }
 }
 

@@ -264,6 +264,7 @@ int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb,
     p.dS = w;
     void* args[] = {(void*)&p};
     IDL_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)iid_loss_kernel, dim3(p.npairs), dim3(LNT), args, 0, (cudaStream_t)stream));
+    note_launch();
     return IDL_OK;
 }
 

@@ -14,6 +14,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <utility>
+#include <vector>
+
 #include "../../include/idelucs_b200.h"
 #include "core.cuh"
 #include "common.h"
@@ -30,6 +35,9 @@ int set_error(int code, const char* fmt, const char* a, long long b) {
     return code;
 }
 
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 constexpr int LIST_CAP = 2048;   // on-chip edit list entries per CTA
 constexpr int SG = 32;           // variant slots per supergroup (Random_N removals precomputed together)
 constexpr int REM_CAP = 3840;    // removed k-mers buffered per supergroup (32 slots x 20 draws x k=6)
@@ -42,6 +50,15 @@ constexpr int STABS = 4;         // gap tables cached in shared memory
 struct VarDesc {
     int32_t kind, rng_id, n_bp, explicit_idx, tab1, tab2;
     float slope1, slope2;
+};
+
+// launch plan passed BY VALUE as a kernel parameter (no host->device copy, nothing cached between calls, CUDA-graph
+// capture records it with the launch): the variant descriptors, output offsets and gap tables of calls with at most SVARS
+// variants / slots and STABS distinct mutation rates.  Bigger plans are uploaded into the workspace instead.
+struct Plan {
+    VarDesc vars[SVARS];
+    long long out_off[SVARS];
+    uint32_t gtab[STABS][RNG_BLOCK];
 };
 
 struct ProfParams {
@@ -71,8 +88,21 @@ struct ProfParams {
     int only_deferred;                // generic kernel: redo only the items the producer/consumer kernel flagged (status bit 1)
     double* stats_partials;           // OUT_STATS: per-CTA (mean, M2) [gridDim][2][4^k]
     double* stats_n;                  // OUT_STATS: per-CTA row count [gridDim]
-    int dbg;                          // development switches of the producer/consumer kernel (IDL_PC_DBG)
+    int dbg;                          // development switches of the producer/consumer kernel (IDL_PC_DBG; builds with -DIDL_DEVTOOLS only)
+    int inline_plan;                  // descriptors / offsets / tables come from the Plan kernel parameter (else from vars / out_off / gtab)
+    void* prep;                       // prepared buffer (prep.cuh): written by prep_kernel, read by colstats16 / the producer/consumer kernel
+    unsigned long long prep_stamp;    // what the prepared buffer must have been prepared for
 };
+static_assert(sizeof(ProfParams) + sizeof(Plan) <= 4000, "kernel parameters must stay below the 4 KB limit");
+
+// development aids are compiled out of release builds
+#ifdef IDL_DEVTOOLS
+#define IDL_DBG(p) ((p).dbg)
+#define IDL_PROF(p) ((p).phase_prof)
+#else
+#define IDL_DBG(p) 0
+#define IDL_PROF(p) (static_cast<unsigned long long*>(nullptr))
+#endif
 
 constexpr int OUT_STATS = 4;          // internal out kind: column statistics of slot 0's float32 frequencies, nothing is written per row
 
@@ -294,8 +324,6 @@ __device__ __forceinline__ void emit_granule_u16x2(void* out_row, int vec, uint2
 
 // ---- register-hungry, rarely executed pieces are kept out of line so that the streaming
 // ---- loop keeps its scaler statistics in registers (64-register budget at 2 CTAs/SM) ----
-struct BlockGen { int cnt; uint32_t e0, e1, e2, e3; };
-
 struct ItemCtx {
     const uint32_t* codes;
     const uint32_t* nmask;
@@ -304,34 +332,6 @@ struct ItemCtx {
     unsigned long long seed;
 };
 
-// edits of one 64-base block of a Bernoulli slot: count + the first four entries
-__device__ __noinline__ BlockGen bern_block(const ItemCtx& cx, int kind, uint32_t rng_id, int b, const uint32_t* T1, float s1,
-                                            const uint32_t* T2, float s2) {
-    BlockGen g;
-    g.e0 = g.e1 = g.e2 = g.e3 = 0u;
-    int k4 = 0;
-    g.cnt = block_edits(kind, cx.seed, cx.seq_id, rng_id, b, cx.L, cx.codes, cx.nmask, T1, s1, T2, s2, [&](uint32_t e) {
-        if (k4 == 0) g.e0 = e; else if (k4 == 1) g.e1 = e; else if (k4 == 2) g.e2 = e; else if (k4 == 3) g.e3 = e;
-        ++k4;
-    });
-    return g;
-}
-// rare (> 4 edits in a block): regenerate straight into the list
-__device__ __noinline__ void bern_block_write(const ItemCtx& cx, int kind, uint32_t rng_id, int b, const uint32_t* T1, float s1,
-                                              const uint32_t* T2, float s2, uint32_t* dst) {
-    block_edits(kind, cx.seed, cx.seq_id, rng_id, b, cx.L, cx.codes, cx.nmask, T1, s1, T2, s2, [&](uint32_t e) { *dst++ = e; });
-}
-__device__ __forceinline__ void put_block(const ItemCtx& cx, const VarDesc& vd, int b, const BlockGen& g, uint32_t* dst,
-                                          const uint32_t* T1, const uint32_t* T2) {
-    if (g.cnt <= 4) {
-        if (g.cnt > 0) dst[0] = g.e0;
-        if (g.cnt > 1) dst[1] = g.e1;
-        if (g.cnt > 2) dst[2] = g.e2;
-        if (g.cnt > 3) dst[3] = g.e3;
-    } else {
-        bern_block_write(cx, vd.kind, (uint32_t)vd.rng_id, b, T1, vd.slope1, T2, vd.slope2, dst);
-    }
-}
 // patch a private uint16 copy (two counts per word) with the deltas of list entry i
 __device__ __forceinline__ void upd16(uint32_t* privc, uint32_t kmer, int d) {
     uint32_t* w = privc + (kmer >> 1);
@@ -352,25 +352,40 @@ __device__ __forceinline__ const uint32_t* gap_table(const ProfSmem<K, NT>& sm, 
     return t < STABS ? sm.gtabs[t] : p.gtab + t * RNG_BLOCK;
 }
 
-// CTA-wide generation of the Bernoulli edit list of one tile (NT-2 blocks + one context block
-// on each side) into sm.list; returns the number of entries (-1 on overflow).  Contains
-// barriers; every thread of the CTA must call it.
+// CTA-wide generation of the Bernoulli edit list of the blocks [b_lo, b_hi) (at most NT of them: thread <-> block, mask
+// generator) into sm.list, position-sorted; returns the number of entries, or -1 when they do not fit LIST_CAP (nothing
+// is written then: the caller retries with fewer blocks — three blocks always fit).  Contains barriers; every thread of
+// the CTA must call it.
 template <int K, int NT>
-__device__ __noinline__ int bernoulli_tile(ProfSmem<K, NT>& sm, const ProfParams& p, const ItemCtx& cx, const VarDesc& vd, int tb0,
-                                           int nblocks) {
-    const int b = tb0 - 1 + (int)threadIdx.x;
-    const bool active = b >= 0 && b < nblocks;
-    const uint32_t* T1 = gap_table(sm, p, vd.tab1);
-    const uint32_t* T2 = gap_table(sm, p, vd.tab2);
-    BlockGen g;
-    g.cnt = 0;
-    if (active) g = bern_block(cx, vd.kind, (uint32_t)vd.rng_id, b, T1, vd.slope1, T2, vd.slope2);
+__device__ __noinline__ int bern_span(ProfSmem<K, NT>& sm, const ProfParams& p, const ItemCtx& cx, const VarDesc& vd, int b_lo, int b_hi) {
+    const int b = b_lo + (int)threadIdx.x;
+    BlockMasks m;
+    m.a = m.b = m.ch = 0;
+    if (b < b_hi)
+        m = block_masks(vd.kind, cx.seed, cx.seq_id, (uint32_t)vd.rng_id, b, cx.L, cx.nmask, gap_table(sm, p, vd.tab1), vd.slope1,
+                        gap_table(sm, p, vd.tab2), vd.slope2);
     int total;
-    const int off = block_exscan<NT>(g.cnt, sm.scan, &total);
-    if (total > LIST_CAP) return -1;
-    if (active) put_block(cx, vd, b, g, sm.list + off, T1, T2);
+    const int off = block_exscan<NT>(block_masks_count(m), sm.scan, &total);
+    if (total > LIST_CAP) return -1;   // uniform
+    block_masks_write(m, b, cx.codes, sm.list + off);
     __syncthreads();
     return total;
+}
+
+// Bernoulli slot, any length: tiles of `span` owned blocks plus one context block on each side (an edit's windows only
+// involve edits within K-1 positions); fn(total, lo, hi) is called CTA-wide per tile and applies the entries of sm.list whose
+// position lies in [lo, hi).  The span halves whenever a tile's edits overflow the on-chip list, so no rate can drop edits.
+template <int K, int NT, class Fn>
+__device__ __forceinline__ void bern_tiles(ProfSmem<K, NT>& sm, const ProfParams& p, const ItemCtx& cx, const VarDesc& vd, int nblocks, Fn fn) {
+    int span = NT - 2;
+    for (int tb0 = 0; tb0 < nblocks;) {
+        const int t1 = tb0 + span < nblocks ? tb0 + span : nblocks;
+        const int total = bern_span<K, NT>(sm, p, cx, vd, tb0 > 0 ? tb0 - 1 : 0, t1 + 1 < nblocks ? t1 + 1 : nblocks);
+        if (total < 0) { span = span > 1 ? span >> 1 : 1; continue; }   // (bern_span ends with the barrier that lets the list be rewritten)
+        fn(total, tb0 * RNG_BLOCK, (long long)t1 * RNG_BLOCK);
+        __syncthreads();   // the list is rewritten by the next tile / slot
+        tb0 = t1;
+    }
 }
 
 // CTA-wide Random_N with many draws: draw -> rank sort into sm.list.  Contains barriers.
@@ -400,7 +415,6 @@ __device__ __noinline__ void long_path(ProfSmem<K, NT>& sm, const ProfParams& p,
     using C = ProfCfg<K, NT>;
     constexpr int VEC = C::VEC, VPT = C::VPT;
     constexpr int ESZ = OUT == IDL_OUT_FREQ_F64 ? 8 : 4;
-    constexpr int TB = NT - 2;
     const int tid = threadIdx.x, lane = tid & 31;
     const int L = cx.L;
     const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
@@ -427,19 +441,14 @@ __device__ __noinline__ void long_path(ProfSmem<K, NT>& sm, const ProfParams& p,
                 if (sgn > 0) { d = warp_sum(d); if (lane == 0 && d) atomicAdd(&sm.dtot[0], d); }
                 __syncthreads();
             } else {
-                for (int tb0 = 0; tb0 < nblocks; tb0 += TB) {
-                    const int total = bernoulli_tile<K, NT>(sm, p, cx, vd, tb0, nblocks);
-                    if (total < 0) { if (tid == 0 && p.status) atomicOr(p.status + item, 1); continue; }
-                    const int lo = tb0 * RNG_BLOCK;
-                    const long long hi = (long long)(tb0 + TB) * RNG_BLOCK;
+                bern_tiles<K, NT>(sm, p, cx, vd, nblocks, [&](int total, int lo, long long hi) {
                     int d = 0;
                     for (int i = tid; i < total; i += NT) {
                         const int pos = (int)(sm.list[i] >> 3);
                         if (pos >= lo && pos < hi) d += apply_hist<K>(cx, sm.list, total, i, sm.hist, sgn);
                     }
                     if (sgn > 0) { d = warp_sum(d); if (lane == 0 && d) atomicAdd(&sm.dtot[0], d); }
-                    __syncthreads();
-                }
+                });
             }
             if (sgn > 0) {
                 const int total = base_total + sm.dtot[0];
@@ -492,70 +501,35 @@ __device__ __noinline__ void prep_cta_slots(ProfSmem<K, NT>& sm, const ProfParam
                                             int copy0, PhaseClock& pc) {
     using C = ProfCfg<K, NT>;
     constexpr int PRIVW = C::PRIVW;
-    constexpr int TB = NT - 2;
     const int tid = threadIdx.x, lane = tid & 31;
     const int L = cx.L;
     const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
     uint32_t* priv = sm.privtmp + copy0 * PRIVW;
     auto slot_var = [&](int slot) -> int { return p.sel ? p.sel[item * p.S + slot] : slot; };
-    // ---- Bernoulli slots jointly: thread <-> (slot, 64-base block) ----
+    // ---- Bernoulli slots jointly: thread <-> (slot, 64-base block), mask generator ----
     const int nb = __popc(bern_mask);
     bool bern_done = nb == 0;
     if (nb > 0 && nb * nblocks <= NT) {
-        // fast path: register-only generator (<= FAST_CAP hits per stream and block)
         const int j = tid / nblocks, b = tid - j * nblocks;
         const bool active = tid < nb * nblocks;
         const int c = active ? (int)__fns(bern_mask, 0, j + 1) : 0;
         const VarDesc vd = vars[slot_var(s0 + c)];
-        FastBlock f;
-        f.cnt = 0; f.ok = true;
+        BlockMasks m;
+        m.a = m.b = m.ch = 0;
         if (active)
-            f = fast_block(vd.kind, cx.seed, cx.seq_id, (uint32_t)vd.rng_id, b, L, cx.nmask, gap_table(sm, p, vd.tab1), vd.slope1,
-                           gap_table(sm, p, vd.tab2), vd.slope2);
+            m = block_masks(vd.kind, cx.seed, cx.seq_id, (uint32_t)vd.rng_id, b, L, cx.nmask, gap_table(sm, p, vd.tab1), vd.slope1,
+                            gap_table(sm, p, vd.tab2), vd.slope2);
         pc.tick(7);
-        if (!__syncthreads_or(active && !f.ok)) {
-            int total;
-            const int off = block_exscan<NT>(f.cnt, sm.scan, &total);
-            pc.tick(8);
-            if (total <= LIST_CAP) {  // uniform
-                bern_done = true;
-                if (active && b == 0) sm.seg_off[j] = off;
-                if (tid == 0) sm.seg_off[nb] = total;
-                if (active && f.cnt) fast_block_write(f, b, cx.codes, sm.list + off);
-                __syncthreads();
-                pc.tick(9);
-                for (int i = tid; i < total; i += NT) {
-                    int jj = 0;
-                    while (i >= sm.seg_off[jj + 1]) ++jj;
-                    const int cc = (int)__fns(bern_mask, 0, jj + 1);
-                    const int so = sm.seg_off[jj];
-                    const int d = apply_priv<K>(cx, sm.list + so, sm.seg_off[jj + 1] - so, i - so, priv + cc * PRIVW);
-                    if (d) atomicAdd(&dtot[cc], d);
-                }
-                pc.tick(10);
-                __syncthreads();
-                pc.tick(11);
-            }
-        }
-    }
-    if (!bern_done && nb > 0 && nb * nblocks <= NT) {  // generic generator (any number of hits per block)
-        const int j = tid / nblocks, b = tid - j * nblocks;
-        const bool active = tid < nb * nblocks;
-        const int c = active ? (int)__fns(bern_mask, 0, j + 1) : 0;
-        const VarDesc vd = vars[slot_var(s0 + c)];
-        const uint32_t* T1 = gap_table(sm, p, vd.tab1);
-        const uint32_t* T2 = gap_table(sm, p, vd.tab2);
-        BlockGen g;
-        g.cnt = 0;
-        if (active) g = bern_block(cx, vd.kind, (uint32_t)vd.rng_id, b, T1, vd.slope1, T2, vd.slope2);
         int total;
-        const int off = block_exscan<NT>(g.cnt, sm.scan, &total);
+        const int off = block_exscan<NT>(block_masks_count(m), sm.scan, &total);
+        pc.tick(8);
         if (total <= LIST_CAP) {  // uniform
             bern_done = true;
             if (active && b == 0) sm.seg_off[j] = off;
             if (tid == 0) sm.seg_off[nb] = total;
-            if (active) put_block(cx, vd, b, g, sm.list + off, T1, T2);
+            block_masks_write(m, b, cx.codes, sm.list + off);
             __syncthreads();
+            pc.tick(9);
             for (int i = tid; i < total; i += NT) {
                 int jj = 0;
                 while (i >= sm.seg_off[jj + 1]) ++jj;
@@ -564,7 +538,9 @@ __device__ __noinline__ void prep_cta_slots(ProfSmem<K, NT>& sm, const ProfParam
                 const int d = apply_priv<K>(cx, sm.list + so, sm.seg_off[jj + 1] - so, i - so, priv + cc * PRIVW);
                 if (d) atomicAdd(&dtot[cc], d);
             }
+            pc.tick(10);
             __syncthreads();
+            pc.tick(11);
         }
     }
     // ---- remaining CTA-wide slots, one after the other ----
@@ -584,17 +560,12 @@ __device__ __noinline__ void prep_cta_slots(ProfSmem<K, NT>& sm, const ProfParam
             random_n_list<K, NT>(sm, cx, vd, sm.list + LIST_CAP / 2);
             for (int i = tid; i < vd.n_bp; i += NT) d += apply_priv<K>(cx, sm.list, vd.n_bp, i, privc);
         } else {
-            for (int tb0 = 0; tb0 < nblocks; tb0 += TB) {
-                const int total = bernoulli_tile<K, NT>(sm, p, cx, vd, tb0, nblocks);
-                if (total < 0) { if (tid == 0 && p.status) atomicOr(p.status + item, 1); continue; }
-                const int lo = tb0 * RNG_BLOCK;
-                const long long hi = (long long)(tb0 + TB) * RNG_BLOCK;
+            bern_tiles<K, NT>(sm, p, cx, vd, nblocks, [&](int total, int lo, long long hi) {
                 for (int i = tid; i < total; i += NT) {
                     const int pos = (int)(sm.list[i] >> 3);
                     if (pos >= lo && pos < hi) d += apply_priv<K>(cx, sm.list, total, i, privc);
                 }
-                __syncthreads();  // list is rewritten by the next tile / slot
-            }
+            });
         }
         d = warp_sum(d);
         if (lane == 0 && d) atomicAdd(&dtot[c], d);
@@ -603,7 +574,7 @@ __device__ __noinline__ void prep_cta_slots(ProfSmem<K, NT>& sm, const ProfParam
 }
 
 template <int K, int NT, int OUT>
-__global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_kernel(const ProfParams p) {
+__global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_kernel(const ProfParams p, const __grid_constant__ Plan plan) {
     using C = ProfCfg<K, NT>;
     constexpr int F = C::F, VEC = C::VEC, VPT = C::VPT, G = C::G, PRIVW = C::PRIVW;
     constexpr int ESZ = OUT == IDL_OUT_FREQ_F64 ? 8 : 4;
@@ -617,19 +588,19 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
     }
 
     const float magic = 8388608.0f - (float)p.pseudocount;
-    const bool cached = p.n_vars <= SVARS && p.S <= SVARS;
+    const bool cached = p.inline_plan != 0;
     if (cached) {
-        for (int i = tid; i < p.n_vars; i += NT) sm.svars[i] = p.vars[i];
-        for (int i = tid; i < p.S; i += NT) sm.sout_off[i] = p.out_off[i];
+        for (int i = tid; i < p.n_vars; i += NT) sm.svars[i] = plan.vars[i];
+        for (int i = tid; i < p.S; i += NT) sm.sout_off[i] = plan.out_off[i];
     }
     for (int i = tid; i < STABS * RNG_BLOCK; i += NT)
-        (&sm.gtabs[0][0])[i] = i < p.n_tabs * RNG_BLOCK ? p.gtab[i] : 0u;
+        (&sm.gtabs[0][0])[i] = i < p.n_tabs * RNG_BLOCK ? (cached ? (&plan.gtab[0][0])[i] : p.gtab[i]) : 0u;
     const VarDesc* __restrict__ vars = cached ? sm.svars : p.vars;
     const long long* __restrict__ out_offs = cached ? sm.sout_off : reinterpret_cast<const long long*>(p.out_off);
 
     PhaseClock pclk;
-    pclk.base = p.phase_prof;
-    pclk.t_prev = p.phase_prof ? clock64() : 0;
+    pclk.base = IDL_PROF(p);
+    pclk.t_prev = IDL_PROF(p) ? clock64() : 0;
     auto phase = [&](int id) { pclk.tick(id); };
     // OUT_STATS: shifted-data column sums of this CTA's rows (shift = first row seen), float64
     double acc1[VPT][4], acc2[VPT][4];
@@ -736,44 +707,15 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
             const int nblk = (L + RNG_BLOCK - 1) / RNG_BLOCK;
             const bool bern = vd.kind == KIND_TRANSITION || vd.kind == KIND_TRANSVERSION || vd.kind == KIND_BOTH;
             if (bern && nblk > 0) {
-                bool done = false;
-                if (nblk <= NT) {   // fast generator, thread <-> 64-base block
-                    FastBlock f;
-                    f.cnt = 0; f.ok = true;
-                    if (tid < nblk)
-                        f = fast_block(vd.kind, cx.seed, cx.seq_id, (uint32_t)vd.rng_id, tid, L, cx.nmask, gap_table(sm, p, vd.tab1), vd.slope1,
-                                       gap_table(sm, p, vd.tab2), vd.slope2);
-                    if (!__syncthreads_or(tid < nblk && !f.ok)) {
-                        int total;
-                        const int off = block_exscan<NT>(f.cnt, sm.scan, &total);
-                        if (total <= LIST_CAP) {
-                            done = true;
-                            if (tid < nblk && f.cnt) fast_block_write(f, tid, cx.codes, sm.list + off);
-                            __syncthreads();
-                            int d = 0;
-                            for (int i = tid; i < total; i += NT) d += apply_hist<K>(cx, sm.list, total, i, sm.hist, 1);
-                            d = warp_sum(d);
-                            if (lane == 0 && d) atomicAdd(&sm.dtot[0], d);
-                        }
+                bern_tiles<K, NT>(sm, p, cx, vd, nblk, [&](int total, int lo, long long hi) {
+                    int d = 0;
+                    for (int i = tid; i < total; i += NT) {
+                        const int pos = (int)(sm.list[i] >> 3);
+                        if (pos >= lo && pos < hi) d += apply_hist<K>(cx, sm.list, total, i, sm.hist, 1);
                     }
-                }
-                if (!done) {        // generic generator, tile by tile
-                    constexpr int TBs = NT - 2;
-                    for (int tb0 = 0; tb0 < nblk; tb0 += TBs) {
-                        const int total = bernoulli_tile<K, NT>(sm, p, cx, vd, tb0, nblk);
-                        if (total < 0) { if (tid == 0 && p.status) atomicOr(p.status + item, 1); continue; }
-                        const int lo = tb0 * RNG_BLOCK;
-                        const long long hi = (long long)(tb0 + TBs) * RNG_BLOCK;
-                        int d = 0;
-                        for (int i = tid; i < total; i += NT) {
-                            const int pos = (int)(sm.list[i] >> 3);
-                            if (pos >= lo && pos < hi) d += apply_hist<K>(cx, sm.list, total, i, sm.hist, 1);
-                        }
-                        d = warp_sum(d);
-                        if (lane == 0 && d) atomicAdd(&sm.dtot[0], d);
-                        __syncthreads();
-                    }
-                }
+                    d = warp_sum(d);
+                    if (lane == 0 && d) atomicAdd(&sm.dtot[0], d);
+                });
             }
             if (vd.kind == KIND_EXPLICIT || (vd.kind == KIND_RANDOM_N && vd.n_bp > 0 && L > 0)) {
                 const uint32_t* lst = sm.list;
@@ -1058,7 +1000,7 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
 
 }  // namespace idl
 #include "profiles_pc.cuh"
-#include "stats_fast.cuh"
+#include "prep.cuh"
 namespace idl {
 
 // ---------------------------------------------------------------------------------------
@@ -1155,14 +1097,29 @@ __global__ void standardize_f64_kernel(const double* __restrict__ x, double* __r
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-static int g_sm_count = 0;
+// per-device facts: SM count, and which kernels already carry their dynamic shared-memory opt-in ON THAT DEVICE
+// (cudaFuncSetAttribute is per device; a process may drive several)
+static std::mutex g_dev_mu;
+static int g_sm_counts[64];
+static std::vector<std::pair<int, const void*>> g_smem_done;
+
 static int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_sm_count = 148;
-    }
-    return g_sm_count;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (g_sm_counts[dev] == 0 && cudaDeviceGetAttribute(&g_sm_counts[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_sm_counts[dev] = 148;
+    return g_sm_counts[dev];
+}
+static cudaError_t ensure_dyn_smem(const void* func, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    for (const auto& d : g_smem_done)
+        if (d.first == dev && d.second == func) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) g_smem_done.emplace_back(dev, func);
+    return e;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1229,7 +1186,8 @@ __global__ void rscale_kernel(const float* __restrict__ scale, float* __restrict
     if (i < F) rscale[i] = 1.0f / scale[i];  // IEEE division: the correctly rounded reciprocal div_rn needs
 }
 
-// workspace layout: [0,8) work counter | vars | out_off | gtab | rscale
+// workspace layout: [0,24) work counters | vars | out_off | gtab | rscale   (vars / out_off / gtab only for plans too big for the
+// Plan kernel parameter)
 constexpr size_t WS_VARS = 64;
 constexpr int MAX_VARIANTS = 4096;
 constexpr int MAX_TABS = 64;
@@ -1237,17 +1195,13 @@ constexpr size_t WS_OUTOFF = WS_VARS + sizeof(VarDesc) * MAX_VARIANTS;
 constexpr size_t WS_GTAB = WS_OUTOFF + sizeof(int64_t) * MAX_VARIANTS;
 constexpr size_t WS_RSCALE = WS_GTAB + sizeof(uint32_t) * RNG_BLOCK * MAX_TABS;
 constexpr size_t WS_PROF = WS_RSCALE + sizeof(float) * 4096;
-constexpr size_t WS_TOTAL = WS_PROF + 8 * 16;  // 16 phase counters
+constexpr size_t WS_TOTAL = WS_PROF + 8 * 16;  // 16 phase counters (development builds)
 
 template <int K, int NT, int OUT>
-static int launch_profiles(const ProfParams& p, cudaStream_t st, int* grid_out = nullptr) {
+static int launch_profiles(const ProfParams& p, const Plan& plan, cudaStream_t st, int* grid_out = nullptr) {
     const size_t smem = sizeof(ProfSmem<K, NT>);
     auto kern = profiles_kernel<K, NT, OUT>;
-    static bool configured = false;
-    if (!configured) {
-        IDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    IDL_CUDA_CHECK(ensure_dyn_smem((const void*)kern, smem));
     int per_sm = 0;
     IDL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
     if (per_sm < 1) return set_error(IDL_ECUDA, "profiles kernel does not fit on an SM%s", "");
@@ -1255,21 +1209,198 @@ static int launch_profiles(const ProfParams& p, cudaStream_t st, int* grid_out =
     if (grid > p.n_items) grid = p.n_items;
     if (grid < 1) grid = 1;
     if (grid_out) *grid_out = (int)grid;
-    kern<<<(unsigned)grid, NT, smem, st>>>(p);
+    kern<<<(unsigned)grid, NT, smem, st>>>(p, plan); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }
 
 template <int K, int NT>
-static int dispatch_out(const ProfParams& p, int out_kind, cudaStream_t st, int* grid_out = nullptr) {
+static int dispatch_out(const ProfParams& p, const Plan& plan, int out_kind, cudaStream_t st, int* grid_out = nullptr) {
     switch (out_kind) {
-        case OUT_STATS: return launch_profiles<K, NT, OUT_STATS>(p, st, grid_out);
-        case IDL_OUT_COUNTS_I32: return launch_profiles<K, NT, IDL_OUT_COUNTS_I32>(p, st);
-        case IDL_OUT_FREQ_F32: return launch_profiles<K, NT, IDL_OUT_FREQ_F32>(p, st);
-        case IDL_OUT_STD_F32: return launch_profiles<K, NT, IDL_OUT_STD_F32>(p, st);
-        case IDL_OUT_FREQ_F64: return launch_profiles<K, NT, IDL_OUT_FREQ_F64>(p, st);
+        case OUT_STATS: return launch_profiles<K, NT, OUT_STATS>(p, plan, st, grid_out);
+        case IDL_OUT_COUNTS_I32: return launch_profiles<K, NT, IDL_OUT_COUNTS_I32>(p, plan, st);
+        case IDL_OUT_FREQ_F32: return launch_profiles<K, NT, IDL_OUT_FREQ_F32>(p, plan, st);
+        case IDL_OUT_STD_F32: return launch_profiles<K, NT, IDL_OUT_STD_F32>(p, plan, st);
+        case IDL_OUT_FREQ_F64: return launch_profiles<K, NT, IDL_OUT_FREQ_F64>(p, plan, st);
     }
     return set_error(IDL_EINVAL, "unknown out_kind%s %lld", "", out_kind);
+}
+
+static int dispatch_k(const ProfParams& p, const Plan& plan, int k, int out_kind, cudaStream_t st, int* grid_out = nullptr) {
+    switch (k) {
+        case 1: return dispatch_out<1, 64>(p, plan, out_kind, st, grid_out);
+        case 2: return dispatch_out<2, 64>(p, plan, out_kind, st, grid_out);
+        case 3: return dispatch_out<3, 64>(p, plan, out_kind, st, grid_out);
+        case 4: return dispatch_out<4, 128>(p, plan, out_kind, st, grid_out);
+        case 5: return dispatch_out<5, 256>(p, plan, out_kind, st, grid_out);
+        case 6: return dispatch_out<6, 512>(p, plan, out_kind, st, grid_out);
+    }
+    return set_error(IDL_EUNSUPPORTED, "idl_profiles: unsupported k%s", "");
+}
+
+// ---- host-side plan of one call: variant descriptors, gap tables, output offsets ----
+struct HostPlan {
+    Plan plan;           // what the kernels receive by value (valid when inl)
+    bool inl;            // fits the kernel parameter
+    int n_tabs, n_bern, n_ent;
+    bool has_explicit, randn_small;   // randn_small: every Random_N slot removes <= 127 windows (the producer/consumer kernel's limit)
+    int kind0;
+};
+
+static int make_plan(const char* who, const idl_variant* variants, int n_variants, const int64_t* out_off, int S, const int64_t* d_edit_off,
+                     const uint32_t* d_edits, unsigned char* ws, cudaStream_t st, HostPlan& hp) {
+    static thread_local VarDesc h_vars[MAX_VARIANTS];
+    static thread_local uint32_t h_gtab[MAX_TABS * RNG_BLOCK];
+    double tab_p[MAX_TABS];
+    int n_tabs = 0;
+    auto table_of = [&](double pr) -> int {
+        for (int t = 0; t < n_tabs; ++t)
+            if (tab_p[t] == pr) return t;
+        if (n_tabs == MAX_TABS) return -1;
+        tab_p[n_tabs] = pr;
+        geometric_table(pr, h_gtab + n_tabs * RNG_BLOCK);
+        return n_tabs++;
+    };
+    hp.n_bern = hp.n_ent = 0;
+    hp.has_explicit = false;
+    hp.randn_small = true;
+    for (int v = 0; v < n_variants; ++v) {
+        const idl_variant& iv = variants[v];
+        VarDesc& d = h_vars[v];
+        d.kind = iv.kind; d.rng_id = iv.rng_id; d.n_bp = iv.n_bp; d.explicit_idx = iv.explicit_idx; d.tab1 = 0; d.tab2 = 0;
+        d.slope1 = 0.f; d.slope2 = 0.f;
+        if (iv.kind < IDL_KIND_CLEAN || iv.kind > IDL_KIND_EXPLICIT) return set_error(IDL_EINVAL, "%s: bad variant kind %lld", who, iv.kind);
+        if (iv.kind == IDL_KIND_TRANSITION || iv.kind == IDL_KIND_BOTH) {
+            if (!(iv.p1 >= 0.0 && iv.p1 <= 1.0)) return set_error(IDL_EINVAL, "%s: p1 out of range", who, 0);
+            d.tab1 = table_of(iv.p1); d.slope1 = gap_slope(iv.p1);
+        }
+        if (iv.kind == IDL_KIND_TRANSVERSION || iv.kind == IDL_KIND_BOTH) {
+            if (!(iv.p2 >= 0.0 && iv.p2 <= 1.0)) return set_error(IDL_EINVAL, "%s: p2 out of range", who, 0);
+            d.tab2 = table_of(iv.p2); d.slope2 = gap_slope(iv.p2);
+        }
+        if (d.tab1 < 0 || d.tab2 < 0) return set_error(IDL_EUNSUPPORTED, "%s: too many distinct mutation rates", who, 0);
+        if (iv.kind == IDL_KIND_RANDOM_N && (iv.n_bp < 0 || iv.n_bp > LIST_CAP / 2)) return set_error(IDL_EUNSUPPORTED, "%s: Random_N n_bp must be <= 1024", who, 0);
+        if (iv.kind == IDL_KIND_EXPLICIT && (!d_edit_off || !d_edits)) return set_error(IDL_EINVAL, "%s: explicit variant without edit lists", who, 0);
+        if (iv.kind == IDL_KIND_EXPLICIT) hp.has_explicit = true;
+        else if (iv.kind == IDL_KIND_RANDOM_N) { if (iv.n_bp * PC_K > 127) hp.randn_small = false; else if (iv.n_bp > 0) hp.n_ent += iv.n_bp; }
+        else if (iv.kind != IDL_KIND_CLEAN) ++hp.n_bern;
+    }
+    hp.kind0 = h_vars[0].kind;
+    hp.n_tabs = n_tabs;
+    hp.inl = n_variants <= SVARS && S <= SVARS && n_tabs <= STABS;
+    if (hp.inl) {
+        memset(&hp.plan, 0, sizeof(hp.plan));
+        memcpy(hp.plan.vars, h_vars, sizeof(VarDesc) * n_variants);
+        for (int s = 0; s < S; ++s) hp.plan.out_off[s] = out_off[s];
+        memcpy(hp.plan.gtab, h_gtab, sizeof(uint32_t) * RNG_BLOCK * n_tabs);
+    } else {   // big plans travel through the workspace (pageable staging: the host arrays may be reused after the calls return)
+        IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_VARS, h_vars, sizeof(VarDesc) * n_variants, cudaMemcpyHostToDevice, st));
+        IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_OUTOFF, out_off, sizeof(int64_t) * S, cudaMemcpyHostToDevice, st));
+        if (n_tabs) IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_GTAB, h_gtab, sizeof(uint32_t) * RNG_BLOCK * n_tabs, cudaMemcpyHostToDevice, st));
+    }
+    return IDL_OK;
+}
+
+// identity of a prepared buffer: FNV-1a over everything the prepared data depends on
+static unsigned long long prep_stamp_of(const uint32_t* d_codes, const int32_t* d_sidx, int64_t n_items, int64_t seq_id0, const idl_variant* variants,
+                                        int n_variants, uint64_t seed, int pseudocount) {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](const void* ptr, size_t nb) {
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(ptr);
+        for (size_t i = 0; i < nb; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    };
+    mix(&d_codes, sizeof(d_codes)); mix(&d_sidx, sizeof(d_sidx)); mix(&n_items, sizeof(n_items)); mix(&seq_id0, sizeof(seq_id0));
+    mix(&seed, sizeof(seed)); mix(&pseudocount, sizeof(pseudocount));
+    for (int v = 0; v < n_variants; ++v) {   // slot 0 (statistics row) and the Bernoulli slots: what the buffer holds
+        const idl_variant& iv = variants[v];
+        const bool bern = iv.kind == IDL_KIND_TRANSITION || iv.kind == IDL_KIND_TRANSVERSION || iv.kind == IDL_KIND_BOTH;
+        if (v == 0 || bern) { mix(&iv.kind, sizeof(iv.kind)); mix(&iv.rng_id, sizeof(iv.rng_id)); mix(&iv.p1, sizeof(iv.p1)); mix(&iv.p2, sizeof(iv.p2)); }
+    }
+    return h ? h : 1ull;
+}
+
+static void fill_params(ProfParams& p, const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off, const int32_t* d_len,
+                        int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items, int64_t seq_id0, int n_variants, const int32_t* d_sel, int S,
+                        uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits, void* d_out, int64_t out_stride, int pseudocount,
+                        int accumulate, const float* d_mean, const float* d_scale, int32_t* d_status, unsigned char* ws, const HostPlan& hp) {
+    memset(&p, 0, sizeof(p));
+    p.codes = d_codes; p.nmask = d_nmask; p.chunk_off = d_chunk_off; p.len = d_len; p.sidx = d_sidx; p.sel = d_sel;
+    p.n_items = n_items; p.seq_id0 = seq_id0; p.n_seqs_total = n_seqs_total; p.S = S; p.n_vars = n_variants; p.n_tabs = hp.n_tabs;
+    p.vars = reinterpret_cast<const VarDesc*>(ws + WS_VARS);
+    p.seed = seed; p.gtab = reinterpret_cast<const uint32_t*>(ws + WS_GTAB);
+    p.edit_off = d_edit_off; p.edits = d_edits; p.out = d_out;
+    p.out_off = reinterpret_cast<const int64_t*>(ws + WS_OUTOFF);
+    p.out_stride = out_stride; p.pseudocount = pseudocount; p.accumulate = accumulate;
+    p.mean = d_mean; p.scale = d_scale; p.status = d_status;
+    p.rscale = reinterpret_cast<const float*>(ws + WS_RSCALE);
+    p.work_counter = reinterpret_cast<unsigned long long*>(ws);
+    p.inline_plan = hp.inl ? 1 : 0;
+#ifdef IDL_DEVTOOLS
+    static const bool want_prof = getenv("IDL_PHASE_PROF") != nullptr;
+    p.phase_prof = want_prof ? reinterpret_cast<unsigned long long*>(ws + WS_PROF) : nullptr;
+    { const char* e = getenv("IDL_PC_DBG"); p.dbg = e ? atoi(e) : 0; }
+#endif
+}
+
+static int profiles_impl(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
+                         const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
+                         int64_t seq_id0, int k, const idl_variant* variants, int n_variants, const int32_t* d_sel,
+                         int S, uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits, int out_kind,
+                         void* d_out, const int64_t* out_off, int64_t out_stride, int pseudocount, int accumulate,
+                         const float* d_mean, const float* d_scale, int32_t* d_status, void* d_workspace,
+                         size_t workspace_bytes, void* stream, double* d_stats_partials, double* d_stats_n, int* n_parts_out,
+                         const void* d_prep, size_t prep_size) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t zero_off = 0;
+    if (out_kind == OUT_STATS) { out_off = &zero_off; out_stride = 0; }
+    if (!d_codes || !d_nmask || !d_chunk_off || !d_len || !variants || (!d_out && out_kind != OUT_STATS) || !out_off || !d_workspace)
+        return set_error(IDL_EINVAL, "idl_profiles: null pointer%s", "");
+    if (workspace_bytes < WS_TOTAL) return set_error(IDL_EINVAL, "idl_profiles: workspace too small%s (need %lld bytes)", "", (long long)WS_TOTAL);
+    if (k < 1 || k > 6) return set_error(IDL_EUNSUPPORTED, "idl_profiles: k must be in 1..6%s (got %lld)", "", k);
+    if (n_variants < 1 || n_variants > MAX_VARIANTS || S < 1 || S > MAX_VARIANTS)
+        return set_error(IDL_EINVAL, "idl_profiles: n_variants / S out of range%s", "");
+    if (!d_sel && S != n_variants) return set_error(IDL_EINVAL, "idl_profiles: S must equal n_variants without d_sel%s", "");
+    if (out_kind == IDL_OUT_STD_F32 && (!d_mean || !d_scale)) return set_error(IDL_EINVAL, "idl_profiles: mean/scale required%s", "");
+    if (accumulate && out_kind != IDL_OUT_COUNTS_I32) return set_error(IDL_EINVAL, "idl_profiles: accumulate only for counts%s", "");
+    if (n_items <= 0) return IDL_OK;
+    const int F = 1 << (2 * k);
+    if (k >= 1 && F >= 4 && (out_stride % 4 != 0)) return set_error(IDL_EINVAL, "idl_profiles: out_stride must be a multiple of 4%s", "");
+
+    unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
+    HostPlan hp;
+    const int rc_plan = make_plan("idl_profiles", variants, n_variants, out_off, S, d_edit_off, d_edits, ws, st, hp);
+    if (rc_plan != IDL_OK) return rc_plan;
+    IDL_CUDA_CHECK(cudaMemsetAsync(ws, 0, 24, st));   // work counter, deferred-item counter, deferred scan cursor
+    ProfParams p;
+    fill_params(p, d_codes, d_nmask, d_chunk_off, d_len, n_seqs_total, d_sidx, n_items, seq_id0, n_variants, d_sel, S, seed, d_edit_off, d_edits,
+                d_out, out_stride, pseudocount, accumulate, d_mean, d_scale, d_status, ws, hp);
+    if (out_kind == IDL_OUT_STD_F32) {
+        rscale_kernel<<<(F + 255) / 256, 256, 0, st>>>(d_scale, reinterpret_cast<float*>(ws + WS_RSCALE), F); note_launch();
+        IDL_CUDA_CHECK(cudaGetLastError());
+    }
+    p.stats_partials = d_stats_partials; p.stats_n = d_stats_n;
+    if (out_kind == OUT_STATS) return dispatch_k(p, hp.plan, k, out_kind, st, n_parts_out);
+    // ---- producer/consumer kernel (k = 6, float outputs, whole-schedule featurisation of PREPARED items) ----
+    bool pc_ok = d_prep && k == 6 && (out_kind == IDL_OUT_FREQ_F32 || out_kind == IDL_OUT_STD_F32) && !d_sel && d_status && hp.inl &&
+                 n_variants <= PC_MAXS && n_items >= 2LL * sm_count() && prep_size >= prep_bytes(n_items);
+    if (pc_ok) {
+        if (hp.has_explicit || !hp.randn_small || hp.n_bern > PC_DENSE || hp.n_ent > PC_LIST || hp.n_ent * PC_K > PC_REM) pc_ok = false;
+        // TMA bulk copies: 16-byte aligned rows
+        if (((uintptr_t)d_out & 15) || (out_stride & 3) || ((uintptr_t)d_codes & 15) || ((uintptr_t)d_nmask & 15) || ((uintptr_t)d_prep & 15)) pc_ok = false;
+        for (int v = 0; v < S && pc_ok; ++v) if (out_off[v] & 3) pc_ok = false;
+    }
+    if (pc_ok) {
+        p.prep = const_cast<void*>(d_prep);
+        p.prep_stamp = prep_stamp_of(d_codes, d_sidx, n_items, seq_id0, variants, n_variants, seed, pseudocount);
+        auto kern = out_kind == IDL_OUT_STD_F32 ? profiles_pc_kernel<IDL_OUT_STD_F32> : profiles_pc_kernel<IDL_OUT_FREQ_F32>;
+        IDL_CUDA_CHECK(ensure_dyn_smem((const void*)kern, sizeof(PcSmem)));
+        long long grid = sm_count();
+        if (grid > n_items) grid = n_items;
+        kern<<<(unsigned)grid, PC_NT, sizeof(PcSmem), st>>>(p, hp.plan); note_launch();
+        IDL_CUDA_CHECK(cudaGetLastError());
+        p.only_deferred = 1;   // whatever the fast kernel could not take is redone by the generic one
+    }
+    return dispatch_k(p, hp.plan, k, out_kind, st);
 }
 
 }  // namespace idl
@@ -1279,6 +1410,7 @@ using namespace idl;
 extern "C" {
 
 int idl_abi_version(void) { return IDL_ABI_VERSION; }
+long long idl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* idl_last_error(void) { return g_err; }
 
 int idl_geometric_table(double p, uint32_t* out128) {
@@ -1301,181 +1433,12 @@ int idl_pack(const uint8_t* d_ascii, const int64_t* d_byte_off, int64_t n, int a
     if (gy > 1024) gy = 1024;
     if (gx * gy > cap * 4 && gx > 1) { gx = cap * 4 / gy; if (gx < 1) gx = 1; }
     pack_kernel<<<dim3((unsigned)gx, (unsigned)gy), PACK_NT, 0, (cudaStream_t)stream>>>(
-        d_ascii, d_byte_off, d_chunk_off, n, alphabet, d_codes, d_nmask, d_len, d_bad);
+        d_ascii, d_byte_off, d_chunk_off, n, alphabet, d_codes, d_nmask, d_len, d_bad); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }
 
 size_t idl_profiles_workspace_bytes(void) { return WS_TOTAL; }
-
-static int profiles_impl(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
-                         const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
-                         int64_t seq_id0, int k, const idl_variant* variants, int n_variants, const int32_t* d_sel,
-                         int S, uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits, int out_kind,
-                         void* d_out, const int64_t* out_off, int64_t out_stride, int pseudocount, int accumulate,
-                         const float* d_mean, const float* d_scale, int32_t* d_status, void* d_workspace,
-                         size_t workspace_bytes, void* stream, double* d_stats_partials, double* d_stats_n, int* n_parts_out) {
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t zero_off = 0;
-    if (out_kind == OUT_STATS) { out_off = &zero_off; out_stride = 0; }
-    if (!d_codes || !d_nmask || !d_chunk_off || !d_len || !variants || (!d_out && out_kind != OUT_STATS) || !out_off || !d_workspace)
-        return set_error(IDL_EINVAL, "idl_profiles: null pointer%s", "");
-    if (workspace_bytes < WS_TOTAL) return set_error(IDL_EINVAL, "idl_profiles: workspace too small%s (need %lld bytes)", "", (long long)WS_TOTAL);
-    if (k < 1 || k > 6) return set_error(IDL_EUNSUPPORTED, "idl_profiles: k must be in 1..6%s (got %lld)", "", k);
-    if (n_variants < 1 || n_variants > MAX_VARIANTS || S < 1 || S > MAX_VARIANTS)
-        return set_error(IDL_EINVAL, "idl_profiles: n_variants / S out of range%s", "");
-    if (!d_sel && S != n_variants) return set_error(IDL_EINVAL, "idl_profiles: S must equal n_variants without d_sel%s", "");
-    if (out_kind == IDL_OUT_STD_F32 && (!d_mean || !d_scale)) return set_error(IDL_EINVAL, "idl_profiles: mean/scale required%s", "");
-    if (accumulate && out_kind != IDL_OUT_COUNTS_I32) return set_error(IDL_EINVAL, "idl_profiles: accumulate only for counts%s", "");
-    if (n_items <= 0) return IDL_OK;
-    const int F = 1 << (2 * k);
-    if (k >= 1 && F >= 4 && (out_stride % 4 != 0)) return set_error(IDL_EINVAL, "idl_profiles: out_stride must be a multiple of 4%s", "");
-
-    // ---- host-side plan: variant descriptors and gap tables ----
-    static thread_local VarDesc h_vars[MAX_VARIANTS];
-    static thread_local uint32_t h_gtab[MAX_TABS * RNG_BLOCK];
-    double tab_p[MAX_TABS];
-    int n_tabs = 0;
-    auto table_of = [&](double pr) -> int {
-        for (int t = 0; t < n_tabs; ++t)
-            if (tab_p[t] == pr) return t;
-        if (n_tabs == MAX_TABS) return -1;
-        tab_p[n_tabs] = pr;
-        geometric_table(pr, h_gtab + n_tabs * RNG_BLOCK);
-        return n_tabs++;
-    };
-    for (int v = 0; v < n_variants; ++v) {
-        const idl_variant& iv = variants[v];
-        VarDesc& d = h_vars[v];
-        d.kind = iv.kind; d.rng_id = iv.rng_id; d.n_bp = iv.n_bp; d.explicit_idx = iv.explicit_idx; d.tab1 = 0; d.tab2 = 0;
-        d.slope1 = 0.f; d.slope2 = 0.f;
-        if (iv.kind < IDL_KIND_CLEAN || iv.kind > IDL_KIND_EXPLICIT) return set_error(IDL_EINVAL, "idl_profiles: bad variant kind%s %lld", "", iv.kind);
-        if (iv.kind == IDL_KIND_TRANSITION || iv.kind == IDL_KIND_BOTH) {
-            if (!(iv.p1 >= 0.0 && iv.p1 <= 1.0)) return set_error(IDL_EINVAL, "idl_profiles: p1 out of range%s", "");
-            d.tab1 = table_of(iv.p1); d.slope1 = gap_slope(iv.p1);
-        }
-        if (iv.kind == IDL_KIND_TRANSVERSION || iv.kind == IDL_KIND_BOTH) {
-            if (!(iv.p2 >= 0.0 && iv.p2 <= 1.0)) return set_error(IDL_EINVAL, "idl_profiles: p2 out of range%s", "");
-            d.tab2 = table_of(iv.p2); d.slope2 = gap_slope(iv.p2);
-        }
-        if (d.tab1 < 0 || d.tab2 < 0) return set_error(IDL_EUNSUPPORTED, "idl_profiles: too many distinct mutation rates%s", "");
-        if (iv.kind == IDL_KIND_RANDOM_N && (iv.n_bp < 0 || iv.n_bp > LIST_CAP / 2)) return set_error(IDL_EUNSUPPORTED, "idl_profiles: Random_N n_bp must be <= 1024%s", "");
-        if (iv.kind == IDL_KIND_EXPLICIT && (!d_edit_off || !d_edits)) return set_error(IDL_EINVAL, "idl_profiles: explicit variant without edit lists%s", "");
-    }
-    unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
-    IDL_CUDA_CHECK(cudaMemsetAsync(ws, 0, 24, st));   // work counter, deferred-item counter, deferred scan cursor
-    // descriptor upload, skipped when this workspace already holds exactly these descriptors
-    // (repeated calls of a training loop then enqueue no host->device copies at all)
-    struct PlanCache { void* ws; int n_variants, S, n_tabs; VarDesc vars[SVARS]; int64_t out_off[SVARS]; double tab_p[MAX_TABS]; };
-    static thread_local PlanCache cache = {nullptr, 0, 0, 0, {}, {}, {}};
-    bool same = cache.ws == d_workspace && cache.n_variants == n_variants && cache.S == S && cache.n_tabs == n_tabs &&
-                n_variants <= SVARS && S <= SVARS;
-    if (same) same = memcmp(cache.vars, h_vars, sizeof(VarDesc) * n_variants) == 0 && memcmp(cache.out_off, out_off, sizeof(int64_t) * S) == 0 &&
-                     memcmp(cache.tab_p, tab_p, sizeof(double) * n_tabs) == 0;
-    if (!same) {
-        IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_VARS, h_vars, sizeof(VarDesc) * n_variants, cudaMemcpyHostToDevice, st));
-        IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_OUTOFF, out_off, sizeof(int64_t) * S, cudaMemcpyHostToDevice, st));
-        if (n_tabs) IDL_CUDA_CHECK(cudaMemcpyAsync(ws + WS_GTAB, h_gtab, sizeof(uint32_t) * RNG_BLOCK * n_tabs, cudaMemcpyHostToDevice, st));
-        cache.ws = nullptr;
-        if (n_variants <= SVARS && S <= SVARS) {
-            cache.ws = d_workspace; cache.n_variants = n_variants; cache.S = S; cache.n_tabs = n_tabs;
-            memcpy(cache.vars, h_vars, sizeof(VarDesc) * n_variants);
-            memcpy(cache.out_off, out_off, sizeof(int64_t) * S);
-            memcpy(cache.tab_p, tab_p, sizeof(double) * n_tabs);
-        }
-    }
-    ProfParams p;
-    p.codes = d_codes; p.nmask = d_nmask; p.chunk_off = d_chunk_off; p.len = d_len; p.sidx = d_sidx; p.sel = d_sel;
-    p.n_items = n_items; p.seq_id0 = seq_id0; p.n_seqs_total = n_seqs_total; p.S = S; p.n_vars = n_variants; p.n_tabs = n_tabs;
-    p.vars = reinterpret_cast<const VarDesc*>(ws + WS_VARS);
-    p.seed = seed; p.gtab = reinterpret_cast<const uint32_t*>(ws + WS_GTAB);
-    p.edit_off = d_edit_off; p.edits = d_edits; p.out = d_out;
-    p.out_off = reinterpret_cast<const int64_t*>(ws + WS_OUTOFF);
-    p.out_stride = out_stride; p.pseudocount = pseudocount; p.accumulate = accumulate;
-    p.mean = d_mean; p.scale = d_scale; p.status = d_status;
-    p.rscale = reinterpret_cast<const float*>(ws + WS_RSCALE);
-    if (out_kind == IDL_OUT_STD_F32) {
-        rscale_kernel<<<(F + 255) / 256, 256, 0, st>>>(d_scale, reinterpret_cast<float*>(ws + WS_RSCALE), F);
-        IDL_CUDA_CHECK(cudaGetLastError());
-    }
-    p.work_counter = reinterpret_cast<unsigned long long*>(ws);
-    static const bool want_prof = getenv("IDL_PHASE_PROF") != nullptr;
-    p.phase_prof = want_prof ? reinterpret_cast<unsigned long long*>(ws + WS_PROF) : nullptr;
-    p.only_deferred = 0;
-    { const char* e = getenv("IDL_PC_DBG"); p.dbg = e ? atoi(e) : 0; }
-    p.stats_partials = d_stats_partials; p.stats_n = d_stats_n;
-    if (out_kind == OUT_STATS && k == 6 && d_status && getenv("IDL_NO_FAST_STATS") == nullptr &&
-        (h_vars[0].kind == IDL_KIND_CLEAN || h_vars[0].kind == IDL_KIND_TRANSITION || h_vars[0].kind == IDL_KIND_TRANSVERSION ||
-         h_vars[0].kind == IDL_KIND_BOTH || (h_vars[0].kind == IDL_KIND_RANDOM_N && h_vars[0].n_bp <= 0))) {
-        // pipelined register-accumulator kernel, one CTA per SM; what it defers (status bit 1) goes to the generic kernel below,
-        // which appends its own parts
-        static bool configured = false;
-        if (!configured) {
-            IDL_CUDA_CHECK(cudaFuncSetAttribute(stats_fast_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SfSmem)));
-            configured = true;
-        }
-        long long grid = sm_count();
-        if (grid > n_items) grid = n_items;
-        stats_fast_kernel<6><<<(unsigned)grid, SF_NT, sizeof(SfSmem), st>>>(p);
-        IDL_CUDA_CHECK(cudaGetLastError());
-        p.only_deferred = 1;
-        p.stats_partials += (size_t)grid * 2 * F;
-        p.stats_n += grid;
-        int g2 = 0;
-        const int rc = dispatch_out<6, 512>(p, out_kind, st, &g2);
-        if (n_parts_out) *n_parts_out = (int)grid + g2;
-        return rc;
-    }
-    if (out_kind == OUT_STATS) {
-        switch (k) {
-            case 1: return dispatch_out<1, 64>(p, out_kind, st, n_parts_out);
-            case 2: return dispatch_out<2, 64>(p, out_kind, st, n_parts_out);
-            case 3: return dispatch_out<3, 64>(p, out_kind, st, n_parts_out);
-            case 4: return dispatch_out<4, 128>(p, out_kind, st, n_parts_out);
-            case 5: return dispatch_out<5, 256>(p, out_kind, st, n_parts_out);
-            case 6: return dispatch_out<6, 512>(p, out_kind, st, n_parts_out);
-        }
-    }
-    // ---- producer/consumer kernel (k = 6, float outputs, whole-schedule featurisation) ----
-    bool pc_ok = k == 6 && (out_kind == IDL_OUT_FREQ_F32 || out_kind == IDL_OUT_STD_F32) && !d_sel && d_status &&
-                 n_variants <= PC_MAXS && n_items >= 2LL * sm_count() && getenv("IDL_NO_PC") == nullptr;
-    if (pc_ok) {
-        int n_bern = 0, n_ent = 0;
-        for (int v = 0; v < n_variants; ++v) {
-            const VarDesc& d = h_vars[v];
-            if (d.kind == IDL_KIND_EXPLICIT) pc_ok = false;
-            else if (d.kind == IDL_KIND_RANDOM_N) { if (d.n_bp * PC_K > 127) pc_ok = false; else if (d.n_bp > 0) n_ent += d.n_bp; }
-            else if (d.kind != IDL_KIND_CLEAN) ++n_bern;
-        }
-        if (n_bern > PC_DENSE || n_ent > LIST_CAP || n_ent * PC_K > PC_REM) pc_ok = false;
-        // TMA bulk copies: 16-byte aligned rows
-        if (((uintptr_t)d_out & 15) || (out_stride & 3) || ((uintptr_t)d_codes & 15) || ((uintptr_t)d_nmask & 15)) pc_ok = false;
-        for (int v = 0; v < S && pc_ok; ++v) if (out_off[v] & 3) pc_ok = false;
-    }
-    if (pc_ok) {
-        auto kern = out_kind == IDL_OUT_STD_F32 ? profiles_pc_kernel<IDL_OUT_STD_F32> : profiles_pc_kernel<IDL_OUT_FREQ_F32>;
-        static bool configured[2] = {false, false};
-        const int ci = out_kind == IDL_OUT_STD_F32 ? 1 : 0;
-        if (!configured[ci]) {
-            IDL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PcSmem)));
-            configured[ci] = true;
-        }
-        long long grid = sm_count();
-        if (grid > n_items) grid = n_items;
-        kern<<<(unsigned)grid, PC_NT, sizeof(PcSmem), st>>>(p);
-        IDL_CUDA_CHECK(cudaGetLastError());
-        p.only_deferred = 1;   // whatever the fast kernel could not take is redone by the generic one
-    }
-    switch (k) {
-        case 1: return dispatch_out<1, 64>(p, out_kind, st);
-        case 2: return dispatch_out<2, 64>(p, out_kind, st);
-        case 3: return dispatch_out<3, 64>(p, out_kind, st);
-        case 4: return dispatch_out<4, 128>(p, out_kind, st);
-        case 5: return dispatch_out<5, 256>(p, out_kind, st);
-        case 6: return dispatch_out<6, 512>(p, out_kind, st);
-    }
-    return set_error(IDL_EUNSUPPORTED, "idl_profiles: unsupported k%s", "");
-}
 
 int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
                  const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
@@ -1487,7 +1450,78 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
     if (out_kind < IDL_OUT_COUNTS_I32 || out_kind > IDL_OUT_FREQ_F64) return set_error(IDL_EINVAL, "idl_profiles: unknown out_kind%s %lld", "", out_kind);
     return profiles_impl(d_codes, d_nmask, d_chunk_off, d_len, n_seqs_total, d_sidx, n_items, seq_id0, k, variants, n_variants, d_sel, S,
                          seed, d_edit_off, d_edits, out_kind, d_out, out_off, out_stride, pseudocount, accumulate, d_mean, d_scale,
-                         d_status, d_workspace, workspace_bytes, stream, nullptr, nullptr, nullptr);
+                         d_status, d_workspace, workspace_bytes, stream, nullptr, nullptr, nullptr, nullptr, 0);
+}
+
+int idl_profiles_prepared(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
+                          const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
+                          int64_t seq_id0, int k, const idl_variant* variants, int n_variants, uint64_t seed, int out_kind,
+                          void* d_out, const int64_t* out_off, int64_t out_stride, int pseudocount,
+                          const float* d_mean, const float* d_scale, int32_t* d_status, const void* d_prep, size_t prep_size,
+                          void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (out_kind != IDL_OUT_FREQ_F32 && out_kind != IDL_OUT_STD_F32) return set_error(IDL_EINVAL, "idl_profiles_prepared: float32 outputs only%s", "");
+    if (!d_prep || !d_status) return set_error(IDL_EINVAL, "idl_profiles_prepared: d_prep and d_status are required%s", "");
+    return profiles_impl(d_codes, d_nmask, d_chunk_off, d_len, n_seqs_total, d_sidx, n_items, seq_id0, k, variants, n_variants, nullptr, n_variants,
+                         seed, nullptr, nullptr, out_kind, d_out, out_off, out_stride, pseudocount, 0, d_mean, d_scale,
+                         d_status, d_workspace, workspace_bytes, stream, nullptr, nullptr, nullptr, d_prep, prep_size);
+}
+
+size_t idl_prepare_bytes(int64_t n_items) { return n_items > 0 ? prep_bytes(n_items) : 0; }
+
+int idl_profiles_prepare(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off, const int32_t* d_len,
+                         int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items, int64_t seq_id0, int k,
+                         const idl_variant* variants, int n_variants, uint64_t seed, int pseudocount, void* d_prep, size_t prep_size,
+                         double* d_partials, double* d_part_n, int max_parts, int* n_parts, int32_t* d_status, void* d_workspace,
+                         size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_codes || !d_nmask || !d_chunk_off || !d_len || !variants || !d_prep || !d_status || !d_workspace)
+        return set_error(IDL_EINVAL, "idl_profiles_prepare: null pointer%s", "");
+    if (k != PC_K) return set_error(IDL_EUNSUPPORTED, "idl_profiles_prepare: k must be 6%s (got %lld)", "", k);
+    if (workspace_bytes < WS_TOTAL) return set_error(IDL_EINVAL, "idl_profiles_prepare: workspace too small%s (need %lld bytes)", "", (long long)WS_TOTAL);
+    if (n_variants < 1 || n_variants > PC_MAXS) return set_error(IDL_EUNSUPPORTED, "idl_profiles_prepare: 1..64 variants%s", "");
+    if (n_items <= 0) { if (n_parts) *n_parts = 0; return IDL_OK; }
+    if (prep_size < prep_bytes(n_items)) return set_error(IDL_EINVAL, "idl_profiles_prepare: d_prep too small%s (need %lld bytes)", "", (long long)prep_bytes(n_items));
+    if (((uintptr_t)d_prep & 15) || ((uintptr_t)d_codes & 15) || ((uintptr_t)d_nmask & 7)) return set_error(IDL_EINVAL, "idl_profiles_prepare: misaligned buffer%s", "");
+    if (d_partials && (!d_part_n || !n_parts || max_parts < sm_count() * 8)) return set_error(IDL_EINVAL, "idl_profiles_prepare: statistics need d_part_n, n_parts and max_parts >= 8 x SMs%s", "");
+    unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
+    int64_t offs[PC_MAXS];
+    for (int s = 0; s < n_variants; ++s) offs[s] = 0;
+    HostPlan hp;
+    const int rc_plan = make_plan("idl_profiles_prepare", variants, n_variants, offs, n_variants, nullptr, nullptr, ws, st, hp);
+    if (rc_plan != IDL_OK) return rc_plan;
+    if (!hp.inl || hp.has_explicit || hp.n_bern > PC_DENSE) return set_error(IDL_EUNSUPPORTED, "idl_profiles_prepare: at most 3 Bernoulli slots, 4 distinct rates, no explicit lists%s", "");
+    if (hp.kind0 == IDL_KIND_RANDOM_N && variants[0].n_bp > 0) return set_error(IDL_EUNSUPPORTED, "idl_profiles_prepare: slot 0 must be clean or a Bernoulli mimic%s", "");
+    IDL_CUDA_CHECK(cudaMemsetAsync(ws, 0, 24, st));
+    ProfParams p;
+    fill_params(p, d_codes, d_nmask, d_chunk_off, d_len, n_seqs_total, d_sidx, n_items, seq_id0, n_variants, nullptr, n_variants, seed, nullptr, nullptr,
+                nullptr, 0, pseudocount, 0, nullptr, nullptr, d_status, ws, hp);
+    p.prep = d_prep;
+    p.prep_stamp = prep_stamp_of(d_codes, d_sidx, n_items, seq_id0, variants, n_variants, seed, pseudocount);
+    IDL_CUDA_CHECK(ensure_dyn_smem((const void*)prep_kernel<PC_K>, sizeof(PrSmem)));
+    int per_sm = 0;
+    IDL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, prep_kernel<PC_K>, PR_NT, sizeof(PrSmem)));
+    if (per_sm < 1) return set_error(IDL_ECUDA, "prepare kernel does not fit on an SM%s", "");
+    long long grid = (long long)sm_count() * per_sm;
+    if (grid > n_items) grid = n_items;
+    prep_kernel<PC_K><<<(unsigned)grid, PR_NT, sizeof(PrSmem), st>>>(p, hp.plan); note_launch();
+    IDL_CUDA_CHECK(cudaGetLastError());
+    if (!d_partials) return IDL_OK;
+    // ---- statistics of slot 0: column sums over the prepared rows + the generic kernel for the items the prepare pass left out ----
+    int parts = sm_count() * 2;
+    if (parts > n_items) parts = (int)n_items;
+    const int rows_per_part = (int)((n_items + parts - 1) / parts);
+    parts = (int)((n_items + rows_per_part - 1) / rows_per_part);
+    colstats16_kernel<<<dim3(PC_F / 4 / CS16_NT, (unsigned)parts), CS16_NT, 0, st>>>(reinterpret_cast<const unsigned char*>(d_prep), n_items, rows_per_part,
+                                                                                   pseudocount, d_partials, d_part_n); note_launch();
+    IDL_CUDA_CHECK(cudaGetLastError());
+    p.only_deferred = 1;
+    p.S = 1; p.n_vars = 1;
+    p.stats_partials = d_partials + (size_t)parts * 2 * PC_F;
+    p.stats_n = d_part_n + parts;
+    int g2 = 0;
+    const int rc = dispatch_k(p, hp.plan, k, OUT_STATS, st, &g2);
+    *n_parts = parts + g2;
+    return rc;
 }
 
 int idl_profile_stats(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off, const int32_t* d_len,
@@ -1501,7 +1535,7 @@ int idl_profile_stats(const uint32_t* d_codes, const uint32_t* d_nmask, const in
     if (n_items <= 0) return IDL_OK;
     return profiles_impl(d_codes, d_nmask, d_chunk_off, d_len, n_seqs_total, d_sidx, n_items, seq_id0, k, variant, 1, nullptr, 1, seed,
                          d_edit_off, d_edits, OUT_STATS, nullptr, nullptr, 0, pseudocount, 0, nullptr, nullptr, d_status, d_workspace,
-                         workspace_bytes, stream, d_partials, d_part_n, n_parts);
+                         workspace_bytes, stream, d_partials, d_part_n, n_parts, nullptr, 0);
 }
 
 int idl_kmer_counts(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
@@ -1524,6 +1558,7 @@ int idl_colstats(const void* d_x, int is_f64, int64_t n, int F, double* d_partia
     const dim3 grid((F + CS_NT - 1) / CS_NT, (unsigned)idl_colstats_parts(n));
     if (is_f64) colstats_kernel<double><<<grid, CS_NT, 0, (cudaStream_t)stream>>>((const double*)d_x, n, F, d_partials, d_part_n);
     else colstats_kernel<float><<<grid, CS_NT, 0, (cudaStream_t)stream>>>((const float*)d_x, n, F, d_partials, d_part_n);
+    note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }
@@ -1532,7 +1567,7 @@ int idl_scaler_finalize(const double* d_partials, const double* d_part_n, int n_
                         double* d_var64, double* d_scale64, float* d_mean32, float* d_scale32, void* stream) {
     if (!d_partials || !d_part_n || n_parts <= 0 || F <= 0) return set_error(IDL_EINVAL, "idl_scaler_finalize: bad argument%s", "");
     scaler_finalize_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_partials, d_part_n, n_parts, F, d_mean64, d_var64,
-                                                                              d_scale64, d_mean32, d_scale32);
+                                                                              d_scale64, d_mean32, d_scale32); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }
@@ -1545,7 +1580,7 @@ int idl_standardize_f32(const float* d_x, float* d_out, int64_t n, int F, const 
     long long grid = (n4 + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (grid > cap) grid = cap;
-    standardize_f32_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_out, n4, F / 4, d_mean32, d_scale32);
+    standardize_f32_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_out, n4, F / 4, d_mean32, d_scale32); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }
@@ -1557,7 +1592,7 @@ int idl_cgr_map(const int32_t* d_counts, int64_t n, int k, int32_t* d_cgr, int a
     long long grid = (total + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (grid > cap) grid = cap;
-    cgr_map_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_counts, d_cgr, total, k, accumulate);
+    cgr_map_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_counts, d_cgr, total, k, accumulate); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }
@@ -1576,7 +1611,7 @@ int idl_revcomp_fold(const int32_t* d_counts, int64_t n, int k, const int32_t* d
     long long grid = (n * R + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (grid > cap) grid = cap;
-    revcomp_fold_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_counts, d_out, n, k, d_canon, R);
+    revcomp_fold_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_counts, d_out, n, k, d_canon, R); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }
@@ -1585,7 +1620,7 @@ int idl_normalize_counts(const int32_t* d_counts, int64_t n, int R, double* d_ou
     if (!d_counts || (!d_out64 && !d_out32) || n < 0 || R < 1) return set_error(IDL_EINVAL, "idl_normalize_counts: bad argument%s", "");
     if (n == 0) return IDL_OK;
     const long long grid = (n * 32 + 255) / 256;
-    normalize_counts_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_counts, n, R, d_out64, d_out32);
+    normalize_counts_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_counts, n, R, d_out64, d_out32); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }
@@ -1598,7 +1633,7 @@ int idl_standardize_f64(const double* d_x, double* d_out64, float* d_out32, int6
     long long grid = (total + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
     if (grid > cap) grid = cap;
-    standardize_f64_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_out64, d_out32, total, F, d_mean64, d_scale64);
+    standardize_f64_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_out64, d_out32, total, F, d_mean64, d_scale64); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }

@@ -3,9 +3,11 @@
 // One persistent CTA of 1024 threads per SM, four roles that only meet through mbarriers:
 //
 //  * PRODUCERS (warps 16..31) prepare sequence i+1 into one of two shared-memory contexts: count
-//    the clean histogram, pack it to uint16, precompute the Random_N removal lists of every slot
-//    and the +-1 delta list of the Bernoulli slots, the per-slot window totals, output rows and
-//    the JOB ORDER (dense slots first, then the sparse slots sorted by window total).
+//    the clean histogram into packed uint16 counters, precompute the Random_N removal lists of
+//    every slot, the per-slot window totals, output rows and the JOB ORDER (dense slots first,
+//    then the sparse slots sorted by window total).  The +-1 delta list of the Bernoulli slots is
+//    NOT generated here: the prepare pass (prep.cuh) left it in global memory and one TMA bulk
+//    load per sequence brings it in for the builders.
 //  * BUILDERS (warps 0..7) write finished 16 KB float rows into a ring of PC_NBUF shared-memory
 //    row buffers (job j uses buffer j mod PC_NBUF).  A Random_N mimic differs from the clean
 //    histogram in <= 120 of 4096 bins and every untouched bin of every variant with the same
@@ -23,8 +25,8 @@
 //    back-pressured global stores), every global write is a full line, and nothing is ever
 //    re-read or partially overwritten in L2.  It also dispatches the items (atomic counter).
 //
-// Items this kernel cannot take (longer than 20 480 bases, > FAST_CAP hits in a 64-base block,
-// delta list overflow) are flagged in d_status (bit 1) and redone by the generic kernel.
+// Items this kernel cannot take (the ones the prepare pass flagged: longer than 20 480 bases,
+// list overflows) are flagged in d_status (bit 1) and redone by the generic kernel.
 // Included by kernels.cu (uses its helpers).
 #pragma once
 
@@ -46,8 +48,35 @@ constexpr uint32_t PC_BIAS2 = 0x80008000u;
 constexpr int PC_MAXS = 64;        // variant slots per sequence
 constexpr int PC_REM = 5888;       // removed k-mers of all Random_N slots of one sequence (51 x 20 x 6 = 6120)
 constexpr int PC_DELTA = 5120;     // Bernoulli +-1 deltas of one sequence
+constexpr int PC_LIST = 1024;      // Random_N draws of all slots of one sequence (PC_REM / K bounds them anyway)
 constexpr int PC_MAXB = 8;         // Bernoulli slots per sequence (producer tables)
 constexpr int PC_DENSE = 3;        // ... of which the builders can take (one delta scratch each; the reference schedule has 3)
+
+// ---- layout of the prepared buffer (written by prep_kernel, prep.cuh) ----
+struct alignas(16) PrepMeta {              // 32 bytes per item
+    int n_delta;                           // entries of the item's delta list
+    int total0;                            // window total of slot 0, pseudocount included (the statistics row)
+    int base_total;                        // clean window total, pseudocount included
+    int flags;                             // != 0: not prepared (generic kernel takes the item)
+    int dtot[PC_DENSE];                    // change of the window total per dense ordinal
+    int pad;
+};
+static_assert(sizeof(PrepMeta) == 32, "PrepMeta layout");
+
+struct PrepHeader {                        // 64 bytes
+    unsigned long long stamp;              // identifies (items, variants, seed, ...) the buffer was prepared for
+    long long n_items;
+    int n_dense, slot0_dense;
+    int pad[10];
+};
+static_assert(sizeof(PrepHeader) == 64, "PrepHeader layout");
+
+constexpr size_t PREP_HIST_BYTES = (size_t)PC_F * 2;          // uint16 histogram of slot 0
+constexpr size_t PREP_DELTA_BYTES = (size_t)PC_DELTA * 2;     // delta list (fixed stride)
+__host__ __device__ inline size_t prep_meta_off() { return sizeof(PrepHeader); }
+__host__ __device__ inline size_t prep_hist_off(long long n) { return sizeof(PrepHeader) + sizeof(PrepMeta) * (size_t)n; }
+__host__ __device__ inline size_t prep_delta_off(long long n) { return prep_hist_off(n) + PREP_HIST_BYTES * (size_t)n; }
+__host__ __device__ inline size_t prep_bytes(long long n) { return prep_delta_off(n) + PREP_DELTA_BYTES * (size_t)n + 16; }
 
 struct alignas(16) PcCtx {
     uint2 clean16[PC_VEC];         // packed clean histogram
@@ -60,6 +89,7 @@ struct alignas(16) PcCtx {
     unsigned char job_build[PC_MAXS];  // job j needs a rebuilt row (dense, or its total differs from job j - PC_NBUF's)
     int n_dense;
     int n_delta;
+    int delta_phase;               // parity of the delta buffer's TMA load (valid when n_delta > 0)
     int defer;                     // item must be redone by the generic kernel
     int base_total;
     long long item;                // -1: no more work
@@ -76,19 +106,16 @@ struct PcSmem {
     int rcorr_bad;                 // a correction did not fit (never seen): every item is deferred to the generic kernel
     // producer scratch
     alignas(16) uint32_t sseq[2][PC_SSEQ_W];   // double-buffered: the TMA load of item i+1 lands while item i is prepared
-    alignas(16) uint32_t list[LIST_CAP + 8];
-    uint16_t delta[PC_DELTA];      // Bernoulli deltas of the sequence being prepared / consumed: kmer | ordinal << 12 | (add ? 0x8000 : 0)
+    alignas(16) uint32_t list[PC_LIST + 8];
+    alignas(16) uint16_t delta[2][PC_DELTA];   // Bernoulli deltas of the sequences of the two contexts (TMA-loaded from the prepared buffer): kmer | ordinal << 12 | (add ? 0x8000 : 0)
     unsigned char m_sorted[PC_MAXS];   // slots sorted by job key (dense first, then window total)
     unsigned char m_lt[PC_MAXS], m_eq[PC_MAXS];   // per slot: slots with a smaller key / with the same key
     unsigned m_exh[2];             // ballots of "the list this position wants is exhausted"
-    int delta_free;                // iterations whose deltas the builders have consumed (single buffer, release / acquire)
-    uint32_t gtabs[STABS][RNG_BLOCK];
-    int scan[PC_HALF / 32 + 2];
-    int seg_off[PC_MAXB + 1];
     int nvalid;
-    int any_over;
+    int prep_bad;                  // the prepared buffer does not belong to this call (stamp mismatch): every item is deferred
     long long q_item[PC_QRING], q_seq[PC_QRING], q_c0[PC_QRING];   // dispatch ring written by the store thread: item, sequence, first chunk, length
     int q_len[PC_QRING];
+    int4 q_meta0[PC_QRING], q_meta1[PC_QRING];   // ... and the item's PrepMeta (n_delta, total0, base_total, flags | dtot[3], pad)
     int q_head;                    // entries published so far
     // launch-uniform slot tables (built once)
     VarDesc svars[PC_MAXS];
@@ -104,7 +131,7 @@ struct PcSmem {
     alignas(16) uint32_t sscratch[PC_NBUF * PC_SCRW];   // sparse jobs: one scratch per active fix warp (= per row buffer)
     // mbarriers.  Per row buffer: free (its last bulk copy has been read) -> built (builders, only when rebuilt)
     // -> full (fix warp: the row is the job's row) -> bulk copy -> free
-    alignas(8) unsigned long long ctx_full[2], ctx_empty[2], row_free[PC_NBUF], row_built[PC_NBUF], row_full[PC_NBUF], seq_full[2];
+    alignas(8) unsigned long long ctx_full[2], ctx_empty[2], row_free[PC_NBUF], row_built[PC_NBUF], row_full[PC_NBUF], seq_full[2], delta_full[2];
     int free_count[PC_NBUF];       // uses of each buffer whose bulk copy has been read.  The builders look ahead and skip the uses that
                                    // need no rebuild; an mbarrier parity wait alone can only tell adjacent phases apart
 };
@@ -170,41 +197,14 @@ __device__ __forceinline__ void st_release_smem(int* ptr, int v) {
 
 __device__ __forceinline__ void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// exclusive scan over the 512 producer threads (named barrier 1)
-__device__ __forceinline__ int pc_exscan(int v, int* scratch, int* total, int ptid) {
-    const int lane = ptid & 31, wid = ptid >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) scratch[wid] = inc;
-    bar_named(1, PC_HALF);
-    if (wid == 0) {
-        int w = lane < PC_HALF / 32 ? scratch[lane] : 0;
-        int winc = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        if (lane < PC_HALF / 32) scratch[lane] = winc - w;
-        if (lane == 31) scratch[PC_HALF / 32] = winc;
-    }
-    bar_named(1, PC_HALF);
-    *total = scratch[PC_HALF / 32];
-    return scratch[wid] + inc - v;
-}
-
 template <int OUT>
 __device__ __noinline__ void pc_producer(PcSmem& sm) {
     const ProfParams& p = sm.params;
     constexpr int K = PC_K;
     const int ptid = threadIdx.x - PC_HALF, lane = ptid & 31;
-    long long t_prev = p.phase_prof ? clock64() : 0;
+    long long t_prev = IDL_PROF(p) ? clock64() : 0;
     auto tick = [&](int id) {
-        if (p.phase_prof && ptid == 0) { const long long t = clock64(); atomicAdd(p.phase_prof + id, (unsigned long long)(t - t_prev)); t_prev = t; }
+        if (IDL_PROF(p) && ptid == 0) { const long long t = clock64(); atomicAdd(IDL_PROF(p) + id, (unsigned long long)(t - t_prev)); t_prev = t; }
     };
     // Items are dispatched by the store thread into a small ring (index, first chunk, length) and the
     // packed words of item A_{i+1} are TMA-loaded into the other half of sseq while A_i is prepared:
@@ -224,10 +224,13 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
     };
     long long cur_item, cur_seq, cur_c0;
     int cur_L;
+    int4 cur_m0, cur_m1;            // PrepMeta of the current item
     int n_loads0 = 0, n_loads1 = 0; // TMA loads issued into each half of sseq (mbarrier phase bookkeeping)
+    int n_dloads0 = 0, n_dloads1 = 0;   // ... and into each delta buffer
     int gj0 = 0;                    // jobs of the previous (not deferred) sequences: the consumers' buffer rotation
+    const unsigned char* prep_delta = reinterpret_cast<const unsigned char*>(p.prep) + prep_delta_off(p.n_items);
     while (ld_acquire_smem(&sm.q_head) < 1) __nanosleep(32);
-    cur_item = sm.q_item[0]; cur_seq = sm.q_seq[0]; cur_c0 = sm.q_c0[0]; cur_L = sm.q_len[0];
+    cur_item = sm.q_item[0]; cur_seq = sm.q_seq[0]; cur_c0 = sm.q_c0[0]; cur_L = sm.q_len[0]; cur_m0 = sm.q_meta0[0]; cur_m1 = sm.q_meta1[0];
     if (ptid == 0) issue_seq_load(0, cur_item, cur_c0, cur_L);
     int cur_phase = 0;
     if (loads_seq(cur_item, cur_L)) ++n_loads0;
@@ -238,6 +241,7 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
         const int qs = (it + 1) & (PC_QRING - 1);
         const long long nx_item = sm.q_item[qs], nx_seq = sm.q_seq[qs], nx_c0 = sm.q_c0[qs];
         const int nx_L = sm.q_len[qs];
+        const int4 nx_m0 = sm.q_meta0[qs], nx_m1 = sm.q_meta1[qs];
         if (ptid == 0) issue_seq_load(b ^ 1, nx_item, nx_c0, nx_L);            // A_{i+1}: lands during this iteration
         const int nx_phase = b ? n_loads0 : n_loads1;
         if (loads_seq(nx_item, nx_L)) { if (b) ++n_loads0; else ++n_loads1; }
@@ -252,8 +256,21 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
         const int L = cur_L;
         const uint32_t seq_id = (uint32_t)(p.seq_id0 + seq);
         const int nhalf = half_count(L);
-        const bool fits = nhalf <= 2 * SSEQ_CHUNKS && !sm.rcorr_bad;
-        if (ptid == 0) { cx.item = item; cx.defer = fits ? 0 : 1; cx.n_delta = 0; sm.nvalid = 0; sm.any_over = 0; }
+        const int n_delta = sm.n_bern > 0 ? cur_m0.x : 0;
+        const bool fits = nhalf <= 2 * SSEQ_CHUNKS && !sm.rcorr_bad && !sm.prep_bad && cur_m0.w == 0 && n_delta <= PC_DELTA;
+        // the delta list of this sequence: one TMA bulk load into the context's delta buffer.  Every consumer role is done with
+        // the buffer's previous occupant (ctx_empty above), and the copy lands while the producers prepare the rest.
+        const int dphase = b ? n_dloads1 : n_dloads0;
+        if (fits && n_delta > 0) {
+            if (ptid == 0) {
+                const uint32_t bytes = ((uint32_t)n_delta * 2u + 15u) & ~15u;
+                fence_proxy_async_smem();
+                mbar_expect_tx(&sm.delta_full[b], bytes);
+                bulk_load(sm.delta[b], prep_delta + (size_t)item * PREP_DELTA_BYTES, bytes, &sm.delta_full[b]);
+            }
+            if (b) ++n_dloads1; else ++n_dloads0;
+        }
+        if (ptid == 0) { cx.item = item; cx.defer = fits ? 0 : 1; cx.n_delta = n_delta; cx.delta_phase = dphase & 1; sm.nvalid = 0; }
         for (int i = ptid; i < PC_MAXS; i += PC_HALF) cx.dtot[i] = 0;
         uint32_t* cw = reinterpret_cast<uint32_t*>(cx.clean16);   // two uint16 counters per word (counts <= 20 480)
         if (fits) {
@@ -277,15 +294,15 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
             bar_named(1, PC_HALF);
             tick(2);
             if (ptid == 0) cx.base_total = PC_F * p.pseudocount + sm.nvalid;
-            // ---- Random_N slots: draws (thread <-> slot, philox call) in rounds of LIST_CAP draws ----
-            const int n_ent = sm.n_ent;   // <= LIST_CAP (host-checked)
+            // ---- Random_N slots: draws (thread <-> slot, philox call) ----
+            const int n_ent = sm.n_ent;   // <= PC_LIST (host-checked)
             {
                 constexpr int e0 = 0;
                 for (int q = ptid; q < p.S * 8; q += PC_HALF) {
                     const int c = q >> 3, j = q & 7;
                     const int nb = sm.kind_class[c] == 1 ? sm.nbp[c] : 0;
                     const int off = sm.rem_off[c] - e0;
-                    if (4 * j < nb && off >= 0 && off + nb <= LIST_CAP) {
+                    if (4 * j < nb && off >= 0 && off + nb <= PC_LIST) {
                         const U4 r = random_n_words(p.seed, seq_id, (uint32_t)sm.svars[c].rng_id, (uint32_t)j);
                         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -295,7 +312,7 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
                 }
                 bar_named(1, PC_HALF);
                 constexpr uint32_t KMASK = (1u << (2 * K)) - 1u, NMASKK = (1u << K) - 1u;
-                const int n_here = n_ent - e0 < LIST_CAP ? n_ent - e0 : LIST_CAP;
+                const int n_here = n_ent - e0 < PC_LIST ? n_ent - e0 : PC_LIST;
                 for (int q = ptid; q < n_here; q += PC_HALF) {
                     const uint32_t me = sm.list[q];
                     const int c = (int)(me >> 25);
@@ -340,66 +357,9 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
                 bar_named(1, PC_HALF);
             }
             tick(3);
-            // ---- Bernoulli slots jointly: thread <-> (slot, 64-base block) ----
-            const int nbs = sm.n_bern;
-            const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
-            if (nbs > 0 && nblocks > 0) {
-                if (nbs * nblocks > PC_HALF) { if (ptid == 0) cx.defer = 1; }
-                else {
-                    const int j = ptid / nblocks, blk = ptid - j * nblocks;
-                    const bool active = ptid < nbs * nblocks;
-                    const int c = active ? sm.bern_slot[j] : 0;
-                    const VarDesc vd = sm.svars[c];
-                    auto table = [&](int t) -> const uint32_t* { return t < STABS ? sm.gtabs[t] : p.gtab + t * RNG_BLOCK; };
-                    FastBlock f;
-                    f.cnt = 0; f.ok = true;
-                    if (active)
-                        f = fast_block(vd.kind, p.seed, seq_id, (uint32_t)vd.rng_id, blk, L, nmask, table(vd.tab1), vd.slope1,
-                                       table(vd.tab2), vd.slope2);
-                    if (active && !f.ok) sm.any_over = 1;
-                    int total;
-                    const int off = pc_exscan(f.cnt, sm.scan, &total, ptid);
-                    if (sm.any_over || total > LIST_CAP) { if (ptid == 0) cx.defer = 1; }
-                    else {
-                        if (active && blk == 0) sm.seg_off[j] = off;
-                        if (ptid == 0) sm.seg_off[nbs] = total;
-                        if (active && f.cnt) fast_block_write(f, blk, codes, sm.list + off);
-                        while (ld_acquire_smem(&sm.delta_free) < it) __nanosleep(32);   // the builders have consumed the previous deltas
-                        bar_named(1, PC_HALF);
-                        for (int i0 = 0; i0 < total; i0 += PC_HALF) {   // uniform trip count: warp collectives inside
-                            const int i = i0 + ptid;
-                            int jj = 0, so = 0, cnt = 0;
-                            if (i < total) {
-                                while (i >= sm.seg_off[jj + 1]) ++jj;
-                                so = sm.seg_off[jj];
-                                // pass 1: how many +-1 deltas does this edit produce
-                                apply_entry<K>(codes, nmask, L, sm.list + so, sm.seg_off[jj + 1] - so, i - so, [&](uint32_t, int) { ++cnt; });
-                            }
-                            // one reservation per warp in the delta list
-                            int inc = cnt;
-#pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) {
-                                const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                                if (lane >= o) inc += t;
-                            }
-                            const int wtot = __shfl_sync(0xffffffffu, inc, 31);
-                            int wbase = 0;
-                            if (lane == 31 && wtot) wbase = atomicAdd(&cx.n_delta, wtot);
-                            wbase = __shfl_sync(0xffffffffu, wbase, 31);
-                            int slot = wbase + inc - cnt;
-                            if (cnt && wbase + wtot <= PC_DELTA) {
-                                const uint32_t tag = (uint32_t)jj << 12;
-                                const int d = apply_entry<K>(codes, nmask, L, sm.list + so, sm.seg_off[jj + 1] - so, i - so, [&](uint32_t kmer, int dd) {
-                                    sm.delta[slot++] = (uint16_t)(kmer | tag | (dd > 0 ? 0x8000u : 0u));
-                                });
-                                if (d) atomicAdd(&cx.dtot[sm.bern_slot[jj]], d);
-                            }
-                        }
-                    }
-                }
-            }
+            // ---- Bernoulli slots: their window totals come from the prepare pass ----
+            if (ptid < sm.n_bern) cx.dtot[sm.bern_slot[ptid]] = ptid == 0 ? cur_m1.x : (ptid == 1 ? cur_m1.y : cur_m1.z);
             bar_named(1, PC_HALF);
-            if (ptid == 0 && cx.n_delta > PC_DELTA) cx.defer = 1;
         }
         if (ptid == 0 && cx.defer) { atomicOr(p.status + item, 2); atomicAdd(p.work_counter + 1, 1ull); }
         // ---- per-slot totals, output rows and the job order (dense slots first, then by window total) ----
@@ -446,7 +406,7 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
         }
         const int O = S - M, a = gj0 % PC_NBUF;
         // (the first round of buffers is all main: the main row is the cheapest to have ready at the start of a sequence)
-        const int noth = (p.dbg & 64) ? 0 : PC_NOTH;
+        const int noth = (IDL_DBG(p) & 64) ? 0 : PC_NOTH;
         auto lane_type = [&](int q) { return (a + q) % PC_NBUF >= PC_NBUF - noth; };
         auto other_type = [&](int q) { return q >= PC_NBUF && lane_type(q); };
         auto lanes_before = [&](int q) {
@@ -487,7 +447,7 @@ __device__ __noinline__ void pc_producer(PcSmem& sm) {
             cx.job_dst[j] = (unsigned long long)cx.grow[s] | (unsigned long long)nb;
         }
         if (!cx.defer) gj0 += S;
-        cur_item = nx_item; cur_seq = nx_seq; cur_c0 = nx_c0; cur_L = nx_L; cur_phase = nx_phase;
+        cur_item = nx_item; cur_seq = nx_seq; cur_c0 = nx_c0; cur_L = nx_L; cur_phase = nx_phase; cur_m0 = nx_m0; cur_m1 = nx_m1;
         tick(4);
         bar_named(1, PC_HALF);
         if (ptid == 0) mbar_arrive(&sm.ctx_full[b]);   // release: hand the context over to the consumers
@@ -562,7 +522,7 @@ __device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
     const float magic = 8388608.0f - (float)p.pseudocount;
     int gj0 = 0;                                     // jobs of the previous sequences (CTA lifetime)
     PcClock clk;
-    clk.start(tid == 0 && (p.dbg & 16) ? p.phase_prof : nullptr);
+    clk.start(tid == 0 && (IDL_DBG(p) & 16) ? IDL_PROF(p) : nullptr);
     for (int it = 0;; ++it) {
         const int b = it & 1;
         clk.tick(13);
@@ -571,7 +531,6 @@ __device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
         PcCtx& cx = sm.ctx[b];
         const long long item = cx.item;
         if (item < 0) return;
-        if (cx.defer && tid == 0) st_release_smem(&sm.delta_free, it + 1);
         if (!cx.defer) {
             const int S = p.S;
             uint2 ck[GPT];
@@ -581,18 +540,20 @@ __device__ __forceinline__ void pc_builder(PcSmem& sm, const ProfParams& p) {
                 ck[j] = cx.clean16[tid + j * NB];
                 cvt_granule(ck[j], magic, c01[j], c23[j]);
             }
-            // all Bernoulli deltas of the sequence into the per-ordinal scratch arrays in ONE scan; the producers may
-            // then write the next sequence's deltas
+            // all Bernoulli deltas of the sequence (TMA-loaded from the prepared buffer) into the per-ordinal scratch arrays in ONE scan
             const int n_delta = cx.n_delta;
             if (cx.n_dense > 0) {
                 bar_named(2, NB);                    // every builder is done with the previous sequence's dense rows (own-bin resets)
-                for (int r = tid; r < n_delta; r += NB) {
-                    const uint32_t e = sm.delta[r];
-                    upd16(sm.dscratch[(e >> 12) & 7u], e & 0xFFFu, (e & 0x8000u) ? 1 : -1);
+                if (n_delta > 0) {
+                    mbar_wait(&sm.delta_full[b], (uint32_t)cx.delta_phase);
+                    const uint16_t* dl = sm.delta[b];
+                    for (int r = tid; r < n_delta; r += NB) {
+                        const uint32_t e = dl[r];
+                        upd16(sm.dscratch[(e >> 12) & 3u], e & 0xFFFu, (e & 0x8000u) ? 1 : -1);
+                    }
                 }
                 bar_named(2, NB);
             }
-            if (tid == 0) st_release_smem(&sm.delta_free, it + 1);
             unsigned key_cur = 0u;                   // window total (float bits) the register row val[] holds; 0: none
             float4 val[GPT];
 #pragma unroll
@@ -644,36 +605,41 @@ __device__ __forceinline__ void pc_store(PcSmem& sm, const ProfParams& p) {
     // ---- dispatcher.  The atomic and the dependent loads of (sequence, length, first chunk) are two global
     // round trips; they are issued one iteration before their results are needed, and a stall here is absorbed
     // by the rows the other roles have already finished.
-    auto load_info = [&](long long item, long long& seq, long long& c0, int& L) {
+    const int4* prep_meta = reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(p.prep) + prep_meta_off());
+    auto load_info = [&](long long item, long long& seq, long long& c0, int& L, int4& m0, int4& m1) {
         seq = item; c0 = 0; L = 0;
+        m0 = make_int4(0, 0, 0, 1); m1 = make_int4(0, 0, 0, 0);
         if (item < p.n_items) {
             if (p.sidx) seq = (long long)p.sidx[item];
             L = p.len[seq];
             c0 = p.chunk_off[seq];
+            m0 = prep_meta[item * 2]; m1 = prep_meta[item * 2 + 1];
         }
     };
-    auto publish = [&](int idx, long long item, long long seq, long long c0, int L) {
+    auto publish = [&](int idx, long long item, long long seq, long long c0, int L, int4 m0, int4 m1) {
         const int qs = idx & (PC_QRING - 1);
-        sm.q_item[qs] = item; sm.q_seq[qs] = seq; sm.q_c0[qs] = c0; sm.q_len[qs] = L;
+        sm.q_item[qs] = item; sm.q_seq[qs] = seq; sm.q_c0[qs] = c0; sm.q_len[qs] = L; sm.q_meta0[qs] = m0; sm.q_meta1[qs] = m1;
         st_release_smem(&sm.q_head, idx + 1);
     };
     {
         long long it4[4], sq4[4], c4[4];
         int l4[4];
+        int4 ma4[4], mb4[4];
         for (int i = 0; i < 4; ++i) it4[i] = (long long)atomicAdd(p.work_counter, 1ull);
-        for (int i = 0; i < 4; ++i) load_info(it4[i], sq4[i], c4[i], l4[i]);
-        for (int i = 0; i < 4; ++i) publish(i, it4[i], sq4[i], c4[i], l4[i]);
+        for (int i = 0; i < 4; ++i) load_info(it4[i], sq4[i], c4[i], l4[i], ma4[i], mb4[i]);
+        for (int i = 0; i < 4; ++i) publish(i, it4[i], sq4[i], c4[i], l4[i], ma4[i], mb4[i]);
     }
     long long a_item = (long long)atomicAdd(p.work_counter, 1ull);   // index 4
     long long b_item = 0, b_seq = 0, b_c0 = 0;
     int b_L = 0;
+    int4 b_m0 = make_int4(0, 0, 0, 1), b_m1 = make_int4(0, 0, 0, 0);
     PcClock clk;
-    clk.start((p.dbg & 48) ? p.phase_prof : nullptr);
+    clk.start((IDL_DBG(p) & 48) ? IDL_PROF(p) : nullptr);
     for (int it = 0;; ++it) {
         const int b = it & 1;
-        if (it >= 1) publish(it + 3, b_item, b_seq, b_c0, b_L);      // loaded during the previous iteration
+        if (it >= 1) publish(it + 3, b_item, b_seq, b_c0, b_L, b_m0, b_m1);      // loaded during the previous iteration
         b_item = a_item;
-        load_info(b_item, b_seq, b_c0, b_L);                          // index it + 4
+        load_info(b_item, b_seq, b_c0, b_L, b_m0, b_m1);              // index it + 4
         a_item = (long long)atomicAdd(p.work_counter, 1ull);          // index it + 5
         clk.tick(6);
         mbar_wait(&sm.ctx_full[b], (it >> 1) & 1);
@@ -692,7 +658,7 @@ __device__ __forceinline__ void pc_store(PcSmem& sm, const ProfParams& p) {
                 mbar_wait(&sm.row_full[buf], (gj / PC_NBUF) & 1);
                 clk.tick(1);
                 unsigned char* dst = reinterpret_cast<unsigned char*>(p.out) + (jd & ~15ull);
-                if (p.dbg & 4) bulk_store_hint(dst, sm.rowbuf[buf], PC_F * 4, pol_ef);
+                if (IDL_DBG(p) & 4) bulk_store_hint(dst, sm.rowbuf[buf], PC_F * 4, pol_ef);
                 else bulk_store(dst, sm.rowbuf[buf], PC_F * 4);
                 bulk_commit();
                 if (gj >= PC_INFL) {
@@ -736,7 +702,7 @@ __device__ __forceinline__ void pc_fix(PcSmem& sm, const ProfParams& p) {
 #pragma unroll
     for (int u = 0; u < RPL; ++u) { km_prev[u] = 0xFFFFu; vt_prev[u] = 0.f; }
     PcClock clk;
-    clk.start(ftid == 0 && (p.dbg & 16) ? p.phase_prof : nullptr);
+    clk.start(ftid == 0 && (IDL_DBG(p) & 16) ? IDL_PROF(p) : nullptr);
     for (int it = 0;; ++it) {
         const int b = it & 1;
         clk.tick(11);
@@ -825,16 +791,20 @@ __device__ __forceinline__ void pc_fix(PcSmem& sm, const ProfParams& p) {
 }
 
 template <int OUT>
-__global__ void __launch_bounds__(PC_NT, 1) profiles_pc_kernel(const ProfParams p) {
+__global__ void __launch_bounds__(PC_NT, 1) profiles_pc_kernel(const ProfParams p, const __grid_constant__ Plan plan) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PcSmem& sm = *reinterpret_cast<PcSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    if (tid == 0) { sm.params = p; sm.rcorr_bad = 0; sm.delta_free = 0; }
+    if (tid == 0) {
+        sm.params = p; sm.rcorr_bad = 0;
+        // the prepared buffer must have been written for exactly this call's items / variants / seed
+        const PrepHeader* h = reinterpret_cast<const PrepHeader*>(p.prep);
+        sm.prep_bad = (h->stamp != p.prep_stamp || h->n_items != p.n_items) ? 1 : 0;
+    }
     __syncthreads();
-    // launch-uniform slot tables
-    for (int i = tid; i < p.n_vars; i += PC_NT) sm.svars[i] = p.vars[i];
-    for (int i = tid; i < p.S; i += PC_NT) sm.sout_off[i] = p.out_off[i];
-    for (int i = tid; i < STABS * RNG_BLOCK; i += PC_NT) (&sm.gtabs[0][0])[i] = i < p.n_tabs * RNG_BLOCK ? p.gtab[i] : 0u;
+    // launch-uniform slot tables (the host only takes this kernel with an inline plan: n_vars, S <= PC_MAXS)
+    for (int i = tid; i < p.n_vars; i += PC_NT) sm.svars[i] = plan.vars[i];
+    for (int i = tid; i < p.S; i += PC_NT) sm.sout_off[i] = plan.out_off[i];
     if (OUT == IDL_OUT_STD_F32)
         for (int i = tid; i < PC_F; i += PC_NT) {
             const float sc = p.scale[i];
@@ -862,7 +832,7 @@ __global__ void __launch_bounds__(PC_NT, 1) profiles_pc_kernel(const ProfParams 
         sm.n_ent = ent;
         sm.n_bern = nb;
         sm.q_head = 0;
-        for (int i = 0; i < 2; ++i) mbar_init(&sm.seq_full[i], 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.seq_full[i], 1); mbar_init(&sm.delta_full[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&sm.ctx_full[i], 1); mbar_init(&sm.ctx_empty[i], PC_NBLD + PC_NFIX + 1); }
         for (int i = 0; i < PC_NBUF; ++i) { mbar_init(&sm.row_free[i], 1); mbar_init(&sm.row_built[i], PC_NBLD); mbar_init(&sm.row_full[i], 1); sm.free_count[i] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

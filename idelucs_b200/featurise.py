@@ -94,11 +94,63 @@ def pack_edit_lists(explicit, n_seqs, device):
     return d_off, d_ent
 
 
+class Prepared(object):
+    """Result of ``prepare``: the device buffer the k = 6 fast path reads its Bernoulli deltas from, and the scaler
+    partials of slot 0 computed on the way."""
+
+    def __init__(self, buf, parts, part_n, key):
+        self.buf, self.parts, self.part_n, self.key = buf, parts, part_n, key
+
+    def scaler(self, group=None):
+        parts, part_n = self.parts, self.part_n
+        if group is not None:
+            parts, part_n = gather_partials(parts, part_n, group)
+        return Scaler.from_partials(parts, part_n)
+
+
+def can_prepare(seqset, k, variants, n_items=None):
+    """whether the two-call whole-schedule path (idl_profiles_prepare / idl_profiles_prepared) applies"""
+    n_items = seqset.n if n_items is None else n_items
+    bern = sum(1 for v in variants if v.kind in (KIND_TRANSITION, KIND_TRANSVERSION, KIND_BOTH))
+    rates = set([v.p1 for v in variants if v.kind in (KIND_TRANSITION, KIND_BOTH)] + [v.p2 for v in variants if v.kind in (KIND_TRANSVERSION, KIND_BOTH)])
+    v0 = variants[0]
+    ok0 = v0.kind in (KIND_CLEAN, KIND_TRANSITION, KIND_TRANSVERSION, KIND_BOTH) or (v0.kind == KIND_RANDOM_N and v0.n_bp <= 0)
+    return (k == 6 and n_items >= 512 and len(variants) <= 64 and bern <= 3 and len(rates) <= 4 and ok0
+            and not any(v.kind == KIND_EXPLICIT for v in variants))
+
+
+def prepare(seqset, k, variants, seed=0, seq_id0=0, pseudocount=1, want_stats=True):
+    """idl_profiles_prepare over the whole SeqSet: ONE pass that generates the Bernoulli mimics' histogram deltas for the
+    profile pass (``profiles(..., prepared=...)``) and the scaler statistics of variants[0]."""
+    lib = _lib.load()
+    device = seqset.device
+    F = 4 ** k
+    n = seqset.n
+    nbytes = lib.idl_prepare_bytes(n)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    max_parts = 2048
+    parts = torch.empty((max_parts, 2, F), dtype=torch.float64, device=device) if want_stats else None
+    part_n = torch.zeros((max_parts,), dtype=torch.float64, device=device) if want_stats else None
+    n_parts = ctypes.c_int(0)
+    status = torch.zeros((max(n, 1),), dtype=torch.int32, device=device)
+    varr = _variant_array(variants)
+    with torch.cuda.device(device):
+        ws = _workspace(device, lib.idl_profiles_workspace_bytes(), "prof")
+        _lib.check(lib.idl_profiles_prepare(_lib.ptr(seqset.codes), _lib.ptr(seqset.nmask), _lib.ptr(seqset.chunk_off), _lib.ptr(seqset.len),
+                                            seqset.n, None, n, int(seq_id0), k, varr, len(variants), ctypes.c_uint64(seed & (2 ** 64 - 1)),
+                                            int(pseudocount), _lib.ptr(buf), nbytes, _lib.ptr(parts), _lib.ptr(part_n), max_parts,
+                                            ctypes.byref(n_parts), _lib.ptr(status), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    if want_stats:
+        parts, part_n = parts[: n_parts.value], part_n[: n_parts.value]
+    return Prepared(buf, parts, part_n, (id(seqset), k, seed, seq_id0, pseudocount, len(variants)))
+
+
 def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_off=None, out_stride=None,
              mean=None, scale=None, sidx=None, sel=None, S=None, edit_lists=None, seq_id0=0, pseudocount=None,
-             accumulate=False, status=None):
+             accumulate=False, status=None, prepared=None):
     """Run K2+K3.  Default output: tensor [S, n_items, 4^k] (variant-major) of the out_kind's
-    dtype.  See include/idelucs_b200.h::idl_profiles for the argument meaning."""
+    dtype.  See include/idelucs_b200.h::idl_profiles for the argument meaning.  ``prepared`` (from ``prepare`` with the
+    same SeqSet / variants / seed / seq_id0) routes float32 outputs through idl_profiles_prepared (k = 6 fast path)."""
     lib = _lib.load()
     device = seqset.device
     F = 4 ** k
@@ -114,13 +166,21 @@ def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_o
         out_stride = F
     assert out.dtype == _OUT_DTYPE[out_kind] and out.is_contiguous()
     varr = _variant_array(variants)
-    if status is None and sel is None and k == 6 and n_items >= 512 and out_kind in (OUT_FREQ_F32, OUT_STD_F32):
-        # lets the library use its producer/consumer kernel (items it defers are flagged here and redone)
-        status = torch.zeros(n_items, dtype=torch.int32, device=device)
     offs = (ctypes.c_int64 * S)(*[int(o) for o in out_off])
     d_eoff, d_ent = (None, None) if edit_lists is None else edit_lists
     with torch.cuda.device(device):
         ws = _workspace(device, lib.idl_profiles_workspace_bytes(), "prof")
+        if prepared is not None:
+            assert sidx is None and sel is None and edit_lists is None and out_kind in (OUT_FREQ_F32, OUT_STD_F32)
+            assert prepared.key == (id(seqset), k, seed, seq_id0, pseudocount, nv), "prepared for a different call"
+            if status is None:
+                status = torch.zeros(n_items, dtype=torch.int32, device=device)
+            _lib.check(lib.idl_profiles_prepared(
+                _lib.ptr(seqset.codes), _lib.ptr(seqset.nmask), _lib.ptr(seqset.chunk_off), _lib.ptr(seqset.len), seqset.n,
+                None, n_items, int(seq_id0), k, varr, nv, ctypes.c_uint64(seed & (2 ** 64 - 1)), out_kind, _lib.ptr(out), offs,
+                int(out_stride), int(pseudocount), _lib.ptr(mean), _lib.ptr(scale), _lib.ptr(status), _lib.ptr(prepared.buf),
+                prepared.buf.numel(), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+            return out
         _lib.check(lib.idl_profiles(
             _lib.ptr(seqset.codes), _lib.ptr(seqset.nmask), _lib.ptr(seqset.chunk_off), _lib.ptr(seqset.len), seqset.n,
             _lib.ptr(sidx), n_items, int(seq_id0), k, varr, nv, _lib.ptr(sel), S, ctypes.c_uint64(seed & (2 ** 64 - 1)),
@@ -130,10 +190,29 @@ def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_o
     return out
 
 
-def profile_stats(seqset, k, variant, seed=0, seq_id0=0, edit_lists=None, group=None, pseudocount=1):
+def schedule_profiles(seqset, k, variants, out_kind=OUT_STD_F32, seed=0, seq_id0=0, group=None, out=None, out_off=None,
+                      out_stride=None, fast=True):
+    """The AugmentFasta computation on the device (idelucs/utils.py:330-366): statistics of variants[0]'s float32 frequencies
+    -> every variant's profile (standardised with them when out_kind is OUT_STD_F32).  Returns (profiles, Scaler).
+    fast=False keeps everything on the generic kernels (any k; the parity tests compare the two)."""
+    if fast and can_prepare(seqset, k, variants):
+        prep = prepare(seqset, k, variants, seed=seed, seq_id0=seq_id0)
+        sc = prep.scaler(group)
+        x = profiles(seqset, k, variants, out_kind=out_kind, seed=seed, seq_id0=seq_id0, mean=sc.mean32, scale=sc.scale32,
+                     out=out, out_off=out_off, out_stride=out_stride, prepared=prep)
+        return x, sc
+    sc = profile_stats(seqset, k, variants[0], seed=seed, seq_id0=seq_id0, group=group, fast=False)
+    x = profiles(seqset, k, variants, out_kind=out_kind, seed=seed, seq_id0=seq_id0, mean=sc.mean32, scale=sc.scale32,
+                 out=out, out_off=out_off, out_stride=out_stride)
+    return x, sc
+
+
+def profile_stats(seqset, k, variant, seed=0, seq_id0=0, edit_lists=None, group=None, pseudocount=1, fast=True):
     """Scaler statistics of one variant's float32 frequency profiles over the whole SeqSet, computed
-    inside the featurisation kernel (no [N, 4^k] matrix is written or re-read).  Equivalent to
+    inside the featurisation kernels (no [N, 4^k] matrix is written or re-read).  Equivalent to
     ``Scaler.fit(profiles(seqset, k, [variant], OUT_FREQ_F32)[0], group)``."""
+    if fast and edit_lists is None and can_prepare(seqset, k, [variant]):
+        return prepare(seqset, k, [variant], seed=seed, seq_id0=seq_id0, pseudocount=pseudocount).scaler(group)
     lib = _lib.load()
     device = seqset.device
     F = 4 ** k
@@ -143,14 +222,12 @@ def profile_stats(seqset, k, variant, seed=0, seq_id0=0, edit_lists=None, group=
     varr = _variant_array([variant])
     n_parts = ctypes.c_int(0)
     d_eoff, d_ent = (None, None) if edit_lists is None else edit_lists
-    # bit 1 = "left to the generic kernel" (set and cleared inside the call)
-    status = torch.zeros((max(seqset.n, 1),), dtype=torch.int32, device=device)
     with torch.cuda.device(device):
         ws = _workspace(device, lib.idl_profiles_workspace_bytes(), "prof")
         _lib.check(lib.idl_profile_stats(_lib.ptr(seqset.codes), _lib.ptr(seqset.nmask), _lib.ptr(seqset.chunk_off), _lib.ptr(seqset.len),
                                          seqset.n, None, seqset.n, int(seq_id0), k, varr, ctypes.c_uint64(seed & (2 ** 64 - 1)),
                                          _lib.ptr(d_eoff), _lib.ptr(d_ent), int(pseudocount), _lib.ptr(parts), _lib.ptr(part_n),
-                                         max_parts, ctypes.byref(n_parts), _lib.ptr(status), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+                                         max_parts, ctypes.byref(n_parts), None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     parts, part_n = parts[: n_parts.value].contiguous(), part_n[: n_parts.value].contiguous()
     if seqset.n == 0:
         parts, part_n = torch.zeros((1, 2, F), dtype=torch.float64, device=device), torch.zeros((1,), dtype=torch.float64, device=device)

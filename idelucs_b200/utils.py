@@ -176,8 +176,9 @@ def augment_device(ss, n_mimics, k=6, seed=None, group=None, seq_id0=0, reduce=F
         sc = ft.Scaler.fit(x32[0], group=group)
         V, n, R = x32.shape
         return sc.transform32(x32.reshape(V * n, R)).reshape(V, n, R), sc, seed
-    sc = ft.profile_stats(ss, k, variants[0], seed=seed, seq_id0=seq_id0, group=group)   # t_norm statistics, never materialised
-    out = ft.profiles(ss, k, variants, out_kind=ft.OUT_STD_F32, seed=seed, mean=sc.mean32, scale=sc.scale32, seq_id0=seq_id0)
+    # t_norm statistics (never materialised) and all standardised slots; k = 6: the prepare pass generates the Bernoulli
+    # mimics once for both
+    out, sc = ft.schedule_profiles(ss, k, variants, out_kind=ft.OUT_STD_F32, seed=seed, seq_id0=seq_id0, group=group)
     return out, sc, seed
 
 

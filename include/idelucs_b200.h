@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define IDL_ABI_VERSION 1
+#define IDL_ABI_VERSION 2
 
 enum {
     IDL_OK = 0,
@@ -72,6 +72,9 @@ typedef struct idl_variant {
 
 int idl_abi_version(void);
 const char* idl_last_error(void);
+/* number of CUDA kernels this library has launched in this process so far (bench.py reports the difference over its timed
+ * region as gpu_launches; kernels replayed from a captured CUDA graph are not counted) */
+long long idl_launch_count(void);
 
 /* T[g-1] = floor((1-(1-p)^g) * 2^32), g = 1..64: the geometric gap table the rng mode
  * uses for an iid Bernoulli(p) process (host function; exported for the parity tests). */
@@ -104,10 +107,12 @@ size_t idl_profiles_workspace_bytes(void);
  * val 0..3 = set A/C/G/T, 4 = set N; position-sorted and unique per list), n_seqs_total =
  * number of sequences the CSR is indexed over.  d_mean/d_scale: float32[4^k] for
  * IDL_OUT_STD_F32.  accumulate != 0 (COUNTS only) adds into d_out like kmers.pyx does.
- * d_status int32[n_items], zero on entry (optional): bit 0 set when an item's edit list overflowed the
- * on-chip list (the item's outputs for that variant are then unmutated).  Bit 1 is used inside the call (k = 6 float
- * outputs: items the producer/consumer kernel hands to the generic kernel) and is clear again when the work is done;
- * without d_status only the generic kernel runs. */
+ * d_status int32[n_items] (optional, zero on entry): scratch flags of the fast kernels (bit 1 marks items handed to the generic
+ * kernel inside a call; clear again when the work is done).  No rate or length makes a mutation get dropped: edit lists that
+ * do not fit on chip are generated in smaller tiles.
+ * Nothing is cached between calls: descriptors, offsets and gap tables of calls with <= 64 variants / slots and <= 4 distinct
+ * rates travel as kernel parameters (such calls enqueue no host->device copy and can be captured in a CUDA graph); bigger
+ * plans are copied into d_workspace on `stream`. */
 int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
                  const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
                  int64_t seq_id0, int k, const idl_variant* variants, int n_variants, const int32_t* d_sel,
@@ -122,15 +127,38 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
  * (count, mean, M2) part; feed d_partials / d_part_n / *n_parts to idl_scaler_finalize (after
  * all-gathering the parts of every rank when sharded).  d_partials double[max_parts][2][4^k],
  * d_part_n double[max_parts]; max_parts >= 8 x number of SMs.  Rows are assigned to CTAs statically, so the sums are
- * run-to-run identical.  d_status int32[n_items], zero on entry (optional): with it, k = 6 and a clean / transition /
- * transversion / combined variant the pipelined kernel (csrc/stats_fast.cuh) takes the call; it marks the few items it
- * cannot take (bit 1: longer than 16 320 bases, a 64-base block with more than 6 hits of one mutation stream), the
- * generic kernel folds those into further parts and clears the bit again.  Bit 0 as in idl_profiles. */
+ * run-to-run identical.  Any k <= 6 and any variant kind (generic kernel); for the k = 6 schedule use idl_profiles_prepare,
+ * which shares the mutation work with the profile pass. */
 int idl_profile_stats(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off, const int32_t* d_len,
                       int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items, int64_t seq_id0, int k,
                       const idl_variant* variant, uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits,
                       int pseudocount, double* d_partials, double* d_part_n, int max_parts, int* n_parts,
                       int32_t* d_status, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Whole-schedule featurisation in two calls (k = 6): AugmentFasta (idelucs/utils.py:321-368) needs the StandardScaler
+ * statistics of pass 0 (t_norm) before it can write any standardised row, so every sequence is visited twice.
+ * idl_profiles_prepare visits it ONCE for everything the Bernoulli mimics need: it writes, into the caller-owned buffer
+ * d_prep (idl_prepare_bytes(n_items) bytes, 16-byte aligned), the +-1 histogram deltas of every transition / transversion /
+ * combined variant (at most 3) and the uint16 histogram + window total of variants[0] (clean or one of those), and — when
+ * d_partials is given — the (count, mean, M2) parts of variants[0]'s float32 frequencies exactly like idl_profile_stats
+ * (d_partials double[max_parts][2][4096], d_part_n double[max_parts], max_parts >= 8 x SMs, *n_parts on return).
+ * idl_profiles_prepared is idl_profiles (float32 outputs, no selection, no explicit lists) for the SAME sequences, items,
+ * variants, seed and pseudocount: its k = 6 producer/consumer kernel loads the prepared deltas instead of generating the
+ * mutations again.  The buffer carries a stamp of what it was prepared for; on a mismatch (or for the few items the prepare
+ * pass flags: longer than 20 480 bases, on-chip list overflows) the generic kernel computes the rows — results are identical
+ * either way.  d_status int32[n_items] must be zero on entry of each call and is zero again afterwards. */
+size_t idl_prepare_bytes(int64_t n_items);
+int idl_profiles_prepare(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off, const int32_t* d_len,
+                         int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items, int64_t seq_id0, int k,
+                         const idl_variant* variants, int n_variants, uint64_t seed, int pseudocount, void* d_prep, size_t prep_bytes,
+                         double* d_partials, double* d_part_n, int max_parts, int* n_parts, int32_t* d_status, void* d_workspace,
+                         size_t workspace_bytes, void* stream);
+int idl_profiles_prepared(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
+                          const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
+                          int64_t seq_id0, int k, const idl_variant* variants, int n_variants, uint64_t seed, int out_kind,
+                          void* d_out, const int64_t* out_off, int64_t out_stride, int pseudocount,
+                          const float* d_mean, const float* d_scale, int32_t* d_status, const void* d_prep, size_t prep_bytes,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Convenience form of the above for kmer_counts (idelucs/kmers.pyx:2-50): raw int32 counts
  * of every sequence into d_counts[n, 4^k] (accumulating when accumulate != 0). */

@@ -147,25 +147,25 @@ int emul_variant(const uint32_t* codes, const uint32_t* nmask, int L, int K, uns
     return 0;
 }
 
-// fast block generator vs the generic one: returns number of blocks where they disagree
-// (blocks where the fast path reports overflow are counted in *n_overflow and skipped)
-int emul_fast_vs_slow(const uint32_t* codes, const uint32_t* nmask, int L, unsigned long long seed, unsigned seq_id,
-                      unsigned rng_id, int kind, double p1, double p2, int* n_overflow) {
+// mask block generator vs the stream-walking one (block_edits): returns the number of blocks where they disagree
+int emul_masks_vs_slow(const uint32_t* codes, const uint32_t* nmask, int L, unsigned long long seed, unsigned seq_id,
+                       unsigned rng_id, int kind, double p1, double p2, int* max_per_block) {
     uint32_t T1[RNG_BLOCK], T2[RNG_BLOCK];
     geometric_table(p1, T1);
     geometric_table(p2, T2);
     int bad = 0;
-    *n_overflow = 0;
+    *max_per_block = 0;
     const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
     for (int b = 0; b < nblocks; ++b) {
         std::vector<uint32_t> slow;
         block_edits(kind, seed, seq_id, rng_id, b, L, codes, nmask, T1, gap_slope(p1), T2, gap_slope(p2),
                     [&](uint32_t e) { slow.push_back(e); });
-        const FastBlock f = fast_block(kind, seed, seq_id, rng_id, b, L, nmask, T1, gap_slope(p1), T2, gap_slope(p2));
-        if (!f.ok) { ++*n_overflow; continue; }
-        uint32_t out[2 * FAST_CAP];
-        fast_block_write(f, b, codes, out);
-        if (f.cnt != (int)slow.size() || !std::equal(slow.begin(), slow.end(), out)) ++bad;
+        const BlockMasks m = block_masks(kind, seed, seq_id, rng_id, b, L, nmask, T1, gap_slope(p1), T2, gap_slope(p2));
+        uint32_t out[RNG_BLOCK];
+        const int cnt = block_masks_count(m);
+        block_masks_write(m, b, codes, out);
+        if (cnt > *max_per_block) *max_per_block = cnt;
+        if (cnt != (int)slow.size() || !std::equal(slow.begin(), slow.end(), out)) ++bad;
     }
     return bad;
 }
@@ -189,63 +189,3 @@ long long emul_div_check(const float* a, const float* b, long long n) {
 }
 
 }  // extern "C"
-
-// position-sorted edit list seen from block b through per-block slots (the statistics kernel's layout,
-// csrc/stats_fast.cuh): previous block's slot, this block's slot, first entry of the next block
-struct SlotView {
-    const uint32_t* a; int na;
-    const uint32_t* b; int nb;
-    const uint32_t* c;
-    uint32_t operator[](int j) const { return j < na ? a[j] : (j < na + nb ? b[j - na] : c[0]); }
-};
-
-template <int K>
-static int slots_vs_flat_k(const uint32_t* codes, const uint32_t* nmask, int L, unsigned long long seed, unsigned seq_id,
-                           unsigned rng_id, int kind, double p1, double p2, int* n_overflow) {
-    constexpr int SLOT = 2 * FAST_CAP;
-    uint32_t T1[RNG_BLOCK], T2[RNG_BLOCK];
-    geometric_table(p1, T1);
-    geometric_table(p2, T2);
-    const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
-    std::vector<uint32_t> slots((size_t)(nblocks + 2) * SLOT, 0u), flat;
-    std::vector<int> cnt(nblocks + 2, 0);
-    *n_overflow = 0;
-    for (int b = 0; b < nblocks; ++b) {
-        const FastBlock f = fast_block(kind, seed, seq_id, rng_id, b, L, nmask, T1, gap_slope(p1), T2, gap_slope(p2));
-        if (!f.ok) { ++*n_overflow; return 0; }   // the kernel defers such an item
-        if (f.cnt) fast_block_write(f, b, codes, slots.data() + (size_t)b * SLOT);
-        cnt[b] = f.cnt;
-        for (int i = 0; i < f.cnt; ++i) flat.push_back(slots[(size_t)b * SLOT + i]);
-    }
-    std::vector<int> c_flat(1 << (2 * K), 0), c_view(1 << (2 * K), 0);
-    int d_flat = 0, d_view = 0;
-    for (int i = 0; i < (int)flat.size(); ++i)
-        d_flat += apply_entry<K>(codes, nmask, L, flat.data(), (int)flat.size(), i, [&](uint32_t kmer, int dd) { c_flat[kmer] += dd; });
-    for (int b = 0; b < nblocks; ++b) {
-        SlotView v;
-        v.na = b > 0 ? cnt[b - 1] : 0;
-        v.a = slots.data() + (size_t)(b > 0 ? b - 1 : 0) * SLOT;
-        v.nb = cnt[b];
-        v.b = slots.data() + (size_t)b * SLOT;
-        v.c = slots.data() + (size_t)(b + 1) * SLOT;
-        const int nn = v.na + v.nb + ((b + 1 < nblocks && cnt[b + 1] > 0) ? 1 : 0);
-        for (int i = 0; i < cnt[b]; ++i)
-            d_view += apply_entry<K>(codes, nmask, L, v, nn, v.na + i, [&](uint32_t kmer, int dd) { c_view[kmer] += dd; });
-    }
-    int bad = d_flat != d_view ? 1 : 0;
-    for (size_t i = 0; i < c_flat.size(); ++i) bad += c_flat[i] != c_view[i] ? 1 : 0;
-    return bad;
-}
-
-extern "C" {
-// +-1 histogram deltas through the per-block slot view == through the flat sorted list; returns mismatches
-int emul_slots_vs_flat(const uint32_t* codes, const uint32_t* nmask, int L, int K, unsigned long long seed, unsigned seq_id,
-                       unsigned rng_id, int kind, double p1, double p2, int* n_overflow) {
-    switch (K) {
-        case 4: return slots_vs_flat_k<4>(codes, nmask, L, seed, seq_id, rng_id, kind, p1, p2, n_overflow);
-        case 5: return slots_vs_flat_k<5>(codes, nmask, L, seed, seq_id, rng_id, kind, p1, p2, n_overflow);
-        case 6: return slots_vs_flat_k<6>(codes, nmask, L, seed, seq_id, rng_id, kind, p1, p2, n_overflow);
-    }
-    return -1;
-}
-}

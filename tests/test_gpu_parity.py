@@ -326,14 +326,11 @@ def test_pc_kernel_equals_generic(ft, SeqSet):
     sc_mean = torch.rand(4096, device="cuda") * 1e-4
     sc_scale = torch.rand(4096, device="cuda") * 1e-5 + 1e-6
     outs = {}
+    prep = ft.prepare(ss, 6, variants, seed=99, seq_id0=7)      # the two-call fast path (idl_profiles_prepare / _prepared)
     for mode in ("pc", "generic"):
-        if mode == "generic":
-            os.environ["IDL_NO_PC"] = "1"
-        try:
-            f = ft.profiles(ss, 6, variants, out_kind=ft.OUT_FREQ_F32, seed=99, seq_id0=7)
-            s = ft.profiles(ss, 6, variants, out_kind=ft.OUT_STD_F32, seed=99, seq_id0=7, mean=sc_mean, scale=sc_scale)
-        finally:
-            os.environ.pop("IDL_NO_PC", None)
+        kw = {"prepared": prep} if mode == "pc" else {}
+        f = ft.profiles(ss, 6, variants, out_kind=ft.OUT_FREQ_F32, seed=99, seq_id0=7, **kw)
+        s = ft.profiles(ss, 6, variants, out_kind=ft.OUT_STD_F32, seed=99, seq_id0=7, mean=sc_mean, scale=sc_scale, **kw)
         outs[mode] = (f, s)
     assert torch.equal(outs["pc"][0], outs["generic"][0])
     assert torch.equal(outs["pc"][1], outs["generic"][1])
@@ -386,12 +383,12 @@ def test_profile_stats_equals_matrix_fit(golden_dir, fasta_files, ft, SeqSet):
     assert sha(x.cpu().numpy()) == g["k5"]["x_train_sha256"]
 
 
-def test_fast_stats_kernel_equals_generic_and_matrix_fit(ft, SeqSet):
-    """the pipelined statistics kernel (k=6, stats_fast.cuh: register accumulators, prefetched 16-base
-    units, per-block edit slots) against the generic OUT_STATS path and against colstats of the
-    materialised float32 profiles (themselves bit-exact against the oracle): clean and Bernoulli
-    slots, ragged lengths incl. 0 / < k / block and chunk boundaries / deferred long ones, Ns, and
-    rates high enough that blocks overflow the fast generator (deferred to the generic kernel)"""
+def test_prepared_stats_equal_generic_and_matrix_fit(ft, SeqSet):
+    """the statistics of the prepare pass (k=6, prep.cuh: packed uint16 histograms of slot 0 + colstats16)
+    against the generic OUT_STATS path and against colstats of the materialised float32 profiles
+    (themselves bit-exact against the oracle): clean and Bernoulli slots, ragged lengths incl. 0 / < k /
+    block and chunk boundaries / deferred long ones, Ns, and rates high enough that the on-chip edit and
+    delta lists overflow (those items are deferred to the generic kernel)"""
     rng = np.random.default_rng(33)
     alph = np.frombuffer(b"ACGTACGTACGTACGTACGTACGTACGTN", dtype=np.uint8)
     lens = rng.integers(1, 12000, size=900)
@@ -405,17 +402,13 @@ def test_fast_stats_kernel_equals_generic_and_matrix_fit(ft, SeqSet):
     few = SeqSet.from_sequences(seqs[:40])
     specs = [ft.VariantSpec(ft.KIND_CLEAN), ft.VariantSpec(ft.KIND_BOTH, 1e-2, 0.5e-2, rng_id=0),
              ft.VariantSpec(ft.KIND_TRANSITION, p1=1e-2, rng_id=1), ft.VariantSpec(ft.KIND_TRANSVERSION, p2=0.5e-2, rng_id=2),
-             ft.VariantSpec(ft.KIND_BOTH, 0.06, 0.05, rng_id=5),      # many blocks with > 6 hits per stream: deferred items
-             ft.VariantSpec(ft.KIND_BOTH, 0.5, 0.4, rng_id=6)]        # every item deferred
+             ft.VariantSpec(ft.KIND_BOTH, 0.06, 0.05, rng_id=5),      # the longer items overflow the delta list: deferred
+             ft.VariantSpec(ft.KIND_BOTH, 0.5, 0.4, rng_id=6)]        # nearly every item deferred
     for spec in specs:
         x = ft.profiles(ss, 6, [spec], out_kind=ft.OUT_FREQ_F32, seed=17, seq_id0=3)[0]
         a = ft.Scaler.fit(x)
-        b = ft.profile_stats(ss, 6, spec, seed=17, seq_id0=3)
-        os.environ["IDL_NO_FAST_STATS"] = "1"
-        try:
-            g = ft.profile_stats(ss, 6, spec, seed=17, seq_id0=3)
-        finally:
-            os.environ.pop("IDL_NO_FAST_STATS", None)
+        b = ft.profile_stats(ss, 6, spec, seed=17, seq_id0=3)                 # prepare pass + colstats16 (+ generic for deferred items)
+        g = ft.profile_stats(ss, 6, spec, seed=17, seq_id0=3, fast=False)     # generic kernel only
         for other in (a, g):
             assert torch.allclose(other.mean64, b.mean64, rtol=1e-13, atol=0), spec
             assert torch.allclose(other.scale64, b.scale64, rtol=1e-9, atol=0), spec
@@ -461,13 +454,13 @@ def test_pc_kernel_repetitive_and_degenerate_sequences(ft, SeqSet):
     mean = torch.rand(4096, device="cuda") * 1e-3
     scale = torch.rand(4096, device="cuda") * 1e-4 + 1e-6
     outs = {}
+    prep = ft.prepare(ss, 6, variants, seed=3)
     for mode in ("pc", "generic"):
-        if mode == "generic":
-            os.environ["IDL_NO_PC"] = "1"
-        try:
-            outs[mode] = ft.profiles(ss, 6, variants, out_kind=ft.OUT_STD_F32, seed=3, mean=mean, scale=scale)
-        finally:
-            os.environ.pop("IDL_NO_PC", None)
+        kw = {"prepared": prep} if mode == "pc" else {}
+        outs[mode] = ft.profiles(ss, 6, variants, out_kind=ft.OUT_STD_F32, seed=3, mean=mean, scale=scale, **kw)
+    # the statistics of the prepare pass == the generic in-kernel statistics (every sequence here is short: nothing deferred)
+    a, b = prep.scaler(), ft.profile_stats(ss, 6, variants[0], seed=3, fast=False)
+    assert torch.allclose(a.mean64, b.mean64, rtol=1e-13, atol=0) and torch.allclose(a.scale64, b.scale64, rtol=1e-9, atol=0)
     assert torch.equal(outs["pc"], outs["generic"])
     # mimic counts of a homopolymer against the oracle's mutate-and-recount
     c = ft.profiles(ss, 6, variants, out_kind=ft.OUT_COUNTS_I32, seed=3).cpu().numpy()

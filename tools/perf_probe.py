@@ -55,8 +55,13 @@ def main():
                            ("all %d variants std" % V, ft.OUT_STD_F32, variants)):
         nv = len(vs)
         o = out.view(torch.int32) if kind == ft.OUT_COUNTS_I32 else out
+        prep = None
+        if kind != ft.OUT_COUNTS_I32 and ft.can_prepare(ss, k, vs):
+            best, avg = timeit(lambda: ft.prepare(ss, k, vs, seed=1))
+            print("%-28s best %8.3f ms avg %8.3f ms   (prepare pass incl. statistics)" % (name, best, avg))
+            prep = ft.prepare(ss, k, vs, seed=1)
         best, avg = timeit(lambda: ft.profiles(ss, k, vs, out_kind=kind, seed=1, out=o, out_off=off[:nv], out_stride=F,
-                                               mean=mean, scale=scale))
+                                               mean=mean, scale=scale, prepared=prep))
         b = nv * n * F * 4 + n * L / 4
         print("%-28s best %8.3f ms avg %8.3f ms  %8.1f Mprofiles/s  %7.1f GB/s" % (name, best, avg, nv * n / best / 1e3, b / best / 1e6))
         if os.environ.get("IDL_PHASE_PROF"):
