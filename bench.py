@@ -401,6 +401,223 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------
+# --workload c5: BASELINE.json configs[4] — Fungi.zip-shaped long genomes, k = 6, n_clusters = 0 (C = 200 embedding path)
+# ------------------------------------------------------------------------------------------
+C5_NMIM = 3          # the CLI default n_mimics (idelucs/__main__.py:283): 4 profiles per genome
+
+
+def c5_lengths(n, seed):
+    """ASSUMPTION (data/Fungi.zip is absent from the reference checkout): lengths log-uniform over 20 kb .. 2 Mb"""
+    rng = np.random.default_rng(seed)
+    return np.exp(rng.uniform(np.log(20000.0), np.log(2000000.0), size=n)).astype(np.int64)
+
+
+def _cpu_worker_c5(args):
+    seed, lens = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import idelucs_oracle as orc
+    try:
+        import refkmers
+        count, kind = refkmers.kmer_counts, "reference-cython-counter"
+    except ImportError:
+        count, kind = orc.kmer_counts, "oracle-numpy-counter"
+    import random
+    np.random.seed(seed); random.seed(seed)
+    rng = np.random.default_rng(seed)
+    alph = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = [bytearray(alph[rng.integers(0, 4, size=int(L))].tobytes()) for L in lens]
+    t0 = time.perf_counter()
+    passes = []
+    for tf in orc.mimic_transforms(C5_NMIM):      # idelucs/utils.py:330-351, one kmersFasta-style pass per transform
+        rows = []
+        for s in seqs:
+            seq = orc.check_sequence("s", bytearray(s))
+            tf(seq)
+            counts = np.ones(F, dtype=np.int32)
+            count(seq, K, counts)
+            rows.append(counts / np.sum(counts))
+        passes.append(np.array(rows))
+    t_norm = passes[0].astype("float32")
+    mean, var, scale = orc.standard_scaler_fit(t_norm)
+    for pss in passes:
+        orc.standard_scaler_transform(pss.astype("float32"), mean, scale)
+    return time.perf_counter() - t0, kind
+
+
+def cpu_reference_c5(genomes_per_core, cores):
+    ctx = mp.get_context("spawn")
+    jobs = [(2000 + i, c5_lengths(genomes_per_core, 500 + i)) for i in range(cores)]
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker_c5, jobs)
+    busy = max(r[0] for r in res)
+    bases = int(sum(int(j[1].sum()) for j in jobs))
+    return cores * genomes_per_core * (C5_NMIM + 1) / busy, bases / busy, busy, res[0][1]
+
+
+def run_c5(args):
+    import torch
+    import torch.distributed as dist
+    from idelucs_b200 import _lib
+    from idelucs_b200 import featurise as ft
+    from idelucs_b200 import parallel
+    from idelucs_b200.seqset import SeqSet
+
+    rank, local, world = parallel.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    n = args.c5_genomes
+    # ---- one global set of world * n genomes, length-balanced contiguous shards (parallel.shard_ranges) ----
+    lens_all = c5_lengths(world * n, 4242)
+    lo, hi = parallel.shard_ranges(lens_all, world)[rank]
+    lens = lens_all[lo:hi]
+    byte_off = np.zeros(lens.size + 1, np.int64)
+    np.cumsum(lens, out=byte_off[1:])
+    g = torch.Generator(device=dev).manual_seed(777 + rank)
+    ascii_dev = torch.randint(0, 4, (int(byte_off[-1]),), device=dev, generator=g, dtype=torch.uint8)
+    ascii_dev.mul_(2).add_(65).add_((ascii_dev >= 69).to(torch.uint8) * 2).add_((ascii_dev >= 73).to(torch.uint8) * 11)
+    ss = SeqSet.from_ascii(ascii_dev, byte_off, device=dev)
+    ss._d_ascii = None
+    variants = ft.mimic_schedule(C5_NMIM)
+    Vc = len(variants)
+    group = dist.group.WORLD if world > 1 else None
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    k_ev = [ev(), ev()]
+
+    def step():
+        # counts of all 4 slots (chunked path: tiles over the whole grid + exact reduction; generic kernel for the genomes below
+        # 65 536 bases) -> float32(count / total) -> StandardScaler statistics of slot 0 -> standardise
+        k_ev[0].record()
+        c = ft.profiles(ss, K, variants, out_kind=ft.OUT_COUNTS_I32, seed=args.seed, seq_id0=lo, pseudocount=1)
+        k_ev[1].record()
+        x = ft.normalize_counts(c, want64=False, want32=True)
+        sc = ft.Scaler.fit(x[0], group=group)
+        sc.transform32(x.view(-1, F))
+        return x
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = lib.idl_launch_count()
+    t_a, t_b = ev(), ev()
+    t_a.record()
+    for _ in range(args.steps):
+        step()
+    t_b.record()
+    n_launches = int(lib.idl_launch_count() - launches0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = t_a.elapsed_time(t_b)
+    kernel_ms = []
+    for _ in range(max(3, args.steps)):
+        step()
+        k_ev[1].synchronize()
+        kernel_ms.append(k_ev[0].elapsed_time(k_ev[1]))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    n_total = int(lens_all.size)
+    bases_total = int(lens_all.sum())
+    value = n_total * Vc / (ms_per_step * 1e-3)
+    kms = float(np.mean(kernel_ms))
+    my_bases = int(lens.sum())
+    alg_bytes = (my_bases + 3) // 4 + (my_bases + 7) // 8 + int(lens.size) * Vc * F * 4
+    peak, peak_src = measured_peak()
+    roofline = {"bound": "hbm", "kernel": "ch_plan + ch_tile_kernel<6> + ch_reduce_kernel<6,COUNTS> + profiles_kernel<6,512,COUNTS> (genomes < 65 536 bases), rank 0",
+                "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes / (kms * 1e-3) / 1e9 / peak,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kms, "traffic": None,
+                "note": "sequence-read bytes (2-bit codes + 1-bit reset mask, read once) + the int32 count rows; this path is bound by "
+                        "instruction issue and shared-memory atomics (one histogram update per base, ~1 warp instruction per base "
+                        "and Bernoulli slot for the counter-based mutation generator), not by HBM: %.1f Gbases/s on this rank" % (my_bases / (kms * 1e-3) / 1e9)}
+    # ---- end to end: pinned host ASCII of a subset -> H2D -> pack -> featurise -> D2H of the standardised rows ----
+    ne = min(args.c5_e2e_genomes, int(lens.size))
+    eb = int(byte_off[ne])
+    host_ascii = torch.empty(eb, dtype=torch.uint8).pin_memory()
+    host_ascii.copy_(ascii_dev[:eb].cpu())
+    host_out = torch.empty((Vc, ne, F), dtype=torch.float32).pin_memory()
+    boff = byte_off[: ne + 1].copy()
+
+    def e2e_step():
+        s2 = SeqSet.from_ascii(host_ascii, boff, device=dev, validate=True)
+        x, _ = ft.schedule_profiles(s2, K, variants, out_kind=ft.OUT_STD_F32, seed=args.seed)
+        host_out.copy_(x, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * ne * Vc / e2e_s, "unit": "profiles/s", "h2d_bytes_per_step": int(eb + (ne + 1) * 16),
+           "d2h_bytes_per_step": int(Vc * ne * F * 4 + ne * 8), "ms_per_step": e2e_s * 1e3, "genomes_per_step": ne,
+           "gbases_per_s": world * eb / e2e_s / 1e9,
+           "api": "SeqSet.from_ascii(pinned host bytes) -> idl_pack / idl_profiles_chunked / idl_normalize_counts / idl_colstats / "
+                  "idl_scaler_finalize / idl_standardize_f32 -> pinned host float32 [4, n, 4096]"}
+    # ---- training on the embedding path: n_clusters = 0 -> C = 200 (idelucs/__main__.py:75-83), materialised pair set ----
+    train = None
+    if args.train_steps > 0:
+        from idelucs_b200.train import ShardedTrainer
+        tr = ShardedTrainer(ss, k=K, n_clusters=200, n_mimics=C5_NMIM, batch_sz=args.c5_batch, seed=7, seq_id0=lo, world=world, materialize_bytes=64 << 30)
+        graphed = tr.enable_cuda_graph()
+        for _ in range(10):
+            tr.step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ta, tb = ev(), ev()
+        ta.record()
+        for _ in range(args.train_steps):
+            loss = tr.step()
+        tb.record()
+        torch.cuda.synchronize()
+        tms = ta.elapsed_time(tb)
+        if world > 1:
+            t = torch.tensor([tms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tms = float(t.item())
+        train = {"pairs_per_s": world * args.c5_batch * args.train_steps / (tms * 1e-3), "ms_per_step": tms / args.train_steps, "steps": args.train_steps,
+                 "final_loss": float(loss.item()), "cuda_graph": bool(graphed), "n_clusters": 200,
+                 "config": "C = 200 output units (n_clusters = 0 embedding path), batch_sz %d per rank, pairs gathered from the materialised "
+                           "[4, n, 4096] profiles, fused IIC kernel at C = 200" % args.c5_batch}
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, bps, busy, kind = cpu_reference_c5(args.c5_cpu_genomes_per_core, cores)
+        cpu = {"value": v, "unit": "profiles/s", "cores": cores, "kind": "port", "gbases_per_s": bps / 1e9,
+               "sample": "%d cores x %d genomes (log-uniform 20 kb .. 2 Mb) x 4 passes of the oracle's restatement of AugmentFasta driving %s, %.1f s busy"
+                         % (cores, args.c5_cpu_genomes_per_core, kind, busy)}
+    line = {"metric": METRIC, "value": value, "unit": "profiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
+            "config": {"workload": "c5: %d synthetic genomes per GPU, lengths log-uniform 20 kb .. 2 Mb (ASSUMPTION: data/Fungi.zip is absent; "
+                                   "BASELINE.json configs[4]), k=6, n_mimics=%d, n_clusters=0 (C=200 embedding path)" % (n, C5_NMIM),
+                       "genomes": n_total, "bases": bases_total, "gbases_per_s": bases_total / (ms_per_step * 1e-3) / 1e9,
+                       "profiles_per_step": n_total * Vc, "sharding": "contiguous length-balanced ranges (parallel.shard_ranges)",
+                       "cache": "packed input per GPU (%.0f MB) exceeds L2 (126 MB); outputs rewritten every step" % ((my_bases * 3 // 8) / 1e6)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": n_launches, "roofline": roofline, "cpu_baseline": cpu, "train": train}
+    print(json.dumps(line))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -443,9 +660,17 @@ def main():
     ap.add_argument("--train_steps", type=int, default=200, help="steps of the secondary training-pairs/s measurement (0 = skip)")
     ap.add_argument("--train_seqs", type=int, default=1000000, help="total sequences of the training workload (configs[3])")
     ap.add_argument("--kernel_timing", action="store_true", help="time the dominant kernel inside the timed loop (adds syncs)")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"], help="c3: BASELINE configs[2] (default, the headline metric); "
+                    "c5: configs[4], Fungi-shaped long genomes")
+    ap.add_argument("--c5_genomes", type=int, default=2000, help="genomes per GPU of the c5 workload")
+    ap.add_argument("--c5_e2e_genomes", type=int, default=256)
+    ap.add_argument("--c5_batch", type=int, default=512)
+    ap.add_argument("--c5_cpu_genomes_per_core", type=int, default=300)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 

@@ -1,7 +1,7 @@
 """``python -m idelucs_b200`` — the reference CLI surface (idelucs/__main__.py:274-318: same
 flags and defaults) driving the B200-native hot path.  Orchestration only: voters x epochs,
-majority vote over voters (k-means on one-hot votes, utils.py:582-602) or HDBSCAN when
---n_clusters=0 and the ``hdbscan`` package is importable, metrics and TSV output."""
+majority vote over voters (k-means on one-hot votes, utils.py:582-602) or HDBSCAN on the latent space when
+--n_clusters=0 (the ``hdbscan`` package if importable, else scikit-learn's implementation), metrics and TSV output."""
 import argparse
 import os
 import sys
@@ -10,28 +10,13 @@ import time
 import numpy as np
 
 
-def label_features(predictions, n_clusters):
-    """vote ensemble of idelucs/utils.py:582-602 (k-means over centred one-hot votes)"""
-    from sklearn.cluster import KMeans
-    n_v, n = predictions.shape
-    feats = np.zeros((n, n_v * n_clusters))
-    for v in range(n_v):
-        feats[np.arange(n), v * n_clusters + predictions[v]] = 1.0
-    feats -= feats.sum(axis=0) / n
-    return KMeans(n_clusters=n_clusters, init="k-means++", n_init=10).fit_predict(feats)
-
-
 def run(args):
     import torch  # noqa: F401
     from . import models
-    from .utils import SummaryFasta, cluster_acc
+    from .utils import SummaryFasta, cluster_acc, label_features
     start = time.time()
     use_hdbscan = False
-    if args["n_clusters"] == 0:
-        try:
-            import hdbscan
-        except ImportError:
-            raise SystemExit("--n_clusters=0 needs the 'hdbscan' package (not installed); pass --n_clusters > 0")
+    if args["n_clusters"] == 0:   # idelucs/__main__.py:75-83: 200 output units, clusters from HDBSCAN on the latent space
         args["n_clusters"], use_hdbscan = 200, True
     model = models.IID_model(args)
     model.names, model.lengths, model.GT, model.cluster_dis = SummaryFasta(model.sequence_file, model.GT_file)
@@ -41,29 +26,45 @@ def run(args):
     print(f"Max. Length: \t {np.max(model.lengths):,}")
     print(f"Avg. Length: \t {round(float(np.mean(model.lengths)), 2):,}")
     model.build_dataloader()
-    predictions, latent = [], None
+    predictions, latent, probabilities = [], None, None
+    min_loss, model_latent = np.inf, None
     for voter in range(args["n_voters"]):
         sys.stdout.write(f"\r........... Training Model ({voter + 1}/{args['n_voters']})................")
         sys.stdout.flush()
         model.net.apply(models.weights_init)
         model.epoch = 0
+        voter_min = np.inf
         for _ in range(args["n_epochs"]):
-            model.contrastive_training_epoch()
-        y_pred, _, latent = model.predict()
-        predictions.append(y_pred.astype(np.int64))
-    if use_hdbscan:
-        y_pred = hdbscan.HDBSCAN(min_cluster_size=len(model.names) // 100 + 1).fit_predict(latent)
-    elif len(predictions) > 1:
-        y_pred = label_features(np.stack(predictions), args["n_clusters"])
+            voter_min = min(voter_min, model.contrastive_training_epoch())
+        y_pred, probabilities, latent = model.predict()
+        if voter_min < min_loss:
+            min_loss, model_latent = voter_min, latent
+        if not use_hdbscan:   # relabel in order of first appearance (__main__.py:131-141)
+            y_pred = y_pred.astype(np.int32)
+            first = {}
+            y_pred = np.array([first.setdefault(int(c), len(first)) for c in y_pred], dtype=np.int32)
+            predictions.append(y_pred)
+    if use_hdbscan:   # __main__.py:149-156 (the last voter's latent space, like the reference)
+        msz = len(model.names) // 100 + 1
+        try:
+            import hdbscan
+            clusterer = hdbscan.HDBSCAN(min_cluster_size=msz, gen_min_span_tree=True, prediction_data=True)
+        except ImportError:   # same algorithm from scikit-learn (>= 1.3) when the hdbscan package is not installed
+            from sklearn.cluster import HDBSCAN
+            clusterer = HDBSCAN(min_cluster_size=max(msz, 2))
+        clusterer.fit(latent)
+        y_pred = clusterer.labels_ + 1
+        probabilities = clusterer.probabilities_
+        args["n_clusters"] = int(np.max(y_pred)) + 1
     else:
-        y_pred = predictions[0]
+        y_pred, probabilities = label_features(np.array(predictions), args["n_clusters"])
     out_dir = os.path.join(os.getcwd(), "Results", os.path.basename(args["sequence_file"]).split(".")[0],
                            time.strftime("%b_%d_%H-%M-%S"))
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, "assignments.tsv"), "w") as fh:
-        fh.write("sequence_id\tassignment\n")
-        for name, c in zip(model.names, y_pred):
-            fh.write(f"{name}\t{int(c)}\n")
+        fh.write("sequence_id\tassignment\tconfidence_score\n")
+        for name, c, pr in zip(model.names, y_pred, probabilities):
+            fh.write(f"{name}\t{int(c)}\t{float(pr):.6f}\n")
     print("\n")
     if model.GT is not None:
         from sklearn import metrics

@@ -37,6 +37,11 @@ PROTOTYPES = {
     "idl_profile_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, ctypes.POINTER(Variant),
                                   c_u64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, ctypes.POINTER(c_int), c_void_p, c_void_p,
                                   c_size_t, c_void_p]),
+    "idl_profiles_chunked_bytes": (c_size_t, [c_i64, c_i64, ctypes.POINTER(Variant), c_int, c_int]),
+    "idl_profiles_chunked": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int,
+                                     ctypes.POINTER(Variant), c_int, c_void_p, c_int, c_u64, c_void_p, c_void_p, c_int,
+                                     c_void_p, ctypes.POINTER(c_i64), c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_i64,
+                                     c_void_p, c_size_t, c_void_p]),
     "idl_prepare_bytes": (c_size_t, [c_i64]),
     "idl_profiles_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, ctypes.POINTER(Variant),
                                      c_int, c_u64, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_int, ctypes.POINTER(c_int), c_void_p,

@@ -220,6 +220,54 @@ IDL_HD int apply_entry(const uint32_t* codes, const uint32_t* nmask, int L, cons
     return dtot;
 }
 
+// apply_entry with the deltas returned in registers instead of through a callback (statically indexed: one word per owned
+// window end): d[t] = removed k-mer | 0x1000 when the clean window ending at p+t is uncounted by the edit, (added k-mer << 16)
+// | 0x10000000 when a mutated window is counted there.  Returns the number of +-1 updates (0..2K); *dtot = change of the
+// number of counted windows.  One evaluation serves both the reservation of list space and the writes.
+template <int K, class List>
+IDL_HD int entry_deltas(const uint32_t* codes, const uint32_t* nmask, int L, const List& list, int n, int i, uint32_t (&d)[K], int* dtot) {
+    constexpr int W = 2 * K - 1;
+    constexpr uint32_t KMASK = (1u << (2 * K)) - 1u;
+    constexpr uint32_t NMASKK = (1u << K) - 1u;
+    const uint32_t ent = list[i];
+    const int p = (int)(ent >> 3);
+    const int pn = (i + 1 < n) ? (int)(list[i + 1] >> 3) : 0x7fffffff;
+    int e_hi = p + K - 1;
+    if (pn - 1 < e_hi) e_hi = pn - 1;
+    if (L - 1 < e_hi) e_hi = L - 1;
+    const int q0 = p - (K - 1);
+    const Window<K> cw = load_window<K>(codes, nmask, q0);
+    uint32_t mb = cw.bases, mn = cw.nbits;
+    for (int j = i; j >= 0; --j) {
+        const uint32_t ej = list[j];
+        const int pj = (int)(ej >> 3);
+        if (pj < q0) break;
+        const int sh = W - 1 - (pj - q0);
+        const uint32_t v = ej & 7u;
+        if (v < 4u) { mb = (mb & ~(3u << (2 * sh))) | (v << (2 * sh)); mn &= ~(1u << sh); }
+        else        { mn |= (1u << sh); }
+    }
+    int cnt = 0, dt = 0;
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        uint32_t v = 0u;
+        if (p + t <= e_hi) {
+            const int sh = K - 1 - t;
+            const bool okc = ((cw.nbits >> sh) & NMASKK) == 0u;
+            const bool okm = ((mn >> sh) & NMASKK) == 0u;
+            const uint32_t kc = (cw.bases >> (2 * sh)) & KMASK;
+            const uint32_t km = (mb >> (2 * sh)) & KMASK;
+            if (!(okc && okm && kc == km)) {
+                if (okc) { v |= kc | 0x1000u; ++cnt; --dt; }
+                if (okm) { v |= (km << 16) | 0x10000000u; ++cnt; ++dt; }
+            }
+        }
+        d[t] = v;
+    }
+    *dtot = dt;
+    return cnt;
+}
+
 // ---------------------------------------------------------------------------------------
 // Random_N specialisation of the delta rule (idelucs/utils.py:89-95 sets bases to N, so
 // windows are only ever REMOVED): draw i of an UNSORTED list of n draws (entry = pos<<3|4)

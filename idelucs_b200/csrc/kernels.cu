@@ -39,6 +39,7 @@ static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 constexpr int LIST_CAP = 2048;   // on-chip edit list entries per CTA
+constexpr int CH_MIN_LEN = 65536; // items at least this long take the chunked path (chunked.cuh) when the caller provides its scratch
 constexpr int SG = 32;           // variant slots per supergroup (Random_N removals precomputed together)
 constexpr int REM_CAP = 3840;    // removed k-mers buffered per supergroup (32 slots x 20 draws x k=6)
 constexpr int ENT_CAP = 1024;    // Random_N draws buffered per supergroup (aliases the edit list)
@@ -92,6 +93,7 @@ struct ProfParams {
     int inline_plan;                  // descriptors / offsets / tables come from the Plan kernel parameter (else from vars / out_off / gtab)
     void* prep;                       // prepared buffer (prep.cuh): written by prep_kernel, read by colstats16 / the producer/consumer kernel
     unsigned long long prep_stamp;    // what the prepared buffer must have been prepared for
+    const int* long_overflow;         // chunked path active (chunked.cuh): items of >= CH_MIN_LEN bases are skipped here while *long_overflow == 0
 };
 static_assert(sizeof(ProfParams) + sizeof(Plan) <= 4000, "kernel parameters must stay below the 4 KB limit");
 
@@ -388,9 +390,9 @@ __device__ __forceinline__ void bern_tiles(ProfSmem<K, NT>& sm, const ProfParams
     }
 }
 
-// CTA-wide Random_N with many draws: draw -> rank sort into sm.list.  Contains barriers.
-template <int K, int NT>
-__device__ __noinline__ void random_n_list(ProfSmem<K, NT>& sm, const ItemCtx& cx, const VarDesc& vd, uint32_t* tmp) {
+// CTA-wide Random_N with many draws: draw -> rank sort into list.  Contains barriers.
+template <int NT>
+__device__ __noinline__ void random_n_sorted(const ItemCtx& cx, const VarDesc& vd, uint32_t* tmp, uint32_t* list) {
     const int n_bp = vd.n_bp;
     for (int call = threadIdx.x; call * 4 < n_bp; call += NT) {
         const U4 r = random_n_words(cx.seed, cx.seq_id, (uint32_t)vd.rng_id, (uint32_t)call);
@@ -403,9 +405,13 @@ __device__ __noinline__ void random_n_list(ProfSmem<K, NT>& sm, const ItemCtx& c
         const uint32_t e = tmp[i];
         int rank = 0;
         for (int j = 0; j < n_bp; ++j) { const uint32_t ej = tmp[j]; rank += (ej < e || (ej == e && j < i)) ? 1 : 0; }
-        sm.list[rank] = e;
+        list[rank] = e;
     }
     __syncthreads();
+}
+template <int K, int NT>
+__device__ __forceinline__ void random_n_list(ProfSmem<K, NT>& sm, const ItemCtx& cx, const VarDesc& vd, uint32_t* tmp) {
+    random_n_sorted<NT>(cx, vd, tmp, sm.list);
 }
 
 // LONG path (L > 65535): patch hist[] itself (int32 counts), one variant at a time.
@@ -669,6 +675,7 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
         cx.seq_id = (uint32_t)(p.seq_id0 + seq);
         cx.seed = p.seed;
         const int L = cx.L;
+        if (p.long_overflow && L >= CH_MIN_LEN && *p.long_overflow == 0) continue;   // the chunked path owns the item
         const int nhalf = ((L + CHUNK_BASES - 1) / CHUNK_BASES) * 2;
         const bool staged = nhalf <= 2 * SSEQ_CHUNKS;
         auto slot_var = [&](int slot) -> int { return p.sel ? p.sel[item * p.S + slot] : slot; };
@@ -1001,6 +1008,7 @@ __global__ void __launch_bounds__(NT, (K == 6 ? 2 : K == 5 ? 4 : 8)) profiles_ke
 }  // namespace idl
 #include "profiles_pc.cuh"
 #include "prep.cuh"
+#include "chunked.cuh"
 namespace idl {
 
 // ---------------------------------------------------------------------------------------
@@ -1342,6 +1350,35 @@ static void fill_params(ProfParams& p, const uint32_t* d_codes, const uint32_t* 
 #endif
 }
 
+// ---- chunked path (chunked.cuh): scratch layout and sizing ----
+struct ChunkLayout { size_t off_tiles, off_rank, off_partials, bytes, smem; int grid; };
+
+static int chunk_dense_cap(const idl_variant* variants, int n_variants, int S) {
+    int nd = 0;
+    for (int v = 0; v < n_variants; ++v) {
+        const int kd = variants[v].kind;
+        nd += (kd == IDL_KIND_TRANSITION || kd == IDL_KIND_TRANSVERSION || kd == IDL_KIND_BOTH || kd == IDL_KIND_EXPLICIT) ? 1 : 0;
+    }
+    return nd < S ? nd : S;
+}
+static ChunkLayout chunk_layout(int64_t n_items, int64_t max_long, int nd_cap) {
+    ChunkLayout l;
+    memset(&l, 0, sizeof(l));
+    l.smem = sizeof(ChSmem) - sizeof(int) * CH_F + sizeof(int) * CH_F * (size_t)(1 + nd_cap);
+    int per_sm = 0;
+    if (ensure_dyn_smem((const void*)ch_tile_kernel<6>, l.smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ch_tile_kernel<6>, CH_NT, l.smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return l;   // grid 0: does not fit
+    }
+    l.grid = sm_count() * per_sm;
+    l.off_tiles = 64;
+    l.off_rank = l.off_tiles + (((size_t)(n_items + 1) * 8 + 15) & ~(size_t)15);
+    l.off_partials = l.off_rank + (((size_t)n_items * 4 + 15) & ~(size_t)15);
+    l.bytes = l.off_partials + (size_t)(max_long + l.grid) * (size_t)(1 + nd_cap) * CH_F * sizeof(int);
+    return l;
+}
+
 static int profiles_impl(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
                          const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
                          int64_t seq_id0, int k, const idl_variant* variants, int n_variants, const int32_t* d_sel,
@@ -1349,7 +1386,7 @@ static int profiles_impl(const uint32_t* d_codes, const uint32_t* d_nmask, const
                          void* d_out, const int64_t* out_off, int64_t out_stride, int pseudocount, int accumulate,
                          const float* d_mean, const float* d_scale, int32_t* d_status, void* d_workspace,
                          size_t workspace_bytes, void* stream, double* d_stats_partials, double* d_stats_n, int* n_parts_out,
-                         const void* d_prep, size_t prep_size) {
+                         const void* d_prep, size_t prep_size, void* d_chunk = nullptr, size_t chunk_size = 0, int64_t max_long = 0) {
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t zero_off = 0;
     if (out_kind == OUT_STATS) { out_off = &zero_off; out_stride = 0; }
@@ -1380,6 +1417,39 @@ static int profiles_impl(const uint32_t* d_codes, const uint32_t* d_nmask, const
     }
     p.stats_partials = d_stats_partials; p.stats_n = d_stats_n;
     if (out_kind == OUT_STATS) return dispatch_k(p, hp.plan, k, out_kind, st, n_parts_out);
+    // ---- chunked path for the long items (k = 6): tiles spread over the whole grid, exact integer reduction ----
+    if (d_chunk && k == 6 && max_long > 0) {
+        const int nd_cap = chunk_dense_cap(variants, n_variants, S);
+        if (nd_cap <= CH_MAX_DENSE && !((uintptr_t)d_chunk & 15)) {
+            const ChunkLayout lay = chunk_layout(n_items, max_long, nd_cap);
+            if (lay.grid > 0 && chunk_size >= lay.bytes) {
+                unsigned char* cb = reinterpret_cast<unsigned char*>(d_chunk);
+                ChParams cp;
+                cp.p = p;
+                cp.hdr = reinterpret_cast<ChHeader*>(cb);
+                cp.tile_off = reinterpret_cast<long long*>(cb + lay.off_tiles);
+                cp.long_rank = reinterpret_cast<int*>(cb + lay.off_rank);
+                cp.partials = reinterpret_cast<int*>(cb + lay.off_partials);
+                cp.max_long = max_long; cp.nd_cap = nd_cap; cp.grid_tiles = lay.grid;
+                ch_plan_kernel<<<1, 1024, 0, st>>>(cp); note_launch();
+                IDL_CUDA_CHECK(cudaGetLastError());
+                IDL_CUDA_CHECK(ensure_dyn_smem((const void*)ch_tile_kernel<6>, lay.smem));
+                ch_tile_kernel<6><<<(unsigned)lay.grid, CH_NT, lay.smem, st>>>(cp, hp.plan); note_launch();
+                IDL_CUDA_CHECK(cudaGetLastError());
+                long long rgrid = (long long)sm_count() * 2;
+                if (rgrid > n_items) rgrid = n_items;
+                switch (out_kind) {
+                    case IDL_OUT_COUNTS_I32: ch_reduce_kernel<6, IDL_OUT_COUNTS_I32><<<(unsigned)rgrid, CH_NT, 0, st>>>(cp, hp.plan); break;
+                    case IDL_OUT_FREQ_F32: ch_reduce_kernel<6, IDL_OUT_FREQ_F32><<<(unsigned)rgrid, CH_NT, 0, st>>>(cp, hp.plan); break;
+                    case IDL_OUT_STD_F32: ch_reduce_kernel<6, IDL_OUT_STD_F32><<<(unsigned)rgrid, CH_NT, 0, st>>>(cp, hp.plan); break;
+                    default: ch_reduce_kernel<6, IDL_OUT_FREQ_F64><<<(unsigned)rgrid, CH_NT, 0, st>>>(cp, hp.plan); break;
+                }
+                note_launch();
+                IDL_CUDA_CHECK(cudaGetLastError());
+                p.long_overflow = &cp.hdr->overflow;   // the generic kernel skips the long items (unless the plan found more than max_long)
+            }
+        }
+    }
     // ---- producer/consumer kernel (k = 6, float outputs, whole-schedule featurisation of PREPARED items) ----
     bool pc_ok = d_prep && k == 6 && (out_kind == IDL_OUT_FREQ_F32 || out_kind == IDL_OUT_STD_F32) && !d_sel && d_status && hp.inl &&
                  n_variants <= PC_MAXS && n_items >= 2LL * sm_count() && prep_size >= prep_bytes(n_items);
@@ -1451,6 +1521,28 @@ int idl_profiles(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t
     return profiles_impl(d_codes, d_nmask, d_chunk_off, d_len, n_seqs_total, d_sidx, n_items, seq_id0, k, variants, n_variants, d_sel, S,
                          seed, d_edit_off, d_edits, out_kind, d_out, out_off, out_stride, pseudocount, accumulate, d_mean, d_scale,
                          d_status, d_workspace, workspace_bytes, stream, nullptr, nullptr, nullptr, nullptr, 0);
+}
+
+size_t idl_profiles_chunked_bytes(int64_t n_items, int64_t max_long_items, const idl_variant* variants, int n_variants, int S) {
+    if (n_items <= 0 || max_long_items <= 0 || !variants || n_variants < 1 || S < 1) return 0;
+    const int nd_cap = chunk_dense_cap(variants, n_variants, S);
+    if (nd_cap > CH_MAX_DENSE) return 0;
+    const ChunkLayout lay = chunk_layout(n_items, max_long_items, nd_cap);
+    return lay.grid > 0 ? lay.bytes : 0;
+}
+
+int idl_profiles_chunked(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
+                         const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
+                         int64_t seq_id0, int k, const idl_variant* variants, int n_variants, const int32_t* d_sel,
+                         int S, uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits, int out_kind,
+                         void* d_out, const int64_t* out_off, int64_t out_stride, int pseudocount, int accumulate,
+                         const float* d_mean, const float* d_scale, void* d_scratch, size_t scratch_bytes, int64_t max_long_items,
+                         void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (out_kind < IDL_OUT_COUNTS_I32 || out_kind > IDL_OUT_FREQ_F64) return set_error(IDL_EINVAL, "idl_profiles_chunked: unknown out_kind%s %lld", "", out_kind);
+    if (!d_scratch || max_long_items < 0) return set_error(IDL_EINVAL, "idl_profiles_chunked: scratch required%s", "");
+    return profiles_impl(d_codes, d_nmask, d_chunk_off, d_len, n_seqs_total, d_sidx, n_items, seq_id0, k, variants, n_variants, d_sel, S,
+                         seed, d_edit_off, d_edits, out_kind, d_out, out_off, out_stride, pseudocount, accumulate, d_mean, d_scale,
+                         nullptr, d_workspace, workspace_bytes, stream, nullptr, nullptr, nullptr, nullptr, 0, d_scratch, scratch_bytes, max_long_items);
 }
 
 int idl_profiles_prepared(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,

@@ -12,7 +12,7 @@
 //     (colstats16_kernel: HBM-bound read of 8 KB per sequence, float64 shifted-data sums in registers),
 //     so the slot-0 mutations are generated once for the statistics AND the profile pass.
 //
-// One CTA of 256 threads per sequence at a time, 4-6 CTAs per SM (35 KB of shared memory each): count the clean
+// One CTA of 256 threads per sequence at a time, 4 CTAs per SM (51 KB of shared memory each): count the clean
 // histogram into packed uint16 counters (shared atomics), mutation masks of every (slot, 64-base block) by
 // the register-only mask generator (core.cuh), CTA scan -> position-sorted edit lists -> +-1 deltas
 // (apply_entry), slot 0's deltas applied to the histogram.  Sequences that do not fit (longer than
@@ -26,19 +26,52 @@ constexpr int PR_NT = 256;
 constexpr int PR_LIST = 2048;              // edits of all dense slots of one sequence
 
 struct PrSmem {
-    alignas(16) uint32_t hist[PC_F / 2];   // packed uint16 pairs: clean histogram, then slot 0's
-    alignas(16) uint32_t sseq[PC_SSEQ_W];  // staged sequence: codes | mask
+    alignas(16) int hist[PC_F];               // clean histogram, then slot 0's (packed to uint16 on the way out)
+    alignas(16) uint32_t sseq[2][PC_SSEQ_W];  // staged sequences (codes | mask): the next item's words arrive (cp.async) while this one is processed
     alignas(16) uint32_t list[PR_LIST + 8];
     alignas(16) uint16_t delta[PC_DELTA];
     uint32_t gtabs[STABS][RNG_BLOCK];
     VarDesc dvar[PC_DENSE];
     int seg_off[PC_DENSE + 1];
-    int scan[PR_NT / 32 + 2];
+    int wsum[2][PR_NT / 32];                  // edits per warp of a generation round (double-buffered: one barrier per round)
     int dtot[PC_DENSE];
     int nvalid, n_delta;
     int nd, slot0_dense;
-    long long next_item;
 };
+
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// counts the windows ending in the 16-base code word u of a staged sequence (idelucs/kmers.pyx:36-47) with shared atomics
+// (ATOMS.POPC.INC); returns how many were counted.  Thread <-> word: a 10 kb sequence is 628 work items (2.5 rounds of 256 threads).
+template <int K>
+__device__ __forceinline__ int pr_count_word(const uint32_t* codes, const uint32_t* nmask, int u, int* hist) {
+    constexpr uint32_t KMASK = (1u << (2 * K)) - 1u;
+    const uint32_t w = codes[u], prev = u > 0 ? codes[u - 1] : 0u;
+    const uint32_t m = nmask[u >> 1], mprev = u > 1 ? nmask[(u >> 1) - 1] : 0xFFFFFFFFu;   // sequence start = preceded by resets (kmers.pyx:14)
+    const uint64_t flags = ((uint64_t)mprev << 32) | (uint64_t)m;   // bit 31-j of m = reset flag of base j of the half-chunk
+    uint64_t inv64 = flags;
+#pragma unroll
+    for (int d = 1; d < K; ++d) inv64 |= flags >> d;                // a window is void if any of its K bases is a reset
+    const uint32_t inv = (uint32_t)(inv64 >> ((u & 1) ? 0 : 16)) & 0xFFFFu;   // bit 15-j = window ending at base j of this word
+    if (inv == 0u) {   // the common case: no reset near the word, 16 unconditional updates
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(&hist[funnel_r(w, prev, 30 - 2 * j) & KMASK], 1);
+        return 16;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (!((inv >> (15 - j)) & 1u)) atomicAdd(&hist[funnel_r(w, prev, 30 - 2 * j) & KMASK], 1);
+    return __popc(~inv & 0xFFFFu);
+}
+
+struct PrItem { int L; long long c0; uint32_t seq_id; };
 
 template <int K>
 __global__ void __launch_bounds__(PR_NT, 4) prep_kernel(const ProfParams p, const __grid_constant__ Plan plan) {
@@ -46,7 +79,7 @@ __global__ void __launch_bounds__(PR_NT, 4) prep_kernel(const ProfParams p, cons
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PrSmem& sm = *reinterpret_cast<PrSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
-    const long long n = p.n_items;
+    const long long n = p.n_items, G = gridDim.x;
     unsigned char* prep = reinterpret_cast<unsigned char*>(p.prep);
     PrepMeta* meta = reinterpret_cast<PrepMeta*>(prep + prep_meta_off());
     uint4* hist_out = reinterpret_cast<uint4*>(prep + prep_hist_off(n));
@@ -71,85 +104,140 @@ __global__ void __launch_bounds__(PR_NT, 4) prep_kernel(const ProfParams p, cons
             for (int i = 0; i < 10; ++i) h.pad[i] = 0;
             *reinterpret_cast<PrepHeader*>(prep) = h;
         }
-        sm.next_item = (long long)atomicAdd(p.work_counter, 1ull);
     }
     for (int i = tid; i < STABS * RNG_BLOCK; i += PR_NT)
         (&sm.gtabs[0][0])[i] = i < p.n_tabs * RNG_BLOCK ? (p.inline_plan ? (&plan.gtab[0][0])[i] : p.gtab[i]) : 0u;
     auto table = [&](int t) -> const uint32_t* { return t < STABS ? sm.gtabs[t] : p.gtab + t * RNG_BLOCK; };
 
-    for (;;) {
-        __syncthreads();   // the previous item is finished; thread 0's next_item is visible
-        const long long item = sm.next_item;
+    // Items are assigned statically (item = blockIdx.x + j * gridDim.x), so the next item is known at once: its metadata is
+    // loaded two iterations ahead and its packed words are copied global -> shared asynchronously (cp.async, no registers)
+    // while the current item is processed — no global-memory latency on the per-item critical path.
+    auto item_of = [&](long long j) { return (long long)blockIdx.x + j * G; };
+    auto load_item = [&](long long item) {
+        PrItem it;
+        it.L = -1; it.c0 = 0; it.seq_id = 0u;
+        if (item < n) {
+            const long long seq = p.sidx ? (long long)__ldg(p.sidx + item) : item;
+            it.L = __ldg(p.len + seq);
+            it.c0 = __ldg(reinterpret_cast<const long long*>(p.chunk_off) + seq);
+            it.seq_id = (uint32_t)(p.seq_id0 + seq);
+        }
+        return it;
+    };
+    auto chunks_of = [](int L) { return (L + CHUNK_BASES - 1) / CHUNK_BASES; };
+    auto issue_copy = [&](int buf, const PrItem& it) {
+        const int nch = chunks_of(it.L);
+        if (it.L > 0 && nch <= SSEQ_CHUNKS) {
+            const unsigned char* gc = reinterpret_cast<const unsigned char*>(p.codes + it.c0 * 4);
+            const unsigned char* gm = reinterpret_cast<const unsigned char*>(p.nmask + it.c0 * 2);
+            unsigned char* sc = reinterpret_cast<unsigned char*>(sm.sseq[buf]);
+            unsigned char* smk = reinterpret_cast<unsigned char*>(sm.sseq[buf] + SSEQ_CW);
+            for (int c = tid; c < nch; c += PR_NT) {
+                cp_async16(sc + c * 16, gc + c * 16);
+                cp_async8(smk + c * 8, gm + c * 8);
+            }
+        }
+        cp_async_commit();
+    };
+    PrItem cur = load_item(item_of(0)), nxt = load_item(item_of(1));
+    issue_copy(0, cur);
+    for (long long j = 0;; ++j) {
+        const long long item = item_of(j);
+        if (item >= n) break;
+        const int buf = (int)(j & 1);
+        const PrItem nn = load_item(item_of(j + 2));   // registers; first used one iteration later
+        __syncthreads();                               // everybody is done with item j-1 (shared buffers, the other sseq half)
+        issue_copy(buf ^ 1, nxt);                      // item j+1: lands during this iteration
+        if (tid == 0) {
+            sm.nvalid = 0; sm.n_delta = 0;
+            for (int q = 0; q < PC_DENSE; ++q) sm.dtot[q] = 0;
+        }
+        for (int i = tid; i < PC_F / 4; i += PR_NT) reinterpret_cast<int4*>(sm.hist)[i] = make_int4(0, 0, 0, 0);
+        const int L = cur.L;
+        const uint32_t seq_id = cur.seq_id;
+        const int nchunks = chunks_of(L);
         const int nd = sm.nd;
         const bool slot0_dense = sm.slot0_dense != 0;
-        __syncthreads();   // everybody has read it
-        if (item >= n) break;
-        if (tid == 0) {
-            sm.next_item = (long long)atomicAdd(p.work_counter, 1ull);   // in flight while this item is processed
-            sm.nvalid = 0; sm.n_delta = 0;
-            for (int j = 0; j < PC_DENSE; ++j) sm.dtot[j] = 0;
-        }
-        const long long seq = p.sidx ? (long long)__ldg(p.sidx + item) : item;
-        const int L = __ldg(p.len + seq);
-        const long long c0 = __ldg(reinterpret_cast<const long long*>(p.chunk_off) + seq);
-        const uint32_t seq_id = (uint32_t)(p.seq_id0 + seq);
-        const int nchunks = (L + CHUNK_BASES - 1) / CHUNK_BASES;
         bool defer = nchunks > SSEQ_CHUNKS;
+        uint32_t* codes = sm.sseq[buf];
+        uint32_t* nmask = sm.sseq[buf] + SSEQ_CW;
+        cp_async_wait<1>();                            // this thread's copies of item j have landed
         if (!defer) {
-            // ---- stage the packed sequence, clear the histogram ----
-            uint32_t* codes = sm.sseq;
-            uint32_t* nmask = sm.sseq + SSEQ_CW;
-            const uint4* gc = reinterpret_cast<const uint4*>(p.codes + c0 * 4);
-            const uint2* gm = reinterpret_cast<const uint2*>(p.nmask + c0 * 2);
-            for (int c = tid; c < nchunks; c += PR_NT) {
-                reinterpret_cast<uint4*>(codes)[c] = __ldg(gc + c);
-                reinterpret_cast<uint2*>(nmask)[c] = __ldg(gm + c);
-            }
             if (tid < 4) codes[nchunks * 4 + tid] = 0u;           // slack chunk (window reads run one word past the end)
             if (tid < 2) nmask[nchunks * 2 + tid] = 0xFFFFFFFFu;
-            for (int i = tid; i < PC_F / 8; i += PR_NT) reinterpret_cast<uint4*>(sm.hist)[i] = make_uint4(0u, 0u, 0u, 0u);
-            __syncthreads();
+        }
+        __syncthreads();                               // ... and everybody else's; histogram cleared
+        if (!defer) {
             // ---- clean histogram (idelucs/kmers.pyx:38-50), two uint16 counters per word ----
             {
                 int nv = 0;
-                for (int h = tid; h < nchunks * 2; h += PR_NT) {
-                    const uint2 w = reinterpret_cast<const uint2*>(codes)[h];
-                    nv += count_half<K>(codes, nmask, h, w.x, w.y, [&](uint32_t kmer) { atomicAdd(&sm.hist[kmer >> 1], 1u << ((kmer & 1u) * 16u)); });
-                }
+                for (int u = tid; u < nchunks * 4; u += PR_NT) nv += pr_count_word<K>(codes, nmask, u, sm.hist);
                 nv = warp_sum(nv);
                 if (lane == 0 && nv) atomicAdd(&sm.nvalid, nv);
             }
-            // ---- mutation masks of every (dense slot, block), position-sorted edit lists (slot-major) ----
+            // ---- mutation masks of every (dense slot, block), position-sorted edit lists (slot-major).  Work item w =
+            // ---- slot * nblocks + block; a round covers 2 * PR_NT items, warp g the 64 consecutive items from w0 + 64 g
+            // ---- (two per lane, masks stay in registers), so ONE barrier per round orders the warps' list segments ----
             const int nblocks = nchunks, W = nd * nblocks;
-            int base = 0;
-            for (int w0 = 0; w0 < W; w0 += PR_NT) {   // uniform trip count (CTA scan inside)
-                const int w = w0 + tid;
-                const bool active = w < W;
-                const int j = active ? w / nblocks : 0, b = active ? w - j * nblocks : 0;
-                BlockMasks m;
-                m.a = m.b = m.ch = 0;
-                if (active) {
-                    const VarDesc vd = sm.dvar[j];
-                    m = block_masks(vd.kind, p.seed, seq_id, (uint32_t)vd.rng_id, b, L, nmask, table(vd.tab1), vd.slope1, table(vd.tab2), vd.slope2);
+            const int wid = tid >> 5;
+            int base = 0, round = 0;
+            for (int w0 = 0; w0 < W; w0 += 2 * PR_NT, ++round) {   // uniform trip count
+                BlockMasks m[2];
+                int cnt[2], bq[2], bb[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int w = w0 + wid * 64 + h * 32 + lane;
+                    m[h].a = m[h].b = m[h].ch = 0;
+                    bq[h] = 0; bb[h] = -1;
+                    if (w < W) {
+                        int q = 0, b = w;
+                        while (b >= nblocks) { b -= nblocks; ++q; }   // (at most PC_DENSE - 1 steps)
+                        const VarDesc vd = sm.dvar[q];
+                        m[h] = block_masks(vd.kind, p.seed, seq_id, (uint32_t)vd.rng_id, b, L, nmask, table(vd.tab1), vd.slope1, table(vd.tab2), vd.slope2);
+                        bq[h] = q; bb[h] = b;
+                    }
+                    cnt[h] = block_masks_count(m[h]);
                 }
-                int total;
-                const int off = block_exscan<PR_NT>(block_masks_count(m), sm.scan, &total);
+                int inc0 = cnt[0], inc1 = cnt[1];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t0 = __shfl_up_sync(0xffffffffu, inc0, o), t1 = __shfl_up_sync(0xffffffffu, inc1, o);
+                    if (lane >= o) { inc0 += t0; inc1 += t1; }
+                }
+                const int tot0 = __shfl_sync(0xffffffffu, inc0, 31), tot1 = __shfl_sync(0xffffffffu, inc1, 31);
+                if (lane == 0) sm.wsum[round & 1][wid] = tot0 + tot1;
+                __syncthreads();
+                int wbase = base, total = 0;
+#pragma unroll
+                for (int g = 0; g < PR_NT / 32; ++g) {
+                    const int v = sm.wsum[round & 1][g];
+                    if (g < wid) wbase += v;
+                    total += v;
+                }
                 if (base + total > PR_LIST) { defer = true; break; }   // uniform
-                if (active && b == 0) sm.seg_off[j] = base + off;
-                block_masks_write(m, b, codes, sm.list + base + off);
+                const int off[2] = {wbase + inc0 - cnt[0], wbase + tot0 + inc1 - cnt[1]};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (bb[h] == 0) sm.seg_off[bq[h]] = off[h];
+                    if (cnt[h]) block_masks_write(m[h], bb[h], codes, sm.list + off[h]);
+                }
                 base += total;
             }
             if (tid == 0) sm.seg_off[nd] = base;
             __syncthreads();   // lists, seg_off and the clean histogram are complete
             if (!defer) {
-                // ---- edits -> +-1 deltas (thread <-> edit); slot 0's deltas also go into the histogram ----
+                // ---- edits -> +-1 deltas (thread <-> edit, one evaluation: the deltas wait in registers for their list slot);
+                // ---- slot 0's deltas also go into the histogram ----
                 for (int i0 = 0; i0 < base; i0 += PR_NT) {   // uniform trip count (warp collectives inside)
                     const int i = i0 + tid;
-                    int jj = 0, so = 0, cnt = 0;
+                    int jj = 0, cnt = 0, dt = 0;
+                    uint32_t d[K];
+#pragma unroll
+                    for (int t = 0; t < K; ++t) d[t] = 0u;
                     if (i < base) {
                         while (i >= sm.seg_off[jj + 1]) ++jj;
-                        so = sm.seg_off[jj];
-                        apply_entry<K>(codes, nmask, L, sm.list + so, sm.seg_off[jj + 1] - so, i - so, [&](uint32_t, int) { ++cnt; });
+                        const int so = sm.seg_off[jj];
+                        cnt = entry_deltas<K>(codes, nmask, L, sm.list + so, sm.seg_off[jj + 1] - so, i - so, d, &dt);
                     }
                     int inc = cnt;
 #pragma unroll
@@ -161,15 +249,24 @@ __global__ void __launch_bounds__(PR_NT, 4) prep_kernel(const ProfParams p, cons
                     int wbase = 0;
                     if (lane == 31 && wtot) wbase = atomicAdd(&sm.n_delta, wtot);
                     wbase = __shfl_sync(0xffffffffu, wbase, 31);
-                    int slot = wbase + inc - cnt;
                     if (cnt && wbase + wtot <= PC_DELTA) {
+                        int slot = wbase + inc - cnt;
                         const uint32_t tag = (uint32_t)jj << 12;
                         const bool to_hist = slot0_dense && jj == 0;
-                        const int d = apply_entry<K>(codes, nmask, L, sm.list + so, sm.seg_off[jj + 1] - so, i - so, [&](uint32_t kmer, int dd) {
-                            sm.delta[slot++] = (uint16_t)(kmer | tag | (dd > 0 ? 0x8000u : 0u));
-                            if (to_hist) upd16(sm.hist, kmer, dd);
-                        });
-                        if (d) atomicAdd(&sm.dtot[jj], d);
+#pragma unroll
+                        for (int t = 0; t < K; ++t) {
+                            if (d[t] & 0x1000u) {
+                                const uint32_t km = d[t] & 0xFFFu;
+                                sm.delta[slot++] = (uint16_t)(km | tag);
+                                if (to_hist) atomicSub(&sm.hist[km], 1);
+                            }
+                            if (d[t] & 0x10000000u) {
+                                const uint32_t km = (d[t] >> 16) & 0xFFFu;
+                                sm.delta[slot++] = (uint16_t)(km | tag | 0x8000u);
+                                if (to_hist) atomicAdd(&sm.hist[km], 1);
+                            }
+                        }
+                        if (dt) atomicAdd(&sm.dtot[jj], dt);
                     }
                 }
                 __syncthreads();
@@ -180,28 +277,34 @@ __global__ void __launch_bounds__(PR_NT, 4) prep_kernel(const ProfParams p, cons
             if (tid == 0) {
                 PrepMeta mt;
                 mt.n_delta = 0; mt.total0 = 0; mt.base_total = 0; mt.flags = 1; mt.pad = 0;
-                for (int j = 0; j < PC_DENSE; ++j) mt.dtot[j] = 0;
+                for (int q = 0; q < PC_DENSE; ++q) mt.dtot[q] = 0;
                 meta[item] = mt;
                 if (p.status) atomicOr(p.status + item, 2);
                 atomicAdd(p.work_counter + 1, 1ull);
             }
-            continue;
+        } else {
+            // ---- hand over: slot 0's histogram, the delta list, the totals ----
+            const int n_delta = sm.n_delta;
+            for (int i = tid; i < PC_F / 8; i += PR_NT) {   // 8 bins -> one 16-byte store of uint16 counts (every count <= 20 480)
+                const int4 lo = reinterpret_cast<const int4*>(sm.hist)[2 * i], hi = reinterpret_cast<const int4*>(sm.hist)[2 * i + 1];
+                hist_out[(size_t)item * (PC_F / 8) + i] = make_uint4((uint32_t)lo.x | ((uint32_t)lo.y << 16), (uint32_t)lo.z | ((uint32_t)lo.w << 16),
+                                                                     (uint32_t)hi.x | ((uint32_t)hi.y << 16), (uint32_t)hi.z | ((uint32_t)hi.w << 16));
+            }
+            const int nq = (n_delta * 2 + 15) >> 4;
+            for (int i = tid; i < nq; i += PR_NT) delta_out[(size_t)item * (PC_DELTA / 8) + i] = reinterpret_cast<const uint4*>(sm.delta)[i];
+            if (tid == 0) {
+                PrepMeta mt;
+                mt.n_delta = n_delta;
+                mt.base_total = PC_F * p.pseudocount + sm.nvalid;
+                mt.total0 = mt.base_total + (slot0_dense ? sm.dtot[0] : 0);
+                mt.flags = 0; mt.pad = 0;
+                for (int q = 0; q < PC_DENSE; ++q) mt.dtot[q] = sm.dtot[q];
+                meta[item] = mt;
+            }
         }
-        // ---- hand over: slot 0's histogram, the delta list, the totals ----
-        const int n_delta = sm.n_delta;
-        for (int i = tid; i < PC_F / 8; i += PR_NT) hist_out[(size_t)item * (PC_F / 8) + i] = reinterpret_cast<const uint4*>(sm.hist)[i];
-        const int nq = (n_delta * 2 + 15) >> 4;
-        for (int i = tid; i < nq; i += PR_NT) delta_out[(size_t)item * (PC_DELTA / 8) + i] = reinterpret_cast<const uint4*>(sm.delta)[i];
-        if (tid == 0) {
-            PrepMeta mt;
-            mt.n_delta = n_delta;
-            mt.base_total = PC_F * p.pseudocount + sm.nvalid;
-            mt.total0 = mt.base_total + (slot0_dense ? sm.dtot[0] : 0);
-            mt.flags = 0; mt.pad = 0;
-            for (int j = 0; j < PC_DENSE; ++j) mt.dtot[j] = sm.dtot[j];
-            meta[item] = mt;
-        }
+        cur = nxt; nxt = nn;
     }
+    cp_async_wait<0>();
 }
 
 // StandardScaler statistics (idelucs/utils.py:354-359) of the prepared slot-0 rows: float32(count / total) per bin

@@ -12,6 +12,8 @@ from ._lib import (KIND_BOTH, KIND_CLEAN, KIND_EXPLICIT, KIND_RANDOM_N, KIND_TRA
 _OUT_DTYPE = {OUT_COUNTS_I32: torch.int32, OUT_FREQ_F32: torch.float32, OUT_STD_F32: torch.float32,
               OUT_FREQ_F64: torch.float64}
 
+LONG_MIN = 65536   # items at least this long take the chunked path (csrc/chunked.cuh)
+
 # hard-coded rates of the reference's AugmentFasta (idelucs/utils.py:330-349)
 P_TRANSITION, P_TRANSVERSION, N_RANDOM_N = 1e-2, 0.5e-2, 20
 
@@ -147,10 +149,11 @@ def prepare(seqset, k, variants, seed=0, seq_id0=0, pseudocount=1, want_stats=Tr
 
 def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_off=None, out_stride=None,
              mean=None, scale=None, sidx=None, sel=None, S=None, edit_lists=None, seq_id0=0, pseudocount=None,
-             accumulate=False, status=None, prepared=None):
+             accumulate=False, status=None, prepared=None, chunked=None):
     """Run K2+K3.  Default output: tensor [S, n_items, 4^k] (variant-major) of the out_kind's
     dtype.  See include/idelucs_b200.h::idl_profiles for the argument meaning.  ``prepared`` (from ``prepare`` with the
-    same SeqSet / variants / seed / seq_id0) routes float32 outputs through idl_profiles_prepared (k = 6 fast path)."""
+    same SeqSet / variants / seed / seq_id0) routes float32 outputs through idl_profiles_prepared (k = 6 fast path).  Sets with
+    sequences of >= 65 536 bases go through idl_profiles_chunked (k = 6; chunked=False forces the generic kernel)."""
     lib = _lib.load()
     device = seqset.device
     F = 4 ** k
@@ -181,6 +184,19 @@ def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_o
                 int(out_stride), int(pseudocount), _lib.ptr(mean), _lib.ptr(scale), _lib.ptr(status), _lib.ptr(prepared.buf),
                 prepared.buf.numel(), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
             return out
+        # long sequences (>= 65 536 bases, k = 6): tiles shared by the whole grid instead of one CTA per sequence
+        n_long = int((seqset.lengths >= LONG_MIN).sum()) if (k == 6 and sidx is None and chunked is not False) else 0
+        if n_long > 0:
+            nbytes = lib.idl_profiles_chunked_bytes(n_items, n_long, varr, nv, S)
+            if nbytes > 0:
+                scratch = _workspace(device, nbytes, "chunk")
+                _lib.check(lib.idl_profiles_chunked(
+                    _lib.ptr(seqset.codes), _lib.ptr(seqset.nmask), _lib.ptr(seqset.chunk_off), _lib.ptr(seqset.len), seqset.n,
+                    None, n_items, int(seq_id0), k, varr, nv, _lib.ptr(sel), S, ctypes.c_uint64(seed & (2 ** 64 - 1)),
+                    _lib.ptr(d_eoff), _lib.ptr(d_ent), out_kind, _lib.ptr(out), offs, int(out_stride), int(pseudocount),
+                    1 if accumulate else 0, _lib.ptr(mean), _lib.ptr(scale), _lib.ptr(scratch), scratch.numel(), n_long,
+                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+                return out
         _lib.check(lib.idl_profiles(
             _lib.ptr(seqset.codes), _lib.ptr(seqset.nmask), _lib.ptr(seqset.chunk_off), _lib.ptr(seqset.len), seqset.n,
             _lib.ptr(sidx), n_items, int(seq_id0), k, varr, nv, _lib.ptr(sel), S, ctypes.c_uint64(seed & (2 ** 64 - 1)),
@@ -195,6 +211,22 @@ def schedule_profiles(seqset, k, variants, out_kind=OUT_STD_F32, seed=0, seq_id0
     """The AugmentFasta computation on the device (idelucs/utils.py:330-366): statistics of variants[0]'s float32 frequencies
     -> every variant's profile (standardised with them when out_kind is OUT_STD_F32).  Returns (profiles, Scaler).
     fast=False keeps everything on the generic kernels (any k; the parity tests compare the two)."""
+    if fast and k == 6 and seqset.n > 0 and int(seqset.lengths.max()) >= LONG_MIN:
+        # long genomes (BASELINE configs[4]): integer counts of every slot through the chunked path (mutations generated once),
+        # then float32(count / total) (idl_normalize_counts: the reference's float64 division + cast), statistics of slot 0,
+        # standardisation — all elementwise passes over a small [V, N, 4096] matrix
+        c = profiles(seqset, k, variants, out_kind=OUT_COUNTS_I32, seed=seed, seq_id0=seq_id0, pseudocount=1)
+        x = normalize_counts(c, want64=False, want32=True)
+        del c
+        sc = Scaler.fit(x[0], group=group)
+        if out_kind == OUT_STD_F32:
+            sc.transform32(x.view(-1, x.shape[-1]))
+        if out is not None:
+            F = x.shape[-1]
+            for s_i, o in enumerate(out_off):
+                torch.as_strided(out.view(-1), (x.shape[1], F), (int(out_stride), 1), int(o)).copy_(x[s_i])
+            return out, sc
+        return x, sc
     if fast and can_prepare(seqset, k, variants):
         prep = prepare(seqset, k, variants, seed=seed, seq_id0=seq_id0)
         sc = prep.scaler(group)

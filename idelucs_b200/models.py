@@ -11,7 +11,7 @@ import torch
 import torch.optim as optim
 
 from .LossFunctions import IID_loss, info_nce_loss
-from .PytorchUtils import NetLinear
+from .PytorchUtils import NetLinear, myNet
 from .utils import SequenceDataset, create_dataloader
 
 # idelucs/models.py:18-21 seeds the global generators at import; kept for drop-in behaviour
@@ -35,11 +35,19 @@ class IID_model(object):
         self.GT_file = args["GT_file"]
         self.n_clusters = args["n_clusters"]
         self.k = args["k"]
-        if args["model_size"] != "linear":
-            raise ValueError("only model_size='linear' (the CLI default) is on the round-1 path")
-        self.n_features = 4 ** self.k
-        self.reduce = False
-        self.net = NetLinear(self.n_features, args["n_clusters"])
+        if args["model_size"] == "linear":
+            self.n_features = 4 ** self.k
+            self.reduce = False
+            self.net = NetLinear(self.n_features, args["n_clusters"])
+        elif args["model_size"] == "small":   # canonical (reverse-complement folded) k-mers, idelucs/models.py:60-66
+            self.n_features = (4 ** self.k + 4 ** (self.k // 2)) // 2 if self.k % 2 == 0 else (4 ** self.k) // 2
+            self.reduce = True
+            self.net = myNet(self.n_features, args["n_clusters"])
+        elif args["model_size"] == "full":
+            raise ValueError("model_size='full' (ResNet18 on FCGR images, idelucs/models.py:68-69) is outside the featurisation hot path; "
+                             "use 'linear' or 'small'")
+        else:
+            raise ValueError("Invalid Model Type")
         self.net.apply(weights_init)
         self.net.to(device)
         self.epoch = 0

@@ -52,3 +52,15 @@ def all_gather_rows(x, counts, group=None):
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad, group=group)
     return torch.cat([o[: int(c)] for o, c in zip(out, counts)], dim=0)
+
+
+def all_gather_ragged(tensors, group=None):
+    """All-gather several row-aligned tensors (same number of rows on a rank, different across ranks): exchanges the row
+    counts once, then one padded all-gather per tensor.  Returns the rank-ordered concatenations (inference tail of
+    idelucs/models.py:164-171: predictions, probabilities and latent vectors of every sequence on every rank)."""
+    world = dist.get_world_size(group)
+    dev = tensors[0].device
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([tensors[0].shape[0]], dtype=torch.int64, device=dev), group=group)
+    counts = [int(c.item()) for c in counts]
+    return [all_gather_rows(t, counts, group) for t in tensors]

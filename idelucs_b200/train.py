@@ -46,6 +46,7 @@ class ShardedTrainer(object):
         self.gen = torch.Generator(device=self.dev).manual_seed(seed * 1000003 + seq_id0 + 1)
         self._graph = None
         self._ids = torch.zeros(batch_sz, dtype=torch.int64, device=self.dev)
+        self._perm, self._cursor, self.epoch = None, 0, 0
 
     def enable_cuda_graph(self, warmup=11):
         """Capture featurise -> forward x2 -> losses -> backward -> RMSprop in ONE CUDA graph: the
@@ -81,9 +82,24 @@ class ShardedTrainer(object):
                 self._graph = None
         return self._graph is not None
 
+    def _next_ids(self):
+        """the next batch of a shuffled epoch over this rank's pairs: every pair once per epoch, a fresh permutation per
+        epoch, the ragged tail dropped (DataLoader(shuffle=True) of idelucs/utils.py:427; the per-rank batch is fixed-size
+        because it feeds a captured CUDA graph)"""
+        n = self.loader.n_pairs
+        if n < self.batch_sz:   # degenerate shard: sample with replacement
+            return torch.randint(0, max(n, 1), (self.batch_sz,), device=self.dev, generator=self.gen)
+        if self._perm is None or self._cursor + self.batch_sz > n:
+            self._perm = torch.randperm(n, device=self.dev, generator=self.gen)
+            self._cursor = 0
+            self.epoch += 1
+        ids = self._perm[self._cursor:self._cursor + self.batch_sz]
+        self._cursor += self.batch_sz
+        return ids
+
     def step(self):
-        """one training step on a random batch of this rank's pairs; returns the loss tensor"""
-        self._ids.copy_(torch.randint(0, self.loader.n_pairs, (self.batch_sz,), device=self.dev, generator=self.gen))
+        """one training step on the next batch of this rank's shuffled pairs; returns the loss tensor"""
+        self._ids.copy_(self._next_ids())
         if self._graph is not None:
             self._graph.replay()
             return self._loss
@@ -113,17 +129,25 @@ class ShardedTrainer(object):
 
     @torch.no_grad()
     def predict(self, seqset, k=6, batch=4096):
-        """cluster assignments of this rank's shard, all-gathered in rank order (models.py:145-172)"""
+        """idelucs/models.py:145-172 over the sharded sequences: (y_pred int64[N], probabilities float32[N], latent
+        float32[N, 64]) of ALL sequences on every rank — each rank featurises and scores its own shard (clean float64
+        profiles, one StandardScaler over all shards), then the three row blocks are all-gathered in rank order."""
         from . import parallel
         f64 = ft.profiles(seqset, k, [ft.VariantSpec(ft.KIND_CLEAN)], out_kind=ft.OUT_FREQ_F64)[0]
         sc = ft.Scaler.fit(f64, group=dist.group.WORLD if self.world > 1 else None)
         x = sc.transform64(f64, want32=True)
         net = self.net
         net.eval()
-        preds = torch.cat([torch.max(net(x[b:b + batch])[0], 1)[1] for b in range(0, x.shape[0], batch)])
+        preds, probs, lats = [], [], []
+        for b in range(0, x.shape[0], batch):
+            out, lat = net(x[b:b + batch])
+            pr, pd = torch.max(out, 1)
+            preds.append(pd); probs.append(pr); lats.append(lat)
         net.train()
+        C = lats[0].shape[1] if lats else 64
+        preds = torch.cat(preds) if preds else torch.zeros(0, dtype=torch.int64, device=self.dev)
+        probs = torch.cat(probs) if probs else torch.zeros(0, dtype=torch.float32, device=self.dev)
+        lats = torch.cat(lats) if lats else torch.zeros((0, C), dtype=torch.float32, device=self.dev)
         if self.world > 1:
-            counts = [torch.zeros(1, dtype=torch.int64, device=self.dev) for _ in range(self.world)]
-            dist.all_gather(counts, torch.tensor([preds.shape[0]], dtype=torch.int64, device=self.dev))
-            preds = parallel.all_gather_rows(preds, [int(c.item()) for c in counts])
-        return preds
+            preds, probs, lats = parallel.all_gather_ragged([preds, probs, lats])
+        return preds, probs, lats

@@ -165,6 +165,45 @@ def kmersFasta(fname, k=6, transform=None, reduce=False):
     return list(ss.names), out[0].cpu().numpy()
 
 
+def reverse_complement(x, k):
+    """idelucs/utils.py:191-206: index of the reverse complement of k-mer index x (A0 C1 G2 T3, first base most significant)"""
+    x, r = (4 ** k - 1) - int(x), 0
+    for _ in range(k):
+        r = (r << 2) | (x & 3)
+        x >>= 2
+    return r
+
+
+def kmer_rev_comp(kmer_counts, k):
+    """idelucs/utils.py:208-221 on a host vector: canonical k-mers (kmer <= reverse complement, increasing) with
+    ``(c[kmer] + c[revcomp]) * 0.5`` written back IN PLACE like the reference (an integer array truncates the product);
+    returns the canonical entries.  Batches on the device: ``featurise.revcomp_fold``."""
+    index = []
+    for kmer in range(4 ** k):
+        rc = reverse_complement(kmer, k)
+        if kmer <= rc:
+            index.append(kmer)
+            kmer_counts[kmer] += kmer_counts[rc]
+            kmer_counts[kmer] *= 0.5
+    return kmer_counts[index]
+
+
+def cgrFasta(fname, k=6, transform=None):
+    """idelucs/utils.py:279-318 -> (names, float64[N, 4^k]): FCGR cell frequencies with the +1 pseudocount (the k-mer
+    profile of kmersFasta under the fixed cell permutation of idelucs/kmers.pyx:110-123)."""
+    ss = load_seqset(fname)
+    if transform is None:
+        variants, lists, seed = [ft.VariantSpec(ft.KIND_CLEAN)], None, 0
+    elif isinstance(transform, _DeviceTransform):
+        variants, lists, seed = [transform.spec(0)], None, _draw_seed()
+    else:
+        variants, lists, seed = [ft.VariantSpec(ft.KIND_EXPLICIT, explicit_idx=0)], _explicit_lists_from_callable(fname, ss, transform), 0
+    counts = ft.profiles(ss, k, variants, out_kind=ft.OUT_COUNTS_I32, seed=seed, edit_lists=lists, pseudocount=0)[0]
+    # the reference seeds the cell array with ones and cgr() adds the window counts (utils.py:292-295)
+    cells = ft.cgr_batch(counts, k, cgr=torch.ones_like(counts))
+    return list(ss.names), ft.normalize_counts(cells).cpu().numpy()
+
+
 def augment_device(ss, n_mimics, k=6, seed=None, group=None, seq_id0=0, reduce=False):
     """Device-resident AugmentFasta: returns (profiles float32 [n_mimics+1, N, 4^k] — slot 0 =
     t_norm, slot j = mimic j — standardised with the t_norm statistics, and the Scaler).
@@ -310,6 +349,41 @@ class SequenceDataset(torch.utils.data.Dataset):
         if self.GT:
             sample["cluster_id"] = self.GT[idx]
         return sample
+
+
+def label_features(predictions, n_clusters):
+    """Vote ensemble of idelucs/utils.py:582-602: k-means (k-means++, n_init=10) over the centred one-hot votes of the
+    voters; returns (labels, fuzzy membership maxima) — inverse squared distances to the centres, normalised per row."""
+    from sklearn.cluster import KMeans
+    from sklearn.metrics.pairwise import euclidean_distances
+    predictions = np.asarray(predictions)
+    n_v, n = predictions.shape
+    feats = np.zeros((n, n_v * n_clusters))
+    for v in range(n_v):
+        for j in range(n_clusters):
+            feats[predictions[v] == j, v * n_clusters + j] = 1.0
+    feats = feats - np.sum(feats, axis=0) / n
+    km = KMeans(n_clusters=n_clusters, init="k-means++", n_init=10)
+    y = km.fit_predict(feats)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        D = 1.0 / euclidean_distances(feats, km.cluster_centers_, squared=True)
+        D /= np.sum(D, axis=1)[:, np.newaxis]
+    return np.array(y), D.max(axis=1)
+
+
+def compute_results(y_pred, data, y_true=None):
+    """idelucs/utils.py:606-625: internal (and, with ground truth, external) clustering metrics -> (dict, assignment)."""
+    from sklearn import metrics
+    d = {"Davies-Boulding": metrics.davies_bouldin_score(data, y_pred), "Silhouette-Score": metrics.silhouette_score(data, y_pred)}
+    if y_true is not None:
+        d["NMI"] = metrics.adjusted_mutual_info_score(y_true, y_pred)
+        d["ARI"] = metrics.adjusted_rand_score(y_true, y_pred)
+        d["Homogeneity"] = metrics.homogeneity_score(y_true, y_pred)
+        d["Completeness"] = metrics.completeness_score(y_true, y_pred)
+        ind, acc = cluster_acc(y_true, y_pred)
+        d["ACC"] = acc
+        return d, ind
+    return d, None
 
 
 def cluster_acc(y_true, y_pred):

@@ -160,6 +160,24 @@ int idl_profiles_prepared(const uint32_t* d_codes, const uint32_t* d_nmask, cons
                           const float* d_mean, const float* d_scale, int32_t* d_status, const void* d_prep, size_t prep_bytes,
                           void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* idl_profiles for sets with LONG sequences (BASELINE configs[4]: Fungi-shaped genomes; the reference takes any length
+ * < 2^31, idelucs/kmers.pyx:14-16).  Same arguments and results as idl_profiles; with k = 6 the items of >= 65 536 bases are
+ * cut into 16 384-base tiles that the whole grid shares (window ends counted with k-1 bases of context, mutations of a tile
+ * generated with one 64-base block of context on each side), per-(CTA, item) int32 partial histograms in d_scratch and an
+ * exact second-stage reduction — no global atomics, no single CTA serialising a 2 Mb genome.  Shorter items (and other k)
+ * take the generic kernel in the same call.  d_scratch: idl_profiles_chunked_bytes(n_items, max_long_items, variants,
+ * n_variants, S) bytes, 16-byte aligned; max_long_items >= number of items with >= 65 536 bases (if the device finds
+ * more, the generic kernel computes them: same results).  At most 7 Bernoulli / explicit slots per item (else: 0 bytes /
+ * generic kernel). */
+size_t idl_profiles_chunked_bytes(int64_t n_items, int64_t max_long_items, const idl_variant* variants, int n_variants, int S);
+int idl_profiles_chunked(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,
+                         const int32_t* d_len, int64_t n_seqs_total, const int32_t* d_sidx, int64_t n_items,
+                         int64_t seq_id0, int k, const idl_variant* variants, int n_variants, const int32_t* d_sel,
+                         int S, uint64_t seed, const int64_t* d_edit_off, const uint32_t* d_edits, int out_kind,
+                         void* d_out, const int64_t* out_off, int64_t out_stride, int pseudocount, int accumulate,
+                         const float* d_mean, const float* d_scale, void* d_scratch, size_t scratch_bytes, int64_t max_long_items,
+                         void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Convenience form of the above for kmer_counts (idelucs/kmers.pyx:2-50): raw int32 counts
  * of every sequence into d_counts[n, 4^k] (accumulating when accumulate != 0). */
 int idl_kmer_counts(const uint32_t* d_codes, const uint32_t* d_nmask, const int64_t* d_chunk_off,

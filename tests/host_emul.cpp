@@ -4,6 +4,7 @@
 // Built by tests/test_host_emul.py with g++; not part of the product library.
 #include <algorithm>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "../idelucs_b200/csrc/core.cuh"
@@ -65,11 +66,24 @@ int emul_counts(const uint32_t* codes, const uint32_t* nmask, int L, int K, int*
 
 }  // extern "C"
 
+static long long g_entry_deltas_bad = 0;   // entry_deltas (register form) vs apply_entry (callback form), every entry ever applied
+
 template <int K>
 static int apply_k(const uint32_t* codes, const uint32_t* nmask, int L, const std::vector<uint32_t>& list, int* counts) {
     int d = 0;
-    for (int i = 0; i < (int)list.size(); ++i)
-        d += apply_entry<K>(codes, nmask, L, list.data(), (int)list.size(), i, [&](uint32_t kmer, int dd) { counts[kmer] += dd; });
+    for (int i = 0; i < (int)list.size(); ++i) {
+        std::vector<std::pair<uint32_t, int>> a, b;
+        const int di = apply_entry<K>(codes, nmask, L, list.data(), (int)list.size(), i, [&](uint32_t kmer, int dd) { counts[kmer] += dd; a.emplace_back(kmer, dd); });
+        d += di;
+        uint32_t reg[K];
+        int dt = 0;
+        const int cnt = entry_deltas<K>(codes, nmask, L, list.data(), (int)list.size(), i, reg, &dt);
+        for (int t = 0; t < K; ++t) {
+            if (reg[t] & 0x1000u) b.emplace_back(reg[t] & 0xFFFu, -1);
+            if (reg[t] & 0x10000000u) b.emplace_back((reg[t] >> 16) & 0xFFFu, +1);
+        }
+        if (a != b || cnt != (int)a.size() || dt != di) ++g_entry_deltas_bad;
+    }
     return d;
 }
 
@@ -171,6 +185,7 @@ int emul_masks_vs_slow(const uint32_t* codes, const uint32_t* nmask, int L, unsi
 }
 
 void emul_geometric_table(double p, uint32_t* out) { geometric_table(p, out); }
+long long emul_entry_deltas_mismatches() { return g_entry_deltas_bad; }
 
 void emul_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
     const U4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);

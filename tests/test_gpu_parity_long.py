@@ -103,6 +103,8 @@ def test_long_sequences_all_variant_kinds_vs_oracle(ft, SeqSet, k):
         v.rng_id = i
     want = _check_all_outputs(ft, ss, seqs, k, variants, seed=0xABCDEF12345, seq_id0=11, lists=lists, explicit=explicit)
     assert want[0, 0].sum() > 60000      # the long items really are long
+    if k == 6:   # k = 6 went through the chunked path (tiles + exact reduction); the generic kernel's int32 long path separately
+        _check_all_outputs(ft, ss, seqs, k, variants, seed=0xABCDEF12345, seq_id0=11, lists=lists, explicit=explicit, chunked=False)
     # selection mode on long items (pair batches: slot 0 + one mimic per item)
     sidx = torch.tensor([0, 2, 1, 0], dtype=torch.int32, device="cuda")
     sel = torch.tensor([[1, 2], [1, 4], [1, 6], [1, 3]], dtype=torch.int32, device="cuda")
@@ -162,3 +164,29 @@ def test_dominant_kernel_standardised_rows_vs_oracle_c3_slab(ft, SeqSet):
     # and the plain frequencies through the same fast path
     f32 = ft.profiles(ss, k, variants, out_kind=ft.OUT_FREQ_F32, seed=seed, seq_id0=5).cpu().numpy()
     assert np.array_equal(f32, w32)
+
+
+def test_chunked_path_many_genomes_equals_generic_and_oracle(ft, SeqSet):
+    """Fungi-shaped set (BASELINE configs[4]): lengths log-uniform over two orders of magnitude, so the tiles of one genome are
+    spread over several CTAs and several genomes share a CTA: chunked counts == generic kernel == oracle, all slots of the
+    reference schedule (n_mimics = 3) plus extra Random_N / clean slots; the statistics + standardised rows built from them"""
+    from idelucs_b200 import utils as U
+    rng = np.random.default_rng(77)
+    lens = np.exp(rng.uniform(np.log(20000), np.log(700000), size=40)).astype(int)
+    lens[[3, 17]] = [65536, 65537]
+    seqs = [_rand_seq(rng, int(L), n_rate=0.001) for L in lens]
+    ss = SeqSet.from_sequences(seqs)
+    variants = ft.mimic_schedule(3) + [ft.VariantSpec(ft.KIND_RANDOM_N, n_bp=20, rng_id=7), ft.VariantSpec(ft.KIND_CLEAN, rng_id=8)]
+    a = ft.profiles(ss, 6, variants, out_kind=ft.OUT_COUNTS_I32, seed=5, seq_id0=100)
+    b = ft.profiles(ss, 6, variants, out_kind=ft.OUT_COUNTS_I32, seed=5, seq_id0=100, chunked=False)
+    assert torch.equal(a, b)
+    idx = [0, 3, 17, int(np.argmax(lens)), int(np.argmin(lens))]
+    for i in idx:   # (_oracle_counts numbers its sequences from seq_id0: one call per item with the true id)
+        w = _oracle_counts([seqs[i]], 6, 5, variants, seq_id0=100 + i)[:, 0]
+        assert np.array_equal(a[:, i].cpu().numpy(), w), i
+    x, sc, _ = U.augment_device(ss, 3, k=6, seed=9)
+    f = ft.profiles(ss, 6, ft.mimic_schedule(3), out_kind=ft.OUT_FREQ_F32, seed=9, chunked=False)
+    scg = ft.Scaler.fit(f[0])
+    assert torch.allclose(sc.mean64, scg.mean64, rtol=1e-12, atol=0) and torch.allclose(sc.scale64, scg.scale64, rtol=1e-9, atol=0)
+    xg = ft.profiles(ss, 6, ft.mimic_schedule(3), out_kind=ft.OUT_STD_F32, seed=9, mean=sc.mean32, scale=sc.scale32, chunked=False)
+    assert torch.equal(x, xg)

@@ -245,3 +245,17 @@ def test_mask_block_generator_equals_stream_walk(emul):
                 assert bad == 0, (L, p1, kind, seq_id)
                 biggest = max(biggest, mx.value)
     assert biggest == 64   # p = 1: every base of a block is edited
+
+
+def test_entry_deltas_register_form_equals_callback_form(emul):
+    """entry_deltas (the prepare kernel's single-evaluation form: deltas returned in registers) produced exactly the
+    +-1 updates of apply_entry for every edit-list entry the tests above pushed through the emulation, plus a dense run"""
+    rng = np.random.default_rng(5)
+    for L, p1, p2 in [(3000, 0.2, 0.1), (500, 0.5, 0.5), (64, 1.0, 0.0)]:
+        s = rand_seq(rng, L, 0.02)
+        codes, nmask, _ = pack(emul, s)
+        for k in (4, 5, 6):
+            c, _ = counts(emul, codes, nmask, L, k)
+            variant(emul, codes, nmask, L, k, 7, 1, 0, orc.KIND_BOTH, p1=p1, p2=p2)
+    emul.emul_entry_deltas_mismatches.restype = ctypes.c_longlong
+    assert emul.emul_entry_deltas_mismatches() == 0
