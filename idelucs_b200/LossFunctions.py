@@ -1,8 +1,8 @@
 """Loss functions with the reference's names and signatures (idelucs/LossFunctions.py).
 
-``IID_loss`` / ``compute_joint`` run the fused sm_100a kernel K5 (forward + backward in one
-cooperative launch) through the C ABI.  ``info_nce_loss`` is a dense 2B x 2B contraction
-and stays PyTorch/cuBLAS, as the scope contract says."""
+``IID_loss`` / ``compute_joint`` run the fused sm_100a kernel K5 (forward + backward in one launch) through the C ABI.
+``info_nce_loss`` runs the fused InfoNCE kernels (idl_info_nce: normalise, similarity, masked
+log-softmax, cross-entropy and the gradient in three launches) on CUDA tensors."""
 import sys
 
 import torch
@@ -66,8 +66,33 @@ def compute_joint(x_out, x_tf_out):
 _targets = {}
 
 
-def info_nce_loss_stacked(h, temperature):
-    """info_nce_loss on the two views already stacked as one [2n, d] tensor (rows 0..n-1 = first view)."""
+class _InfoNCE(torch.autograd.Function):
+    """fused CUDA form (idl_info_nce): value and gradient with respect to the stacked latent in three launches"""
+
+    @staticmethod
+    def forward(ctx, h, temperature):
+        lib = _lib.load()
+        x = h.detach().contiguous().float()
+        n2, D = x.shape
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        dh = torch.empty_like(x)
+        from .featurise import _workspace
+        with torch.cuda.device(x.device):
+            ws = _workspace(x.device, lib.idl_info_nce_workspace_bytes(n2, D), "nce%d_%d" % (n2, D))
+            _lib.check(lib.idl_info_nce(_lib.ptr(x), n2, D, float(temperature), _lib.ptr(loss), _lib.ptr(dh), _lib.ptr(ws), ws.numel(),
+                                        _lib.stream_ptr()))
+        ctx.save_for_backward(dh)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dh,) = ctx.saved_tensors
+        return grad_out * dh, None
+
+
+def _info_nce_torch(h, temperature):
+    """mask-gather-free PyTorch formulation (any device / width): cross-entropy of the self-masked similarity rows against
+    the index of the other view == the reference's [positive, negatives] gather with label 0"""
     n2 = h.shape[0]
     feats = F.normalize(h.float(), dim=1)
     logits = (feats @ feats.T) / temperature
@@ -79,9 +104,16 @@ def info_nce_loss_stacked(h, temperature):
     return F.cross_entropy(logits, _targets[key])
 
 
+def info_nce_loss_stacked(h, temperature):
+    """info_nce_loss on the two views already stacked as one [2n, d] tensor (rows 0..n-1 = first view).  CUDA tensors with a
+    latent width of 32 / 64 / 128 (the reference's encoders have 64) take the fused kernels; anything else the PyTorch form."""
+    if h.is_cuda and h.dim() == 2 and h.shape[1] in (32, 64, 128) and h.shape[0] % 2 == 0 and h.shape[0] >= 2:
+        return _InfoNCE.apply(h, temperature)
+    return _info_nce_torch(h, temperature)
+
+
 def info_nce_loss(z1, z2, temperature):
-    """SimCLR NT-Xent (idelucs/LossFunctions.py:65-98).  The reference gathers [positive,
-    negatives] per row with boolean masks and takes cross-entropy against label 0; that equals
-    the cross-entropy of the self-masked similarity row against the index of the other view,
-    which needs no mask gathers (and no host synchronisation)."""
+    """SimCLR NT-Xent (idelucs/LossFunctions.py:65-98).  The reference gathers [positive, negatives] per row with boolean
+    masks and takes cross-entropy against label 0; that equals the cross-entropy of the self-masked similarity row against
+    the index of the other view, which needs no mask gathers (and no host synchronisation)."""
     return info_nce_loss_stacked(torch.cat((z1, z2), 0), temperature)

@@ -1,4 +1,5 @@
-// idelucs_b200 — K5: IIC mutual-information loss, forward + backward in ONE cooperative launch.
+// idelucs_b200 — K5: IIC mutual-information loss, forward + backward in ONE launch (cooperative for C > 16; C <= 16 takes
+// the single-CTA kernel of train_ops.cu).
 //
 // Replaces idelucs/LossFunctions.py:20-62 (IID_loss -> compute_joint) and its autograd
 // backward.  The reference materialises a [B, C, C] broadcast product (82 MB at C=200) and
@@ -251,6 +252,8 @@ int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb,
     if (!d_z1 || !d_z2 || !d_workspace || B < 1 || C < 1) return set_error(IDL_EINVAL, "idl_iid_loss: bad argument%s", "");
     if (C > LMAXC) return set_error(IDL_EUNSUPPORTED, "idl_iid_loss: n_clusters > 256 not supported%s (got %lld)", "", C);
     if (workspace_bytes < idl_iid_loss_workspace_bytes(C)) return set_error(IDL_EINVAL, "idl_iid_loss: workspace too small%s", "");
+    // the usual configurations (n_clusters = 3 .. 12) have a joint of at most 16 x 16: one ordinary CTA, no grid barriers
+    if (C <= IID_SMALL_MAXC) return iid_loss_small_launch(d_z1, d_z2, B, C, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, stream);
     LossParams p;
     p.z1 = d_z1; p.z2 = d_z2; p.B = B; p.C = C;
     p.nt = (C + LT - 1) / LT; p.npairs = p.nt * (p.nt + 1) / 2;

@@ -1,0 +1,358 @@
+// idelucs_b200 — the small latency-bound pieces of the training step that sit between the hot-path kernels and the
+// PyTorch/cuBLAS MLP (idelucs/models.py:113-143), each one launch instead of a dozen framework kernels:
+//
+//   * idl_info_nce      InfoNCE / NT-Xent of idelucs/LossFunctions.py:65-98 on the stacked latent [2B, D]: row normalisation,
+//                       the 2B x 2B similarity (never materialised: D = 64, the whole contraction is 67 MFLOP), self-masked
+//                       log-sum-exp, cross-entropy against the other view, and the closed-form gradient back to the latent —
+//                       three launches (normalise / log-sum-exp / gradient), fixed-order reductions (run-to-run identical)
+//   * iid_loss_small    the IIC loss (LossFunctions.py:20-62) for C <= 16 clusters in ONE ordinary CTA (no cooperative launch,
+//                       no grid barriers): the headline configuration has C = 5, i.e. a 5 x 5 joint
+//   * idl_rmsprop_step  torch.optim.RMSprop's update (alpha, eps, weight_decay; no momentum, not centred — what
+//                       idelucs/models.py:86 constructs) on a flat parameter shard in one elementwise pass, so that a
+//                       data-parallel step can reduce-scatter the gradient, update 1/N of the parameters per rank and
+//                       all-gather them
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "common.h"
+
+namespace idl {
+
+// ---------------------------------------------------------------------------------------------------------------
+// InfoNCE
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int NCE_NT = 256;          // 8 warps: warp <-> row
+constexpr int NCE_RB = NCE_NT / 32;  // rows per CTA
+constexpr int NCE_TJ = 32;           // rows of the other operand per tile (lane <-> row)
+constexpr int NCE_MAXD = 128;
+
+// F.normalize(x, dim=1): x / max(||x||_2, 1e-12)
+__global__ void __launch_bounds__(NCE_NT) nce_normalize_kernel(const float* __restrict__ h, int n2, int D, float* __restrict__ fn,
+                                                                float* __restrict__ inv_norm) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * NCE_RB + (threadIdx.x >> 5);
+    if (row >= n2) return;
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { const float v = h[(size_t)row * D + d]; ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int d = lane; d < D; d += 32) fn[(size_t)row * D + d] = h[(size_t)row * D + d] * inv;
+    if (lane == 0) inv_norm[row] = inv;
+}
+
+// lse_i = log sum_{j != i} exp(fn_i . fn_j / T) and the row's loss term lse_i - fn_i . fn_pos(i) / T.
+// |s| <= 1/T, so exp(s) needs no running maximum (T = 0.85: e^-1.18 .. e^1.18).
+template <int D>
+__global__ void __launch_bounds__(NCE_NT) nce_lse_kernel(const float* __restrict__ fn, int n2, float inv_t, float* __restrict__ lse,
+                                                          float* __restrict__ rowloss) {
+    __shared__ float si[NCE_RB][D];
+    __shared__ float sj[NCE_TJ][D + 1];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int i = blockIdx.x * NCE_RB + w;
+    const int half = n2 >> 1;
+    for (int q = tid; q < NCE_RB * D; q += NCE_NT) {
+        const int r = q / D, d = q - r * D;
+        const int row = blockIdx.x * NCE_RB + r;
+        si[r][d] = row < n2 ? fn[(size_t)row * D + d] : 0.f;
+    }
+    float sum = 0.f, spos = 0.f;
+    const int pos = i < half ? i + half : i - half;
+    for (int j0 = 0; j0 < n2; j0 += NCE_TJ) {
+        __syncthreads();
+        for (int q = tid; q < NCE_TJ * D; q += NCE_NT) {
+            const int r = q / D, d = q - r * D;
+            sj[r][d] = j0 + r < n2 ? fn[(size_t)(j0 + r) * D + d] : 0.f;
+        }
+        __syncthreads();
+        const int j = j0 + lane;
+        float s = 0.f;
+#pragma unroll 16
+        for (int d = 0; d < D; ++d) s = fmaf(si[w][d], sj[lane][d], s);
+        s *= inv_t;
+        if (j < n2 && j != i && i < n2) {
+            sum += __expf(s) * 1.0f;
+            if (j == pos) spos = s;
+        }
+    }
+    // fixed-order warp reduction: lanes 0..31 summed by a shuffle tree (same tree every run)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); spos += __shfl_xor_sync(0xffffffffu, spos, o); }
+    if (lane == 0 && i < n2) {
+        const float l = logf(sum);
+        lse[i] = l;
+        rowloss[i] = l - spos;
+    }
+}
+
+// d loss / d h: dfn_i = (1 / (n2 T)) [ sum_{j != i} (P_ij + P_ji) fn_j - 2 fn_pos(i) ],  P_ij = exp(s_ij - lse_i);
+// then through the normalisation: dh_i = inv_i (dfn_i - fn_i (fn_i . dfn_i)).  Block 0 also reduces the loss.
+template <int D>
+__global__ void __launch_bounds__(NCE_NT) nce_grad_kernel(const float* __restrict__ fn, const float* __restrict__ inv_norm, const float* __restrict__ lse,
+                                                           const float* __restrict__ rowloss, int n2, float inv_t, float* __restrict__ loss,
+                                                           float* __restrict__ dh) {
+    __shared__ float si[NCE_RB][D];
+    __shared__ float sj[NCE_TJ][D + 1];
+    __shared__ float slse[NCE_TJ];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int i = blockIdx.x * NCE_RB + w;
+    const int half = n2 >> 1;
+    for (int q = tid; q < NCE_RB * D; q += NCE_NT) {
+        const int r = q / D, d = q - r * D;
+        const int row = blockIdx.x * NCE_RB + r;
+        si[r][d] = row < n2 ? fn[(size_t)row * D + d] : 0.f;
+    }
+    const float lse_i = i < n2 ? lse[i] : 0.f;
+    const int pos = i < half ? i + half : i - half;
+    float acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = 0.f;
+    for (int j0 = 0; j0 < n2; j0 += NCE_TJ) {
+        __syncthreads();
+        for (int q = tid; q < NCE_TJ * D; q += NCE_NT) {
+            const int r = q / D, d = q - r * D;
+            sj[r][d] = j0 + r < n2 ? fn[(size_t)(j0 + r) * D + d] : 0.f;
+        }
+        if (tid < NCE_TJ) slse[tid] = j0 + tid < n2 ? lse[j0 + tid] : 0.f;
+        __syncthreads();
+        const int j = j0 + lane;
+        float s = 0.f;
+#pragma unroll 16
+        for (int d = 0; d < D; ++d) s = fmaf(si[w][d], sj[lane][d], s);
+        s *= inv_t;
+        float wgt = 0.f;
+        if (j < n2 && j != i && i < n2) {
+            wgt = __expf(s - lse_i) + __expf(s - slse[lane]);
+            if (j == pos) wgt -= 2.f;
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[d] = fmaf(wgt, sj[lane][d], acc[d]);
+    }
+    // reduce the lanes' partial vectors (fixed tree), lane d % 32 keeps dimension d
+    float mine[(D + 31) / 32];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        float v = acc[d];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((d & 31) == lane) mine[d >> 5] = v;
+    }
+    if (i < n2) {
+        const float scale = inv_t / (float)n2;
+        float dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < (D + 31) / 32; ++q) {
+            const int d = q * 32 + lane;
+            if (d < D) { mine[q] *= scale; dot = fmaf(si[w][d], mine[q], dot); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        const float inv = inv_norm[i];
+#pragma unroll
+        for (int q = 0; q < (D + 31) / 32; ++q) {
+            const int d = q * 32 + lane;
+            if (d < D) dh[(size_t)i * D + d] = inv * (mine[q] - si[w][d] * dot);
+        }
+    }
+    if (blockIdx.x == 0 && w == 0 && loss) {   // mean of the row terms, fixed order
+        float l = 0.f;
+        for (int r = lane; r < n2; r += 32) l += rowloss[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        if (lane == 0) *loss = l / (float)n2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// IIC loss, C <= 16: one CTA
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int IS_NT = 512;
+constexpr int IS_MAXC = 16;
+
+__global__ void __launch_bounds__(IS_NT) iid_loss_small_kernel(const float* __restrict__ z1, const float* __restrict__ z2, int B, int C, float lamb,
+                                                                float eps, float* __restrict__ loss, float* __restrict__ joint,
+                                                                float* __restrict__ dz1, float* __restrict__ dz2) {
+    __shared__ float part[IS_NT / 32][IS_MAXC * IS_MAXC];   // per-warp partial S
+    __shared__ float S[IS_MAXC][IS_MAXC + 1];               // S, then Ssym
+    __shared__ float dS[IS_MAXC][IS_MAXC + 1];
+    __shared__ float marg[IS_MAXC], corr[IS_MAXC], gvec[IS_MAXC];
+    __shared__ float red[4];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int np = C * C;
+    // ---- S_ij = sum_b z1[b,i] z2[b,j] (LossFunctions.py:54-58): warp <-> rows b = w, w+16, ...; lane <-> pairs ----
+    {
+        float a[IS_MAXC * IS_MAXC / 32];
+#pragma unroll
+        for (int q = 0; q < IS_MAXC * IS_MAXC / 32; ++q) a[q] = 0.f;
+        for (int b = w; b < B; b += IS_NT / 32) {
+#pragma unroll
+            for (int q = 0; q < IS_MAXC * IS_MAXC / 32; ++q) {
+                const int pr = lane + 32 * q;
+                if (pr < np) { const int i = pr / C, j = pr - i * C; a[q] = fmaf(__ldg(z1 + (size_t)b * C + i), __ldg(z2 + (size_t)b * C + j), a[q]); }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < IS_MAXC * IS_MAXC / 32; ++q) { const int pr = lane + 32 * q; if (pr < np) part[w][pr] = a[q]; }
+    }
+    __syncthreads();
+    if (tid < np) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < IS_NT / 32; ++g) s += part[g][tid];   // fixed order
+        S[tid / C][tid % C] = s;
+    }
+    __syncthreads();
+    // ---- symmetrise, normalise, marginals (:59-60, :28-34) — one warp, everything fits in a few registers ----
+    if (w == 0) {
+        float tot = 0.f;
+        for (int pr = lane; pr < np; pr += 32) { const int i = pr / C, j = pr - i * C; tot += (S[i][j] + S[j][i]) * 0.5f; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) red[0] = tot;
+    }
+    __syncthreads();
+    const float T = red[0];
+    float ssym = 0.f, P = 0.f;
+    int pi = 0, pj = 0;
+    if (tid < np) {
+        pi = tid / C; pj = tid - pi * C;
+        ssym = (S[pi][pj] + S[pj][pi]) * 0.5f;
+        P = ssym / T;
+    }
+    __syncthreads();
+    if (tid < np) S[pi][pj] = P;          // S now holds the normalised joint
+    __syncthreads();
+    if (tid < C) {
+        float m = 0.f, c = 0.f;
+        for (int j = 0; j < C; ++j) { const float v = S[tid][j]; m += v; if (v < eps) c += eps - v; }
+        marg[tid] = m; corr[tid] = c;
+    }
+    __syncthreads();
+    // ---- clamp, entropy terms (:36-44) and the pieces of the gradient ----
+    float term = 0.f, Aij = 0.f;
+    if (tid < np) {
+        const bool cl = P < eps;
+        const float Pc = cl ? eps : P;
+        const float pic = marg[pi] < eps ? eps : marg[pi], pjc = marg[pj] < eps ? eps : marg[pj];
+        const float inner = logf(Pc) - lamb * logf(pjc) - lamb * logf(pic);
+        term = -Pc * inner;
+        Aij = cl ? 0.f : (-inner - 1.f);
+        if (joint) joint[pi * C + pj] = P;
+    }
+    if (tid < C) {
+        const float m = marg[tid];
+        gvec[tid] = m < eps ? 0.f : lamb * (m + corr[tid]) / m;
+    }
+    // block sums of term and A.P (np <= 256 values: warps 0..7), fixed order
+    {
+        float t = term, ap = Aij * P;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { t += __shfl_xor_sync(0xffffffffu, t, o); ap += __shfl_xor_sync(0xffffffffu, ap, o); }
+        if (lane == 0) { part[w][0] = t; part[w][1] = ap; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float l = 0.f, ap = 0.f;
+        for (int g = 0; g < IS_NT / 32; ++g) { l += part[g][0]; ap += part[g][1]; }
+        float gp = ap;
+        for (int i = 0; i < C; ++i) gp += 2.f * gvec[i] * marg[i];
+        if (loss) *loss = l;
+        red[1] = gp;
+    }
+    __syncthreads();
+    if (!dz1 && !dz2) return;
+    if (tid < np) dS[pi][pj] = (Aij + gvec[pi] + gvec[pj] - red[1]) / T;   // dL/dSsym (symmetric)
+    __syncthreads();
+    // ---- dz1[b,i] = sum_j z2[b,j] dS[i,j];  dz2[b,j] = sum_i z1[b,i] dS[i,j] ----
+    for (int q = tid; q < B * C; q += IS_NT) {
+        const int b = q / C, c = q - b * C;
+        float a1 = 0.f, a2 = 0.f;
+        for (int j = 0; j < C; ++j) {
+            const float d = dS[c][j];
+            a1 = fmaf(__ldg(z2 + (size_t)b * C + j), d, a1);
+            a2 = fmaf(__ldg(z1 + (size_t)b * C + j), d, a2);
+        }
+        if (dz1) dz1[q] = a1;
+        if (dz2) dz2[q] = a2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// RMSprop (torch.optim.RMSprop, momentum = 0, centered = False): g = grad * gscale + wd * p; v = alpha v + (1 - alpha) g^2;
+// p -= lr * g / (sqrt(v) + eps)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v, long long n, float lr, float alpha,
+                               float eps, float wd, float gscale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float pp = p[i];
+        const float gg = fmaf(wd, pp, g[i] * gscale);
+        const float vv = fmaf(1.0f - alpha, gg * gg, alpha * v[i]);
+        v[i] = vv;
+        p[i] = pp - lr * (gg / (sqrtf(vv) + eps));
+    }
+}
+
+// C <= 16: called by idl_iid_loss (iid_loss.cu)
+int iid_loss_small_launch(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float* d_loss, float* d_joint, float* d_dz1,
+                          float* d_dz2, void* stream) {
+    iid_loss_small_kernel<<<1, IS_NT, 0, (cudaStream_t)stream>>>(d_z1, d_z2, B, C, lamb, eps, d_loss, d_joint, d_dz1, d_dz2); note_launch();
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
+}
+
+}  // namespace idl
+
+using namespace idl;
+
+extern "C" {
+
+size_t idl_info_nce_workspace_bytes(int n2, int D) {
+    if (n2 < 2 || D < 1 || D > NCE_MAXD) return 0;
+    return sizeof(float) * ((size_t)n2 * D + 3 * (size_t)n2) + 64;
+}
+
+int idl_info_nce(const float* d_h, int n2, int D, float temperature, float* d_loss, float* d_dh, void* d_workspace, size_t workspace_bytes,
+                 void* stream) {
+    if (!d_h || !d_workspace || n2 < 2 || (n2 & 1) || !(temperature > 0.f)) return set_error(IDL_EINVAL, "idl_info_nce: bad argument%s", "");
+    if (D != 32 && D != 64 && D != 128) return set_error(IDL_EUNSUPPORTED, "idl_info_nce: latent width must be 32, 64 or 128%s (got %lld)", "", D);
+    if (workspace_bytes < idl_info_nce_workspace_bytes(n2, D)) return set_error(IDL_EINVAL, "idl_info_nce: workspace too small%s", "");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* fn = reinterpret_cast<float*>(d_workspace);
+    float* inv = fn + (size_t)n2 * D;
+    float* lse = inv + n2;
+    float* rowloss = lse + n2;
+    const int grid = (n2 + NCE_RB - 1) / NCE_RB;
+    const float inv_t = 1.0f / temperature;
+    nce_normalize_kernel<<<grid, NCE_NT, 0, st>>>(d_h, n2, D, fn, inv); note_launch();
+    switch (D) {
+        case 32: nce_lse_kernel<32><<<grid, NCE_NT, 0, st>>>(fn, n2, inv_t, lse, rowloss); break;
+        case 64: nce_lse_kernel<64><<<grid, NCE_NT, 0, st>>>(fn, n2, inv_t, lse, rowloss); break;
+        default: nce_lse_kernel<128><<<grid, NCE_NT, 0, st>>>(fn, n2, inv_t, lse, rowloss); break;
+    }
+    note_launch();
+    if (d_dh) {
+        switch (D) {
+            case 32: nce_grad_kernel<32><<<grid, NCE_NT, 0, st>>>(fn, inv, lse, rowloss, n2, inv_t, d_loss, d_dh); break;
+            case 64: nce_grad_kernel<64><<<grid, NCE_NT, 0, st>>>(fn, inv, lse, rowloss, n2, inv_t, d_loss, d_dh); break;
+            default: nce_grad_kernel<128><<<grid, NCE_NT, 0, st>>>(fn, inv, lse, rowloss, n2, inv_t, d_loss, d_dh); break;
+        }
+        note_launch();
+    } else if (d_loss) {
+        return set_error(IDL_EINVAL, "idl_info_nce: the loss is reduced by the gradient kernel; pass d_dh%s", "");
+    }
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
+}
+
+int idl_rmsprop_step(float* d_param, const float* d_grad, float* d_square_avg, int64_t n, float lr, float alpha, float eps, float weight_decay,
+                     float grad_scale, void* stream) {
+    if (!d_param || !d_grad || !d_square_avg || n < 0) return set_error(IDL_EINVAL, "idl_rmsprop_step: bad argument%s", "");
+    if (n == 0) return IDL_OK;
+    long long grid = (n + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    rmsprop_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_param, d_grad, d_square_avg, n, lr, alpha, eps, weight_decay, grad_scale); note_launch();
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
+}
+
+}  // extern "C"

@@ -5,9 +5,10 @@ Each rank owns a contiguous shard of the packed sequences, regenerates its pair 
 the fly with the mimic kernel (selection mode — the 1.6 TB x_train of the reference never
 exists), runs the reference's training step (idelucs/models.py:113-143: two forwards,
 (1-w) InfoNCE + w IIC loss, backward, RMSprop) with the fused IIC kernel, and all-reduces the
-gradients of the data-parallel MLP replicas over NCCL: the replicas' .grad tensors are views into ONE flat
-buffer, averaged by a single all-reduce per step (8.5 MB at k=6) that is captured in the step's CUDA graph
-together with everything else.  batch_sz is PER RANK (weak scaling in the batch, strong in the data set)."""
+gradients of the data-parallel MLP replicas over NCCL: parameters, gradients and the RMSprop state live in flat buffers;
+per step one reduce-scatter of the gradient (8.5 MB at k=6), the optimiser on this rank's shard (idl_rmsprop_step) and one
+all-gather of the parameters, all captured in the step's CUDA graph; the next pair batch is regenerated on a side stream
+under them.  batch_sz is PER RANK (weak scaling in the batch, strong in the data set)."""
 import torch
 import torch.distributed as dist
 
@@ -18,11 +19,22 @@ from .models import weights_init
 
 
 class ShardedTrainer(object):
+    """Data-parallel replica of the reference's training step (idelucs/models.py:113-143) fed by the mimic kernel.
+
+    Step layout (captured in ONE CUDA graph, two streams):
+      side stream  pair batch t+1 regenerated from the packed sequences (selection mode of idl_profiles) — independent of
+                   the weights, so it runs under the collectives of step t;
+      main stream  forward over the stacked [2B, F] batch t -> fused InfoNCE + fused IIC loss -> backward into ONE flat
+                   gradient buffer -> reduce-scatter (AVG) -> idl_rmsprop_step on this rank's 1/N of the flat parameters
+                   -> all-gather of the parameters.  At N = 1 the collectives vanish and the optimiser is one pass.
+    The parameters of the network are views into one flat buffer, so the optimiser and the collectives see one tensor."""
+
     def __init__(self, seqset, k=6, n_clusters=5, n_mimics=50, batch_sz=512, lamb=2.8, weight=0.25, lr=1e-3, seed=0,
-                 seq_id0=0, world=1, materialize_bytes=0):
+                 seq_id0=0, world=1, materialize_bytes=0, alpha=0.99, eps=1e-8, weight_decay=0.01):
         from .utils import PairBatchLoader
         self.dev = seqset.device
         self.world = world
+        self.rank = dist.get_rank() if world > 1 else 0
         group = dist.group.WORLD if world > 1 else None
         self.loader = PairBatchLoader(seqset, n_mimics, k=k, batch_size=batch_sz, seed=seed, group=group, seq_id0=seq_id0,
                                       materialize_bytes=materialize_bytes, drop_last=True)
@@ -31,33 +43,59 @@ class ShardedTrainer(object):
         net.apply(weights_init)
         net.to(self.dev)
         self.net = net
-        self._flat_grad = None
-        if world > 1:   # identical replicas (same seed); gradients live in one flat buffer = one NCCL call per step
-            params = [p for p in net.parameters() if p.requires_grad]
-            self._flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=self.dev)
-            o = 0
-            for p in params:
-                p.grad = self._flat_grad[o:o + p.numel()].view_as(p)
-                o += p.numel()
-            for p in params:   # replicas must start identical whatever the RNG state of the rank was
-                dist.broadcast(p.data, src=0)
-        self.opt = torch.optim.RMSprop(self.net.parameters(), lr=lr, weight_decay=0.01, capturable=True)
+        # ---- flat parameter / gradient / second-moment buffers (padded to a multiple of 4 * world elements) ----
+        params = [p for p in net.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in params)
+        self._n = n
+        pad = (-n) % (4 * world)
+        self._flat_param = torch.zeros(n + pad, dtype=torch.float32, device=self.dev)
+        self._flat_grad = torch.zeros(n + pad, dtype=torch.float32, device=self.dev)
+        o = 0
+        for p in params:
+            self._flat_param[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self._flat_param[o:o + p.numel()].view_as(p)
+            p.grad = self._flat_grad[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        if world > 1:   # replicas must start identical whatever the RNG state of the rank was
+            dist.broadcast(self._flat_param, src=0)
+        self._shard = (n + pad) // world
+        self._sq = torch.zeros(self._shard, dtype=torch.float32, device=self.dev)
+        self._grad_shard = torch.zeros(self._shard, dtype=torch.float32, device=self.dev) if world > 1 else None
+        self.lr, self.alpha, self.eps, self.weight_decay = lr, alpha, eps, weight_decay
         self.lamb, self.weight, self.batch_sz = lamb, weight, batch_sz
         self.gen = torch.Generator(device=self.dev).manual_seed(seed * 1000003 + seq_id0 + 1)
         self._graph = None
-        self._ids = torch.zeros(batch_sz, dtype=torch.int64, device=self.dev)
+        self._ids = torch.zeros(batch_sz, dtype=torch.int64, device=self.dev)       # pair ids of the NEXT batch (graph input)
         self._perm, self._cursor, self.epoch = None, 0, 0
+        self._side = torch.cuda.Stream(device=self.dev)
+        self._batch = None       # the batch the next step consumes (featurised by the previous step; static buffer once created)
+
+    # ---- optimiser: torch.optim.RMSprop's arithmetic on the flat shard (idl_rmsprop_step) ----
+    def _optimizer_step(self):
+        from . import _lib
+        lib = _lib.load()
+        if self.world > 1:
+            dist.reduce_scatter_tensor(self._grad_shard, self._flat_grad, op=dist.ReduceOp.AVG)
+            g = self._grad_shard
+            p = self._flat_param[self.rank * self._shard:(self.rank + 1) * self._shard]
+        else:
+            g, p = self._flat_grad, self._flat_param
+        with torch.cuda.device(self.dev):
+            _lib.check(lib.idl_rmsprop_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(self._sq), self._shard, self.lr, self.alpha, self.eps,
+                                            self.weight_decay, 1.0, _lib.stream_ptr()))
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._flat_param, p)
 
     def enable_cuda_graph(self, warmup=11):
-        """Capture featurise -> forward x2 -> losses -> backward -> RMSprop in ONE CUDA graph: the
-        step is launch-bound (~100 small kernels), so replaying a graph removes the host from the
-        loop.  The pair ids are the only input (static buffer filled before every replay).
+        """Capture the whole step (both streams) in ONE CUDA graph: the step is launch-bound, so replaying a graph removes the
+        host from the loop.  The pair ids of the next batch are the only input (static buffer filled before every replay).
         Returns False (and stays eager) if capture is not possible."""
         try:
             s = torch.cuda.Stream(device=self.dev)
             s.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(s):
                 for _ in range(warmup):
+                    self._ids.copy_(self._next_ids())
                     self._step_from_ids()
             torch.cuda.current_stream(self.dev).wait_stream(s)
             g = torch.cuda.CUDAGraph()
@@ -97,8 +135,17 @@ class ShardedTrainer(object):
         self._cursor += self.batch_sz
         return ids
 
+    def _featurise(self, ids):
+        """pair batch as one stacked [2B, F] tensor (rows 0..B-1 = 'true' side)"""
+        batch = self.loader.batch(ids)
+        if "both" in batch:
+            return batch["both"]
+        return torch.cat((batch["true"], batch["modified"]), 0)
+
     def step(self):
         """one training step on the next batch of this rank's shuffled pairs; returns the loss tensor"""
+        if self._batch is None:   # the very first batch has no previous step to featurise it
+            self._batch = self._featurise(self._next_ids()).clone()
         self._ids.copy_(self._next_ids())
         if self._graph is not None:
             self._graph.replay()
@@ -106,25 +153,23 @@ class ShardedTrainer(object):
         return self._step_from_ids()
 
     def _step_from_ids(self):
-        batch = self.loader.batch(self._ids)
-        if self._flat_grad is None:
-            self.opt.zero_grad(set_to_none=True)
-        else:
-            self._flat_grad.zero_()
-        if "both" in batch:   # one pass over the stacked [2B, F] batch: same per-row math as the reference's two forwards
-            B = batch["true"].shape[0]   # (models.py:121-122; dropout masks are independent per row either way), half the launches
-            z, h = self.net(batch["both"])
-            nce = info_nce_loss_stacked(h, 0.85)
-            z1, z2 = z[:B], z[B:]
-        else:
-            z1, h1 = self.net(batch["true"])
-            z2, h2 = self.net(batch["modified"])
-            nce = info_nce_loss(h1, h2, 0.85)
-        loss = (1 - self.weight) * nce + self.weight * IID_loss(z1, z2, lamb=self.lamb)
+        if self._batch is None:
+            self._batch = self._featurise(self._ids).clone()
+        main = torch.cuda.current_stream(self.dev)
+        # ---- side stream: batch t+1 (ids in self._ids) into a fresh buffer ----
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            nxt = self._featurise(self._ids)
+        # ---- main stream: step t on self._batch ----
+        x = self._batch
+        B = x.shape[0] // 2
+        self._flat_grad.zero_()
+        z, h = self.net(x)      # one pass over the stacked [2B, F] batch: same per-row math as the reference's two forwards
+        loss = (1 - self.weight) * info_nce_loss_stacked(h, 0.85) + self.weight * IID_loss(z[:B], z[B:], lamb=self.lamb)
         loss.backward()
-        if self._flat_grad is not None:
-            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.AVG)
-        self.opt.step()
+        self._optimizer_step()
+        main.wait_stream(self._side)
+        self._batch.copy_(nxt)   # (static buffer: the graph's next replay reads it)
         return loss.detach()
 
     @torch.no_grad()

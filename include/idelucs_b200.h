@@ -228,13 +228,29 @@ int idl_normalize_counts(const int32_t* d_counts, int64_t n, int R, double* d_ou
  * unclamped — compute_joint's return value); d_dz1, d_dz2 float32 [B, C] = dLoss/dz.
  * C <= idl_iid_loss_max_clusters().  d_workspace: idl_iid_loss_workspace_bytes(C) bytes of
  * scratch (fixed-order partial sums; no float atomics, results are run-to-run identical).
- * One cooperative launch: the device must be able to co-schedule ceil(C/16)*(ceil(C/16)+1)/2
- * CTAs of 256 threads (136 at C = 256; a B200 has 148 SMs). */
+ * C <= 16 (every configuration of Example/ALL_RESULTS.tsv): one ordinary CTA.  C > 16: one cooperative launch, the device
+ * must be able to co-schedule ceil(C/16)*(ceil(C/16)+1)/2 CTAs of 256 threads (136 at C = 256; a B200 has 148 SMs). */
 int idl_iid_loss_max_clusters(void);
 size_t idl_iid_loss_workspace_bytes(int C);
 int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float* d_loss,
                  float* d_joint, float* d_dz1, float* d_dz2, void* d_workspace, size_t workspace_bytes,
                  void* stream);
+
+/* F2 — replaces info_nce_loss (idelucs/LossFunctions.py:65-98; weight 1 - w = 0.75 of the training loss, models.py:128) on the
+ * two views stacked as one [n2 = 2B, D] float32 matrix (rows 0..B-1 = first view): F.normalize, the n2 x n2 similarity / temperature
+ * (never materialised), the self-masked log-softmax and the cross-entropy against the other view — value into d_loss, gradient
+ * with respect to d_h into d_dh [n2, D] (required: the gradient kernel also reduces the loss).  D in {32, 64, 128}; n2 even.
+ * d_workspace: idl_info_nce_workspace_bytes(n2, D).  Three launches, fixed-order reductions. */
+size_t idl_info_nce_workspace_bytes(int n2, int D);
+int idl_info_nce(const float* d_h, int n2, int D, float temperature, float* d_loss, float* d_dh, void* d_workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* Optimiser step of the data-parallel consumer (idelucs/models.py:86 torch.optim.RMSprop(lr, weight_decay=0.01); momentum 0,
+ * not centred) on a flat float32 shard, one elementwise pass: g = grad * grad_scale + weight_decay * p;
+ * v = alpha v + (1 - alpha) g^2; p -= lr g / (sqrt(v) + eps).  With N ranks the step is reduce-scatter(grad) ->
+ * idl_rmsprop_step on 1/N of the parameters -> all-gather(parameters). */
+int idl_rmsprop_step(float* d_param, const float* d_grad, float* d_square_avg, int64_t n, float lr, float alpha, float eps, float weight_decay,
+                     float grad_scale, void* stream);
 
 /* F1 — FASTA ingest on the host.  Replaces the record loop of kmersFasta
  * (idelucs/utils.py:229-261), which the reference re-runs on every pass (n_mimics + 1 times per training run,

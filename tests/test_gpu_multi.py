@@ -58,8 +58,17 @@ def _worker(rank, world, port, ret):
     w = next(tr.net.parameters()).detach().clone()
     dist.all_gather(ws, w)
     ok = ok and all(torch.equal(ws[0], x) for x in ws)
-    preds = tr.predict(ss, k=k)
-    ok = ok and preds.shape[0] == n
+    preds, probs, lat = tr.predict(ss, k=k)      # inference tail: all three row blocks all-gathered in rank order
+    ok = ok and preds.shape[0] == n and probs.shape[0] == n and tuple(lat.shape) == (n, 64)
+    if rank == 0:   # ... and equal to scoring the unsharded set with the same (replicated) network
+        x = ft.Scaler.fit(ft.profiles(full, k, [ft.VariantSpec(ft.KIND_CLEAN)], out_kind=ft.OUT_FREQ_F64)[0])
+        f64 = ft.profiles(full, k, [ft.VariantSpec(ft.KIND_CLEAN)], out_kind=ft.OUT_FREQ_F64)[0]
+        xs = x.transform64(f64, want32=True)
+        tr.net.eval()
+        with torch.no_grad():
+            out, lat_full = tr.net(xs)
+        tr.net.train()
+        ok = ok and torch.allclose(lat_full, lat, rtol=1e-4, atol=1e-4) and bool((out.argmax(1) == preds).float().mean() > 0.99)
     t = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -474,3 +474,85 @@ def test_pc_kernel_repetitive_and_degenerate_sequences(ft, SeqSet):
             cnt = np.zeros(4096, np.int32)
             orc.kmer_counts(mut, 6, cnt)
             assert np.array_equal(c[v, i], cnt), (i, v)
+
+
+def _ref_style_info_nce(z1, z2, temperature):
+    """the reference's mask-gather formulation (idelucs/LossFunctions.py:65-98), restated on the tensors' device"""
+    n = z1.shape[0]
+    dev = z1.device
+    feats = torch.nn.functional.normalize(torch.cat((z1, z2), 0).float(), dim=1)
+    lab = torch.cat([torch.arange(n, device=dev), torch.arange(n, device=dev)])
+    lab = (lab.unsqueeze(0) == lab.unsqueeze(1))
+    sim = feats @ feats.T
+    eye = torch.eye(2 * n, dtype=torch.bool, device=dev)
+    lab, sim = lab[~eye].view(2 * n, -1), sim[~eye].view(2 * n, -1)
+    logits = torch.cat([sim[lab].view(2 * n, -1), sim[~lab].view(2 * n, -1)], dim=1) / temperature
+    return torch.nn.functional.cross_entropy(logits, torch.zeros(2 * n, dtype=torch.long, device=dev))
+
+
+def test_fused_info_nce_matches_reference_formulation():
+    """idl_info_nce (normalise + similarity + masked log-softmax + cross-entropy + gradient, three
+    launches) against the reference's formulation and its autograd gradient, in float64 as the yardstick"""
+    from idelucs_b200.LossFunctions import info_nce_loss, info_nce_loss_stacked
+    torch.manual_seed(3)
+    for n, d, scale in ((512, 64, 1.0), (256, 64, 30.0), (5, 64, 1.0), (37, 32, 0.1), (100, 128, 3.0), (1, 64, 1.0)):
+        a = (torch.randn(n, d, device="cuda") * scale).requires_grad_(True)
+        b = (torch.randn(n, d, device="cuda") * scale + 0.3 * a.detach()).requires_grad_(True)
+        want = _ref_style_info_nce(a.double(), b.double(), 0.85)
+        gwa, gwb = torch.autograd.grad(want, (a, b))
+        got = info_nce_loss(a, b, 0.85)
+        gga, ggb = torch.autograd.grad(got, (a, b))
+        assert abs(want.item() - got.item()) < 1e-5, (n, d, want.item(), got.item())
+        tol = 1e-4 * float(max(gwa.abs().max(), gwb.abs().max())) + 1e-9
+        assert float((gwa - gga).abs().max()) < tol and float((gwb - ggb).abs().max()) < tol, (n, d)
+        got2 = info_nce_loss_stacked(torch.cat((a, b), 0), 0.85)
+        assert got2.item() == got.item()                                  # run-to-run identical (fixed-order reductions)
+        # float32 reference formulation agrees to its own rounding
+        w32 = _ref_style_info_nce(a, b, 0.85)
+        assert abs(w32.item() - got.item()) < 1e-5
+
+
+def test_iid_loss_small_kernel_equals_tiled_kernel_and_oracle():
+    """C <= 16 takes the single-CTA kernel (train_ops.cu): same loss / joint / gradients as the oracle's closed form, for the
+    shapes of the reference's configurations (C = 3, 5, 12; last ragged batch 332 / 287) and clamped entries"""
+    from idelucs_b200.LossFunctions import IID_loss, compute_joint
+    rng = np.random.default_rng(8)
+    for B, C, lamb in ((512, 5, 2.8), (332, 5, 2.8), (287, 3, 2.5), (256, 12, 2.8), (64, 16, 1.0), (7, 1, 2.0), (512, 2, 2.8)):
+        z1 = torch.softmax(torch.from_numpy(rng.normal(size=(B, C)).astype(np.float32) * 3), 1).cuda().requires_grad_(True)
+        z2 = torch.softmax(torch.from_numpy(rng.normal(size=(B, C)).astype(np.float32) * 3), 1).cuda().requires_grad_(True)
+        loss = IID_loss(z1, z2, lamb=lamb)
+        loss.backward()
+        wl, wd1, wd2 = orc.IID_loss_grad(z1.detach().cpu().numpy(), z2.detach().cpu().numpy(), lamb=lamb)
+        assert abs(loss.item() - wl) < 1e-5, (B, C, loss.item(), wl)
+        m = max(np.abs(wd1).max(), np.abs(wd2).max(), 1e-12)
+        assert np.abs(z1.grad.cpu().numpy() - wd1).max() < 1e-4 * m and np.abs(z2.grad.cpu().numpy() - wd2).max() < 1e-4 * m, (B, C)
+        np.testing.assert_allclose(compute_joint(z1, z2).cpu().numpy(), orc.compute_joint(z1.detach().cpu().numpy(), z2.detach().cpu().numpy()),
+                                   rtol=1e-5, atol=1e-8)
+    # a cluster nobody uses: clamped marginal and joint entries
+    z1 = torch.zeros(64, 4, device="cuda"); z1[:, 0] = 0.5; z1[:, 1] = 0.5
+    z2 = z1.clone()
+    z1.requires_grad_(True); z2.requires_grad_(True)
+    loss = IID_loss(z1, z2, lamb=2.8)
+    loss.backward()
+    wl, wd1, wd2 = orc.IID_loss_grad(z1.detach().cpu().numpy(), z2.detach().cpu().numpy(), lamb=2.8)
+    assert abs(loss.item() - wl) < 1e-5
+    assert np.abs(z1.grad.cpu().numpy() - wd1).max() < 1e-4 * max(np.abs(wd1).max(), 1e-12)
+
+
+def test_rmsprop_step_matches_torch():
+    """idl_rmsprop_step == torch.optim.RMSprop(lr, weight_decay=0.01) (idelucs/models.py:86) over several steps"""
+    from idelucs_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(1)
+    n = 100003
+    p_ref = torch.nn.Parameter(torch.randn(n, device="cuda"))
+    p = p_ref.detach().clone()
+    sq = torch.zeros(n, device="cuda")
+    opt = torch.optim.RMSprop([p_ref], lr=1e-3, weight_decay=0.01)
+    for step in range(5):
+        g = torch.randn(n, device="cuda") * (10.0 ** (step - 2))
+        p_ref.grad = g.clone()
+        opt.step()
+        _lib.check(lib.idl_rmsprop_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(sq), n, 1e-3, 0.99, 1e-8, 0.01, 1.0, _lib.stream_ptr()))
+    assert torch.allclose(p, p_ref.detach(), rtol=2e-6, atol=1e-7)
+    assert torch.allclose(sq, opt.state[p_ref]["square_avg"], rtol=2e-6, atol=0)

@@ -30,7 +30,14 @@ def _worker(rank, world, port, ret):
     gp, gn = ft.gather_partials(torch.from_numpy(parts), torch.from_numpy(ns))
     mean, var = orc.merge_partials(gp.numpy(), gn.numpy())
     rows = parallel.all_gather_rows(torch.from_numpy(X[lo:hi]), [h - l for l, h in ranges])
-    ok = (np.allclose(mean, X.astype(np.float64).mean(axis=0), rtol=1e-13) and
+    # inference tail (idelucs/models.py:164-171): predictions, probabilities and latent rows of every rank, rank order
+    yp = torch.arange(lo, hi, dtype=torch.int64) % 7
+    pr = torch.from_numpy(X[lo:hi, 0].copy())
+    lat = torch.from_numpy(X[lo:hi].copy())
+    g_y, g_p, g_l = parallel.all_gather_ragged([yp, pr, lat])
+    tail_ok = (torch.equal(g_y, torch.arange(0, 5000, dtype=torch.int64) % 7) and torch.equal(g_p, torch.from_numpy(X[:, 0].copy()))
+               and torch.equal(g_l, torch.from_numpy(X)))
+    ok = tail_ok and (np.allclose(mean, X.astype(np.float64).mean(axis=0), rtol=1e-13) and
           np.allclose(var, X.astype(np.float64).var(axis=0), rtol=1e-9, atol=1e-30) and var[7] == 0.0 and
           torch.equal(rows, torch.from_numpy(X)) and float(gn.sum()) == 5000.0)
     t = torch.tensor([1.0 if ok else 0.0])
