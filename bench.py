@@ -93,6 +93,27 @@ def cpu_reference(n_seq_per_core, cores):
     return cores * n_seq_per_core * V / busy, busy, wall, res[0][1]
 
 
+def cpu_train_reference(n_pairs, n_clusters, batch_sz, cores):
+    """pairs/s of the reference's training epoch on the host (oracle/train_port.py: idelucs/models.py:113-143 with torch on the
+    CPU, torch.set_num_threads(cpu_count - 2) as idelucs/__main__.py:316, DataLoader(shuffle=True, num_workers=4) as
+    idelucs/utils.py:427).  x_train holds random normal values: the cost of a step does not depend on them."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import train_port
+    torch.set_num_threads(max(1, cores - 2))
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((n_pairs, 2, F), generator=g).numpy()
+    tr = train_port.Trainer(x, F, n_clusters, batch_sz=batch_sz, lamb=2.8, weight=0.25, lr=1e-3, num_workers=4)
+    warm = train_port.Trainer(x[: max(batch_sz * 2, n_pairs // 8)], F, n_clusters, batch_sz=batch_sz, num_workers=4)
+    warm.contrastive_training_epoch()
+    t0 = time.perf_counter()
+    tr.contrastive_training_epoch()
+    dt = time.perf_counter() - t0
+    return {"pairs_per_s": n_pairs / dt, "cores": cores, "torch_threads": max(1, cores - 2), "dataloader_workers": 4, "kind": "port",
+            "sample": "one epoch over %d synthetic pairs (k=6: 4096 features, batch_sz=%d, n_clusters=%d) of the reference's "
+                      "contrastive_training_epoch restated in oracle/train_port.py (pinned against the live reference), %.1f s" % (n_pairs, batch_sz, n_clusters, dt)}
+
+
 # ------------------------------------------------------------------------------------------
 class ClockSampler(object):
     """SM clock / throttle reasons sampled every ~5 ms during the timed region, in-process through NVML
@@ -377,8 +398,11 @@ def run_ours(args):
         train = {"pairs_per_s": world * 512 * args.train_steps / (tms * 1e-3), "ms_per_step": tms / args.train_steps,
                  "steps": args.train_steps, "final_loss": float(loss.item()), "cuda_graph": bool(graphed),
                  "config": "synthetic %d sequences x 2000 bp sharded over %d GPU(s), k=6, n_mimics=50, batch_sz=512 per rank, "
-                           "n_clusters=5, RMSprop, (1-w) InfoNCE + w IIC (BASELINE.json configs[3]); batches regenerated on the "
-                           "fly by the mimic kernel; MLP / InfoNCE in PyTorch fp32" % (nt * world, world)}
+                           "n_clusters=5, RMSprop, (1-w) InfoNCE + w IIC (BASELINE.json configs[3]); shuffled epochs; batches regenerated "
+                           "on a side stream by the mimic kernel; fused InfoNCE / IIC / RMSprop kernels, MLP in PyTorch fp32; "
+                           "gradient reduce-scatter + parameter all-gather inside the step's CUDA graph" % (nt * world, world)}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            train["cpu_baseline"] = cpu_train_reference(args.cpu_train_pairs, 5, 512, os.cpu_count() or 1)
     if rank != 0:
         return
     cpu = None
@@ -598,6 +622,8 @@ def run_c5(args):
                  "final_loss": float(loss.item()), "cuda_graph": bool(graphed), "n_clusters": 200,
                  "config": "C = 200 output units (n_clusters = 0 embedding path), batch_sz %d per rank, pairs gathered from the materialised "
                            "[4, n, 4096] profiles, fused IIC kernel at C = 200" % args.c5_batch}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            train["cpu_baseline"] = cpu_train_reference(args.cpu_train_pairs, 200, args.c5_batch, os.cpu_count() or 1)
     if rank != 0:
         return
     cpu = None
@@ -660,6 +686,7 @@ def main():
     ap.add_argument("--train_steps", type=int, default=200, help="steps of the secondary training-pairs/s measurement (0 = skip)")
     ap.add_argument("--train_seqs", type=int, default=1000000, help="total sequences of the training workload (configs[3])")
     ap.add_argument("--kernel_timing", action="store_true", help="time the dominant kernel inside the timed loop (adds syncs)")
+    ap.add_argument("--cpu_train_pairs", type=int, default=16384, help="pairs of the CPU training baseline's timed epoch")
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"], help="c3: BASELINE configs[2] (default, the headline metric); "
                     "c5: configs[4], Fungi-shaped long genomes")
     ap.add_argument("--c5_genomes", type=int, default=2000, help="genomes per GPU of the c5 workload")

@@ -345,3 +345,31 @@ def test_live_fasta_record_loop_vs_native_scanner(tmp_path):
             c = np.ones(64, np.int32)
             orc.kmer_counts(seq, 3, c)
             assert np.array_equal(c / c.sum(), want[r]), (i, r)
+
+
+@pytest.mark.skipif(not ref_live.available(), reason="reference mount absent")
+def test_live_training_epoch_port(fasta_files):
+    """oracle/train_port.py (the CPU baseline of bench.py's train.pairs_per_s) against the live reference's
+    contrastive_training_epoch (idelucs/models.py:113-143): same seeds, same x_train, same loader order -> the same epoch
+    losses (identical torch ops on the CPU)"""
+    import random
+    import torch
+    from torch.utils.data import DataLoader
+    import train_port
+    ref = ref_live.load()
+    from idelucs import models as rmodels
+    from idelucs import utils as rutils
+    np.random.seed(0); random.seed(0)
+    x = rutils.AugmentFasta(fasta_files["Actinopterygii"], 3, k=4)
+    args = {"sequence_file": fasta_files["Actinopterygii"], "GT_file": None, "n_clusters": 3, "k": 4, "model_size": "linear", "n_mimics": 3,
+            "batch_sz": 64, "lambda": 2.8, "lr": 1e-3, "weight": 0.25, "scheduler": None, "optimizer": "RMSprop"}
+    torch.manual_seed(5)
+    m = rmodels.IID_model(args)
+    m.dataloader = DataLoader(rutils.AugmentedDataset(x), batch_size=64, shuffle=True, num_workers=0)
+    torch.manual_seed(6)
+    want = [m.contrastive_training_epoch() for _ in range(2)]
+    torch.manual_seed(5)
+    t = train_port.Trainer(x, 256, 3, batch_sz=64, lamb=2.8, weight=0.25, lr=1e-3, num_workers=0)
+    torch.manual_seed(6)
+    got = [t.contrastive_training_epoch() for _ in range(2)]
+    assert np.allclose(want, got, rtol=1e-6, atol=1e-7), (want, got)
