@@ -201,6 +201,50 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+def bind_to_gpu_numa(local):
+    """Best effort: run this process (and first-touch its pinned buffers) on the NUMA node the GPU hangs off, so that the
+    host side of the D2H / H2D copies does not cross the socket interconnect.  Returns the node or None."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+def d2h_ceiling(dev_buf, host_buf, steps, world, dist, torch):
+    """aggregate device->host bandwidth of plain pinned copies of the e2e result size, every rank at once (GB/s)"""
+    for _ in range(2):
+        host_buf.copy_(dev_buf, non_blocking=True)
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        host_buf.copy_(dev_buf, non_blocking=True)
+        torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    if world > 1:
+        t = torch.tensor([dt], device=dev_buf.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return world * dev_buf.numel() * dev_buf.element_size() / dt / 1e9
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -228,6 +272,7 @@ def run_ours(args):
     rank, local, world = parallel.init_from_env()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa_node = bind_to_gpu_numa(local)
     n = args.n_seqs
     # ---- synthetic input: iid uniform ACGT, generated on the device from a fixed seed ----
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -337,8 +382,14 @@ def run_ours(args):
             t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
+        ceil_gbs = d2h_ceiling(dev_out, host_out, args.steps, world, dist, torch)
+        d2h_bytes = int(V * ne * F * 4 + ne * 8)
         e2e = {"value": world * ne * V / e2e_s, "unit": "profiles/s", "h2d_bytes_per_step": int(ne * SEQ_LEN + (ne + 1) * 16),
-               "d2h_bytes_per_step": int(V * ne * F * 4 + ne * 8), "ms_per_step": e2e_s * 1e3,
+               "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1e3,
+               "d2h_ceiling_GBps": ceil_gbs, "d2h_achieved_GBps": world * d2h_bytes / e2e_s / 1e9,
+               "frac_of_d2h_ceiling": (world * d2h_bytes / e2e_s / 1e9) / ceil_gbs, "numa_node": numa_node,
+               "note": "the step's device->host copy of the float32 profiles (335 kB per profile) is the bound: d2h_ceiling is the aggregate "
+                       "bandwidth of plain pinned copies of the same size issued by all ranks at once on this box",
                "sequences_per_step": ne, "api": "SeqSet.from_ascii(pinned host bytes) -> idl_pack / idl_profiles_prepare / "
                "idl_scaler_finalize / idl_profiles_prepared -> pinned host float32 [51, n, 4096]"}
 
@@ -397,10 +448,13 @@ def run_ours(args):
             tms = float(t.item())
         train = {"pairs_per_s": world * 512 * args.train_steps / (tms * 1e-3), "ms_per_step": tms / args.train_steps,
                  "steps": args.train_steps, "final_loss": float(loss.item()), "cuda_graph": bool(graphed),
+                 "optimizer_step": {"single": "idl_rmsprop_step (one pass)", "nccl": "NCCL all-reduce + idl_rmsprop_step",
+                                    "symm": "idl_rmsprop_allreduce_step: one kernel over symmetric memory (%s)"
+                                            % ("NVLS multimem.ld_reduce / multimem.st" if getattr(tr, "_mc", (0, 0))[0] else "peer loads / stores")}[tr._mode],
                  "config": "synthetic %d sequences x 2000 bp sharded over %d GPU(s), k=6, n_mimics=50, batch_sz=512 per rank, "
                            "n_clusters=5, RMSprop, (1-w) InfoNCE + w IIC (BASELINE.json configs[3]); shuffled epochs; batches regenerated "
                            "on a side stream by the mimic kernel; fused InfoNCE / IIC / RMSprop kernels, MLP in PyTorch fp32; "
-                           "gradient reduce-scatter + parameter all-gather inside the step's CUDA graph" % (nt * world, world)}
+                           "gradient mean + RMSprop + parameter broadcast as one kernel inside the step's CUDA graph" % (nt * world, world)}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             train["cpu_baseline"] = cpu_train_reference(args.cpu_train_pairs, 5, 512, os.cpu_count() or 1)
     if rank != 0:
@@ -422,7 +476,7 @@ def run_ours(args):
                                    % (V * n * F * 4 / 1e9), "cache": "inputs+outputs per step exceed L2 (126 MB) by >100x, no flush needed",
                        "mutation_rates": "transition 1e-2, transversion 5e-3, Random_N 20 (idelucs/utils.py:330-349)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": n_launches, "roofline": roofline, "cpu_baseline": cpu, "train": train, "fasta_ingest": ingest}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -641,7 +695,7 @@ def run_c5(args):
                        "profiles_per_step": n_total * Vc, "sharding": "contiguous length-balanced ranges (parallel.shard_ranges)",
                        "cache": "packed input per GPU (%.0f MB) exceeds L2 (126 MB); outputs rewritten every step" % ((my_bases * 3 // 8) / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": n_launches, "roofline": roofline, "cpu_baseline": cpu, "train": train}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_reference(args):
@@ -667,10 +721,24 @@ def run_reference(args):
                                        % (cores, args.ref_seqs_per_core, kind)},
             "e2e": {"value": value, "unit": "profiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line))
+    emit(line)
+
+
+_OUT = None
+
+
+def emit(line):
+    """the ONE JSON line on the process's real stdout (everything else any library prints goes to stderr)"""
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")   # keep the real stdout for the JSON line ...
+    os.dup2(2, 1)                      # ... and send whatever else writes to fd 1 (NCCL's version banner, warnings) to stderr
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -6,9 +6,8 @@ the fly with the mimic kernel (selection mode — the 1.6 TB x_train of the refe
 exists), runs the reference's training step (idelucs/models.py:113-143: two forwards,
 (1-w) InfoNCE + w IIC loss, backward, RMSprop) with the fused IIC kernel, and all-reduces the
 gradients of the data-parallel MLP replicas over NCCL: parameters, gradients and the RMSprop state live in flat buffers;
-per step one reduce-scatter of the gradient (8.5 MB at k=6), the optimiser on this rank's shard (idl_rmsprop_step) and one
-all-gather of the parameters, all captured in the step's CUDA graph; the next pair batch is regenerated on a side stream
-under them.  batch_sz is PER RANK (weak scaling in the batch, strong in the data set)."""
+per step ONE kernel averages the gradient slices over NVLink (8.5 MB at k=6), applies RMSprop and broadcasts the new parameters
+(idl_rmsprop_allreduce_step), captured in the step's CUDA graph; the next pair batch is regenerated on a side stream.  batch_sz is PER RANK (weak scaling in the batch, strong in the data set)."""
 import torch
 import torch.distributed as dist
 
@@ -25,12 +24,13 @@ class ShardedTrainer(object):
       side stream  pair batch t+1 regenerated from the packed sequences (selection mode of idl_profiles) — independent of
                    the weights, so it runs under the collectives of step t;
       main stream  forward over the stacked [2B, F] batch t -> fused InfoNCE + fused IIC loss -> backward into ONE flat
-                   gradient buffer -> reduce-scatter (AVG) -> idl_rmsprop_step on this rank's 1/N of the flat parameters
-                   -> all-gather of the parameters.  At N = 1 the collectives vanish and the optimiser is one pass.
+                   gradient buffer -> idl_rmsprop_allreduce_step: gradient mean + RMSprop + parameter broadcast as one kernel
+                   over NVLink peer memory (symmetric buffers, NVLS multimem when available; NCCL all-reduce + idl_rmsprop_step
+                   when symmetric memory cannot be set up).  At N = 1 the optimiser is one elementwise pass.
     The parameters of the network are views into one flat buffer, so the optimiser and the collectives see one tensor."""
 
     def __init__(self, seqset, k=6, n_clusters=5, n_mimics=50, batch_sz=512, lamb=2.8, weight=0.25, lr=1e-3, seed=0,
-                 seq_id0=0, world=1, materialize_bytes=0, alpha=0.99, eps=1e-8, weight_decay=0.01):
+                 seq_id0=0, world=1, materialize_bytes=0, alpha=0.99, eps=1e-8, weight_decay=0.01, use_symmetric_memory=True):
         from .utils import PairBatchLoader
         self.dev = seqset.device
         self.world = world
@@ -43,13 +43,28 @@ class ShardedTrainer(object):
         net.apply(weights_init)
         net.to(self.dev)
         self.net = net
-        # ---- flat parameter / gradient / second-moment buffers (padded to a multiple of 4 * world elements) ----
+        # ---- flat parameter / gradient / second-moment buffers (padded to a multiple of 4 * world elements).  With several
+        # ranks the two big buffers are SYMMETRIC memory (every rank maps every rank's copy, plus an NVLS multicast address when
+        # the fabric has one): the optimiser step is then ONE kernel that reduces, updates and broadcasts over NVLink ----
         params = [p for p in net.parameters() if p.requires_grad]
         n = sum(p.numel() for p in params)
         self._n = n
         pad = (-n) % (4 * world)
-        self._flat_param = torch.zeros(n + pad, dtype=torch.float32, device=self.dev)
-        self._flat_grad = torch.zeros(n + pad, dtype=torch.float32, device=self.dev)
+        self._mode = "single"
+        self._flat_param = self._flat_grad = None
+        if world > 1 and use_symmetric_memory:
+            try:
+                self._setup_symmetric(n + pad)
+                self._mode = "symm"
+            except Exception as e:  # noqa: BLE001 — symmetric memory not available on this fabric / build: NCCL all-reduce instead
+                self._symm_error = repr(e)
+        if world > 1:   # every rank must take the same path
+            okf = torch.tensor([1.0 if self._mode == "symm" else 0.0], device=self.dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            self._mode = "symm" if float(okf.item()) == 1.0 else "nccl"
+        if self._mode != "symm":
+            self._flat_param = torch.zeros(n + pad, dtype=torch.float32, device=self.dev)
+            self._flat_grad = torch.zeros(n + pad, dtype=torch.float32, device=self.dev)
         o = 0
         for p in params:
             self._flat_param[o:o + p.numel()].copy_(p.data.reshape(-1))
@@ -58,9 +73,8 @@ class ShardedTrainer(object):
             o += p.numel()
         if world > 1:   # replicas must start identical whatever the RNG state of the rank was
             dist.broadcast(self._flat_param, src=0)
-        self._shard = (n + pad) // world
+        self._shard = (n + pad) // world if self._mode == "symm" else n + pad
         self._sq = torch.zeros(self._shard, dtype=torch.float32, device=self.dev)
-        self._grad_shard = torch.zeros(self._shard, dtype=torch.float32, device=self.dev) if world > 1 else None
         self.lr, self.alpha, self.eps, self.weight_decay = lr, alpha, eps, weight_decay
         self.lamb, self.weight, self.batch_sz = lamb, weight, batch_sz
         self.gen = torch.Generator(device=self.dev).manual_seed(seed * 1000003 + seq_id0 + 1)
@@ -70,21 +84,41 @@ class ShardedTrainer(object):
         self._side = torch.cuda.Stream(device=self.dev)
         self._batch = None       # the batch the next step consumes (featurised by the previous step; static buffer once created)
 
-    # ---- optimiser: torch.optim.RMSprop's arithmetic on the flat shard (idl_rmsprop_step) ----
+    def _setup_symmetric(self, n_total):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        grp = dist.group.WORLD
+        g = symm.empty(n_total, dtype=torch.float32, device=self.dev)
+        p = symm.empty(n_total, dtype=torch.float32, device=self.dev)
+        self._hg, self._hp = symm.rendezvous(g, grp), symm.rendezvous(p, grp)
+        g.zero_(); p.zero_()
+        self._flat_grad, self._flat_param = g, p
+        self._gp = (ctypes.c_uint64 * self.world)(*[int(x) for x in self._hg.buffer_ptrs])
+        self._pp = (ctypes.c_uint64 * self.world)(*[int(x) for x in self._hp.buffer_ptrs])
+        self._pads = (ctypes.c_uint64 * self.world)(*[int(x) for x in self._hg.signal_pad_ptrs])
+        self._sync = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        if 4 * 34 * self.world > int(self._hg.signal_pad_size):
+            raise RuntimeError("signal pad too small for the in-kernel channels")
+        mc_g = int(getattr(self._hg, "multicast_ptr", 0) or 0)
+        mc_p = int(getattr(self._hp, "multicast_ptr", 0) or 0)
+        self._mc = (mc_g, mc_p) if (mc_g and mc_p) else (0, 0)
+
+    # ---- optimiser: torch.optim.RMSprop's arithmetic on flat buffers ----
     def _optimizer_step(self):
         from . import _lib
         lib = _lib.load()
-        if self.world > 1:
-            dist.reduce_scatter_tensor(self._grad_shard, self._flat_grad, op=dist.ReduceOp.AVG)
-            g = self._grad_shard
-            p = self._flat_param[self.rank * self._shard:(self.rank + 1) * self._shard]
-        else:
-            g, p = self._flat_grad, self._flat_param
         with torch.cuda.device(self.dev):
-            _lib.check(lib.idl_rmsprop_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(self._sq), self._shard, self.lr, self.alpha, self.eps,
-                                            self.weight_decay, 1.0, _lib.stream_ptr()))
-        if self.world > 1:
-            dist.all_gather_into_tensor(self._flat_param, p)
+            if self._mode == "symm":
+                # ONE kernel: the ranks meet (signal pads), mean of every rank's gradient slice (NVLS multimem.ld_reduce, or peer
+                # loads) -> RMSprop on this rank's slice -> new parameters stored into every rank's buffer, the ranks meet again
+                _lib.check(lib.idl_rmsprop_allreduce_step(self._gp, self._pp, self._mc[0], self._mc[1], _lib.ptr(self._sq),
+                                                          self._flat_grad.numel(), self.rank, self.world, self.lr, self.alpha, self.eps,
+                                                          self.weight_decay, self._pads, _lib.ptr(self._sync), 32, _lib.stream_ptr()))
+                return
+            if self._mode == "nccl":
+                dist.all_reduce(self._flat_grad, op=dist.ReduceOp.AVG)
+            _lib.check(lib.idl_rmsprop_step(_lib.ptr(self._flat_param), _lib.ptr(self._flat_grad), _lib.ptr(self._sq), self._shard, self.lr,
+                                            self.alpha, self.eps, self.weight_decay, 1.0, _lib.stream_ptr()))
 
     def enable_cuda_graph(self, warmup=11):
         """Capture the whole step (both streams) in ONE CUDA graph: the step is launch-bound, so replaying a graph removes the

@@ -252,6 +252,21 @@ int idl_info_nce(const float* d_h, int n2, int D, float temperature, float* d_lo
 int idl_rmsprop_step(float* d_param, const float* d_grad, float* d_square_avg, int64_t n, float lr, float alpha, float eps, float weight_decay,
                      float grad_scale, void* stream);
 
+/* The data-parallel optimiser step as ONE kernel over NVLink peer memory (gradient all-reduce + RMSprop + parameter
+ * broadcast): gradients and parameters live in symmetric buffers, h_grad_peers / h_param_peers are HOST arrays of the `world`
+ * device addresses at which this process sees every rank's buffer (entry `rank` = its own), grad_multicast / param_multicast the
+ * NVLS multicast addresses of the same buffers or 0.  This rank reduces the slice [rank * n_total / world, +n_total / world) of
+ * the gradients (multimem.ld_reduce when a multicast address is given: the switch adds the operands; otherwise one load per peer,
+ * rank order), averages, applies idl_rmsprop_step's update to its slice (d_square_avg: n_total / world floats, local) and writes
+ * the new parameters into every rank's buffer (multimem.st / one store per peer).  n_total % (4 * world) == 0, world <= 16.
+ * Synchronisation of the ranks (all gradients written before, all parameters visible after): inside the kernel when
+ * h_signal_pads is given — HOST array of the `world` device addresses of every rank's symmetric-memory signal pad (uint32 flags,
+ * zero when idle; the kernel uses flags [channel * world, (channel + 2) * world) with torch's put / wait protocol) together with
+ * d_sync, two zero-initialised uint32 words in local device memory (zero again afterwards) — else by the caller. */
+int idl_rmsprop_allreduce_step(const uint64_t* h_grad_peers, const uint64_t* h_param_peers, uint64_t grad_multicast, uint64_t param_multicast,
+                               float* d_square_avg, int64_t n_total, int rank, int world, float lr, float alpha, float eps, float weight_decay,
+                               const uint64_t* h_signal_pads, uint32_t* d_sync, int channel, void* stream);
+
 /* F1 — FASTA ingest on the host.  Replaces the record loop of kmersFasta
  * (idelucs/utils.py:229-261), which the reference re-runs on every pass (n_mimics + 1 times per training run,
  * once more per predict): '#' lines skipped (:230); a '>' line closes the running record only while its id is
