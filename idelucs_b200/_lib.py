@@ -62,8 +62,7 @@ PROTOTYPES = {
     "idl_info_nce_workspace_bytes": (c_size_t, [c_int, c_int]),
     "idl_info_nce": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "idl_rmsprop_step": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float, c_void_p]),
-    "idl_rmsprop_allreduce_step": (c_int, [c_void_p, c_void_p, c_u64, c_u64, c_void_p, c_i64, c_int, c_int, c_float, c_float, c_float, c_float,
-                                           c_void_p, c_void_p, c_int, c_void_p]),
+    "idl_rmsprop_allreduce_step": (c_int, [c_void_p, c_void_p, c_u64, c_u64, c_void_p, c_i64, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p]),
     "idl_fasta_scan": (c_int, [c_void_p, c_i64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "idl_fasta_extract": (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),
     "idl_iid_loss_max_clusters": (c_int, []),

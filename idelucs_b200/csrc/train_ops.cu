@@ -315,105 +315,60 @@ __device__ __forceinline__ void multimem_st(float* mc_addr, float4 v) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-struct PeerPads { uint32_t* p[MAX_PEERS]; };
+// Every thread requests AR_U 16-byte units of the reduced gradient (and of its local state) before it touches the first result:
+// the kernel is bound by the NVLink round trip (a few microseconds per dependent access), not by bandwidth — 8.5 MB of gradients
+// are 1 MB per rank at 8 GPUs — so the loads of a thread must overlap each other.
+constexpr int AR_U = 4;
 
-// signal-pad handshake (the protocol of torch's symmetric-memory barrier, on channels of our own): a flag per (channel, sender)
-// in the receiver's pad; the sender flips it 0 -> 1 with release semantics, the receiver flips it back 1 -> 0 with acquire
-__device__ __forceinline__ void pad_put(uint32_t* addr) {
-    uint32_t old;
-    do { asm volatile("atom.release.sys.global.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(addr) : "memory"); } while (old != 0u);
-}
-__device__ __forceinline__ void pad_wait(uint32_t* addr) {
-    uint32_t old;
-    do { asm volatile("atom.acquire.sys.global.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(addr) : "memory"); } while (old != 1u);
-}
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* addr) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(uint32_t* addr, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
-
-// pads.p[0] == nullptr: no in-kernel synchronisation (the caller brackets the launch with barriers of its own).
-// Otherwise: CTA 0 meets every peer on channel `chan` (all gradients are written) and releases the other CTAs through
-// sync[0]; the CTA that finishes last meets every peer on channel `chan + 1` (all parameter stores are visible) before the
-// kernel ends.  sync: two zero-initialised words in local device memory, zero again when the kernel ends.
 __global__ void __launch_bounds__(256) rmsprop_allreduce_kernel(const PeerPtrs grads, const PeerPtrs params, const float* grad_mc, float* param_mc,
                                                                   float* __restrict__ sq, long long shard, int rank, int world, float lr, float alpha,
-                                                                  float eps, float wd, const PeerPads pads, uint32_t* sync, int chan) {
-    __shared__ int s_last;
+                                                                  float eps, float wd) {
     const long long base = (long long)rank * shard;
     const float inv_world = 1.0f / (float)world;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // this thread's first unit of local state is requested before the ranks meet
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p;
-    if (i4 < shard / 4) {
-        p = *reinterpret_cast<const float4*>(params.p[rank] + base + i4 * 4);
-        v = reinterpret_cast<const float4*>(sq)[i4];
-    }
-    if (pads.p[0]) {
-        if (blockIdx.x == 0) {
-            if ((int)threadIdx.x < world) {
-                pad_put(pads.p[threadIdx.x] + (size_t)chan * world + rank);
-                pad_wait(pads.p[rank] + (size_t)chan * world + threadIdx.x);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) st_release_gpu(sync, 1u);
-        } else {
-            if (threadIdx.x == 0) while (ld_acquire_gpu(sync) == 0u) { }
-            __syncthreads();
-        }
-    }
-    for (; i4 < shard / 4; i4 += stride) {
-        const long long idx = base + i4 * 4;
-        float4 g;
-        if (grad_mc) {
-            g = multimem_ld_reduce_add(grad_mc + idx);
-        } else {
-            g = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < world; ++r) {   // rank order: the same sum on every run
-                const float4 t = *reinterpret_cast<const float4*>(grads.p[r] + idx);
-                g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
-            }
-        }
-        float* gp = &g.x; float* pp = &p.x; float* vp = &v.x;
+    const long long units = shard / 4, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < units; i0 += stride * AR_U) {
+        float4 g[AR_U], p[AR_U], v[AR_U];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float gg = fmaf(wd, pp[e], gp[e] * inv_world);
-            const float vv = fmaf(1.0f - alpha, gg * gg, alpha * vp[e]);
-            vp[e] = vv;
-            pp[e] = pp[e] - lr * (gg / (sqrtf(vv) + eps));
+        for (int u = 0; u < AR_U; ++u) {
+            const long long i4 = i0 + u * stride;
+            if (i4 < units) {
+                const long long idx = base + i4 * 4;
+                if (grad_mc) {
+                    g[u] = multimem_ld_reduce_add(grad_mc + idx);
+                } else {
+                    g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int r = 0; r < world; ++r) {   // rank order: the same sum on every run
+                        const float4 t = *reinterpret_cast<const float4*>(grads.p[r] + idx);
+                        g[u].x += t.x; g[u].y += t.y; g[u].z += t.z; g[u].w += t.w;
+                    }
+                }
+                p[u] = *reinterpret_cast<const float4*>(params.p[rank] + idx);
+                v[u] = reinterpret_cast<const float4*>(sq)[i4];
+            }
         }
-        reinterpret_cast<float4*>(sq)[i4] = v;
-        if (param_mc) {
-            multimem_st(param_mc + idx, p);
-        } else {
-            for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(params.p[r] + idx) = p;
-        }
-        if (i4 + stride < shard / 4) {
-            p = *reinterpret_cast<const float4*>(params.p[rank] + idx + stride * 4);
-            v = reinterpret_cast<const float4*>(sq)[i4 + stride];
+#pragma unroll
+        for (int u = 0; u < AR_U; ++u) {
+            const long long i4 = i0 + u * stride;
+            if (i4 < units) {
+                const long long idx = base + i4 * 4;
+                float* gp = &g[u].x; float* pp = &p[u].x; float* vp = &v[u].x;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float gg = fmaf(wd, pp[e], gp[e] * inv_world);
+                    const float vv = fmaf(1.0f - alpha, gg * gg, alpha * vp[e]);
+                    vp[e] = vv;
+                    pp[e] = pp[e] - lr * (gg / (sqrtf(vv) + eps));
+                }
+                reinterpret_cast<float4*>(sq)[i4] = v[u];
+                if (param_mc) {
+                    multimem_st(param_mc + idx, p[u]);
+                } else {
+                    for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(params.p[r] + idx) = p[u];
+                }
+            }
         }
     }
     __threadfence_system();
-    if (pads.p[0]) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned done = atomicAdd(sync + 1, 1u);
-            __threadfence_system();
-            s_last = done == gridDim.x - 1 ? 1 : 0;
-        }
-        __syncthreads();
-        if (s_last) {
-            if ((int)threadIdx.x < world) {
-                pad_put(pads.p[threadIdx.x] + (size_t)(chan + 1) * world + rank);
-                pad_wait(pads.p[rank] + (size_t)(chan + 1) * world + threadIdx.x);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) { sync[0] = 0u; sync[1] = 0u; }
-        }
-    }
 }
 
 // C <= 16: called by idl_iid_loss (iid_loss.cu)
@@ -481,30 +436,24 @@ int idl_rmsprop_step(float* d_param, const float* d_grad, float* d_square_avg, i
 
 int idl_rmsprop_allreduce_step(const uint64_t* h_grad_peers, const uint64_t* h_param_peers, uint64_t grad_multicast, uint64_t param_multicast,
                                float* d_square_avg, int64_t n_total, int rank, int world, float lr, float alpha, float eps, float weight_decay,
-                               const uint64_t* h_signal_pads, uint32_t* d_sync, int channel, void* stream) {
+                               void* stream) {
     if (!h_grad_peers || !h_param_peers || !d_square_avg || world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || n_total <= 0 ||
         n_total % (4LL * world) != 0)
         return set_error(IDL_EINVAL, "idl_rmsprop_allreduce_step: bad argument%s (n_total must be a multiple of 4 x world, world <= 16)", "");
-    if (h_signal_pads && (!d_sync || channel < 0)) return set_error(IDL_EINVAL, "idl_rmsprop_allreduce_step: in-kernel synchronisation needs d_sync and a channel%s", "");
     PeerPtrs g, p;
-    PeerPads pads;
-    for (int r = 0; r < MAX_PEERS; ++r) { g.p[r] = nullptr; p.p[r] = nullptr; pads.p[r] = nullptr; }
+    for (int r = 0; r < MAX_PEERS; ++r) { g.p[r] = nullptr; p.p[r] = nullptr; }
     for (int r = 0; r < world; ++r) {
         g.p[r] = reinterpret_cast<float*>((uintptr_t)h_grad_peers[r]);
         p.p[r] = reinterpret_cast<float*>((uintptr_t)h_param_peers[r]);
         if (!g.p[r] || !p.p[r] || (h_grad_peers[r] & 15) || (h_param_peers[r] & 15)) return set_error(IDL_EINVAL, "idl_rmsprop_allreduce_step: null / misaligned peer pointer%s", "");
-        if (h_signal_pads) {
-            pads.p[r] = reinterpret_cast<uint32_t*>((uintptr_t)h_signal_pads[r]);
-            if (!pads.p[r]) return set_error(IDL_EINVAL, "idl_rmsprop_allreduce_step: null signal pad%s", "");
-        }
     }
     const long long shard = n_total / world;
-    long long grid = (shard / 4 + 255) / 256;   // one 16-byte unit per thread while it fits one wave: every remote load is in flight at once
-    if (grid > 148 * 8) grid = 148 * 8;         // (all CTAs are co-resident: the in-kernel release of CTA 0 cannot deadlock)
+    long long grid = (shard / 4 + 256 * AR_U - 1) / (256 * AR_U);
+    if (grid > 148) grid = 148;   // measured on 2 and 8 B200s (tools/symm_probe.py): more CTAs do not move the NVLS-bound kernel
     if (grid < 1) grid = 1;
     rmsprop_allreduce_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(g, p, reinterpret_cast<const float*>((uintptr_t)grad_multicast),
                                                                                reinterpret_cast<float*>((uintptr_t)param_multicast), d_square_avg, shard,
-                                                                               rank, world, lr, alpha, eps, weight_decay, pads, d_sync, channel); note_launch();
+                                                                               rank, world, lr, alpha, eps, weight_decay); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }

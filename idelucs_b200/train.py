@@ -95,10 +95,6 @@ class ShardedTrainer(object):
         self._flat_grad, self._flat_param = g, p
         self._gp = (ctypes.c_uint64 * self.world)(*[int(x) for x in self._hg.buffer_ptrs])
         self._pp = (ctypes.c_uint64 * self.world)(*[int(x) for x in self._hp.buffer_ptrs])
-        self._pads = (ctypes.c_uint64 * self.world)(*[int(x) for x in self._hg.signal_pad_ptrs])
-        self._sync = torch.zeros(2, dtype=torch.int32, device=self.dev)
-        if 4 * 34 * self.world > int(self._hg.signal_pad_size):
-            raise RuntimeError("signal pad too small for the in-kernel channels")
         mc_g = int(getattr(self._hg, "multicast_ptr", 0) or 0)
         mc_p = int(getattr(self._hp, "multicast_ptr", 0) or 0)
         self._mc = (mc_g, mc_p) if (mc_g and mc_p) else (0, 0)
@@ -109,11 +105,13 @@ class ShardedTrainer(object):
         lib = _lib.load()
         with torch.cuda.device(self.dev):
             if self._mode == "symm":
-                # ONE kernel: the ranks meet (signal pads), mean of every rank's gradient slice (NVLS multimem.ld_reduce, or peer
-                # loads) -> RMSprop on this rank's slice -> new parameters stored into every rank's buffer, the ranks meet again
+                # ONE kernel: mean of every rank's gradient slice (NVLS multimem.ld_reduce, or peer loads) -> RMSprop on this rank's
+                # slice -> new parameters stored into every rank's buffer; symmetric-memory barriers (5 us each) on both sides
+                self._hg.barrier(channel=0)
                 _lib.check(lib.idl_rmsprop_allreduce_step(self._gp, self._pp, self._mc[0], self._mc[1], _lib.ptr(self._sq),
                                                           self._flat_grad.numel(), self.rank, self.world, self.lr, self.alpha, self.eps,
-                                                          self.weight_decay, self._pads, _lib.ptr(self._sync), 32, _lib.stream_ptr()))
+                                                          self.weight_decay, _lib.stream_ptr()))
+                self._hp.barrier(channel=0)
                 return
             if self._mode == "nccl":
                 dist.all_reduce(self._flat_grad, op=dist.ReduceOp.AVG)

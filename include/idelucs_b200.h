@@ -259,13 +259,11 @@ int idl_rmsprop_step(float* d_param, const float* d_grad, float* d_square_avg, i
  * the gradients (multimem.ld_reduce when a multicast address is given: the switch adds the operands; otherwise one load per peer,
  * rank order), averages, applies idl_rmsprop_step's update to its slice (d_square_avg: n_total / world floats, local) and writes
  * the new parameters into every rank's buffer (multimem.st / one store per peer).  n_total % (4 * world) == 0, world <= 16.
- * Synchronisation of the ranks (all gradients written before, all parameters visible after): inside the kernel when
- * h_signal_pads is given — HOST array of the `world` device addresses of every rank's symmetric-memory signal pad (uint32 flags,
- * zero when idle; the kernel uses flags [channel * world, (channel + 2) * world) with torch's put / wait protocol) together with
- * d_sync, two zero-initialised uint32 words in local device memory (zero again afterwards) — else by the caller. */
+ * The caller synchronises the ranks before (all gradients written) and after (all parameters visible) the call — two
+ * symmetric-memory barriers of 5 us each; handshakes inside the kernel were measured slower (profiles/symm_probe_r2.txt). */
 int idl_rmsprop_allreduce_step(const uint64_t* h_grad_peers, const uint64_t* h_param_peers, uint64_t grad_multicast, uint64_t param_multicast,
                                float* d_square_avg, int64_t n_total, int rank, int world, float lr, float alpha, float eps, float weight_decay,
-                               const uint64_t* h_signal_pads, uint32_t* d_sync, int channel, void* stream);
+                               void* stream);
 
 /* F1 — FASTA ingest on the host.  Replaces the record loop of kmersFasta
  * (idelucs/utils.py:229-261), which the reference re-runs on every pass (n_mimics + 1 times per training run,

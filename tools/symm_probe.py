@@ -54,12 +54,9 @@ def main():
     plain = torch.randn(n, device="cuda")
     shard = torch.zeros(n // world, device="cuda")
 
-    pads = (ctypes.c_uint64 * world)(*[int(x) for x in hg.signal_pad_ptrs])
-    sync = torch.zeros(2, dtype=torch.int32, device="cuda")
-
-    def kern(mcast=True, fused=False):
+    def kern(mcast=True):
         _lib.check(lib.idl_rmsprop_allreduce_step(gp, pp, mc[0] if mcast else 0, mc[1] if mcast else 0, _lib.ptr(sq), n, rank, world,
-                                                  1e-3, 0.99, 1e-8, 0.01, pads if fused else None, _lib.ptr(sync) if fused else None, 32, _lib.stream_ptr()))
+                                                  1e-3, 0.99, 1e-8, 0.01, _lib.stream_ptr()))
 
     def full():
         hg.barrier(channel=0); kern(); hp.barrier(channel=0)
@@ -70,7 +67,6 @@ def main():
 
     res = [("barrier", timed(lambda: hg.barrier(channel=0))), ("kernel (NVLS)" if mc[0] else "kernel (peer)", timed(kern)),
            ("kernel (peer loads/stores)", timed(lambda: kern(False))), ("barrier + kernel + barrier", timed(full)),
-           ("kernel with in-kernel handshakes", timed(lambda: kern(True, True))),
            ("NCCL all_reduce", timed(lambda: dist.all_reduce(plain, op=dist.ReduceOp.AVG))), ("NCCL reduce_scatter + all_gather", timed(rs_ag)),
            ("local rmsprop (full)", timed(lambda: _lib.check(lib.idl_rmsprop_step(_lib.ptr(plain), _lib.ptr(plain), _lib.ptr(plain), n, 1e-3, 0.99, 1e-8, 0.01, 1.0, _lib.stream_ptr()))))]
     if rank == 0:
