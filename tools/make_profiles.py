@@ -29,7 +29,7 @@ for k, t in [o for o in order if o[0].startswith("idl::")][:24]:
 open(os.path.join(P, "launches_%s.md" % tag), "w").write("\n".join(out) + "\n")
 
 # ---- full capture of the dominant kernel
-rep = os.path.join(G, "prof_pc_r1.ncu-rep")
+rep = os.path.join(G, "prof_pc_%s.ncu-rep" % tag)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 r = list(csv.reader(raw.splitlines())); h, u, row = r[0], r[1], r[2]
 keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
