@@ -13,6 +13,7 @@ _OUT_DTYPE = {OUT_COUNTS_I32: torch.int32, OUT_FREQ_F32: torch.float32, OUT_STD_
               OUT_FREQ_F64: torch.float64}
 
 LONG_MIN = 65536   # items at least this long take the chunked path (csrc/chunked.cuh)
+MAX_EDIT_POS = 1 << 29   # edit entries are pos << 3 | val in 32 bits: mutated variants need sequences shorter than this
 
 # hard-coded rates of the reference's AugmentFasta (idelucs/utils.py:330-349)
 P_TRANSITION, P_TRANSVERSION, N_RANDOM_N = 1e-2, 0.5e-2, 20
@@ -86,6 +87,8 @@ def pack_edit_lists(explicit, n_seqs, device):
             pos, val = pos[order], val[order]
             if pos.size and (np.diff(pos) <= 0).any():
                 raise ValueError("explicit edit positions must be unique per sequence")
+            if pos.size and (int(pos[-1]) >= MAX_EDIT_POS or int(pos[0]) < 0):
+                raise ValueError("edit positions must be in [0, 2^29): entries are pos << 3 | val in 32 bits")
             chunks.append(((pos << 3) | val).astype(np.uint32))
             offs.append(offs[-1] + pos.size)
     ent = np.concatenate(chunks) if chunks else np.zeros(0, np.uint32)
@@ -168,6 +171,8 @@ def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_o
         out_off = [s * n_items * F for s in range(S)]
         out_stride = F
     assert out.dtype == _OUT_DTYPE[out_kind] and out.is_contiguous()
+    if seqset.n and int(seqset.lengths.max()) >= MAX_EDIT_POS and any(v.kind != KIND_CLEAN for v in variants):
+        raise _lib.IdelucsB200Error("mimic variants need sequences shorter than 2^29 bases (32-bit edit entries); clean counting takes any length < 2^31")
     varr = _variant_array(variants)
     offs = (ctypes.c_int64 * S)(*[int(o) for o in out_off])
     d_eoff, d_ent = (None, None) if edit_lists is None else edit_lists

@@ -104,7 +104,8 @@ size_t idl_profiles_workspace_bytes(void);
  * out_off[s] + w*out_stride of d_out (elements of the out_kind's type; multiples of 4).
  * The RNG sequence id of an item is seq_id0 + its sequence index.
  * d_edit_off / d_edits: CSR edit lists for IDL_KIND_EXPLICIT variants (entry = pos<<3 | val,
- * val 0..3 = set A/C/G/T, 4 = set N; position-sorted and unique per list), n_seqs_total =
+ * val 0..3 = set A/C/G/T, 4 = set N; position-sorted and unique per list; positions < 2^29, which also bounds the length of
+ * sequences that take a non-clean variant — clean counting accepts any length < 2^31), n_seqs_total =
  * number of sequences the CSR is indexed over.  d_mean/d_scale: float32[4^k] for
  * IDL_OUT_STD_F32.  accumulate != 0 (COUNTS only) adds into d_out like kmers.pyx does.
  * d_status int32[n_items] (optional, zero on entry): scratch flags of the fast kernels (bit 1 marks items handed to the generic
