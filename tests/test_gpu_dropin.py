@@ -150,3 +150,22 @@ def test_cgr_and_reduce_match_oracle(fasta_files):
     x = U.AugmentFasta(fasta_files["Influenza-A"], 3, k=4, reduce=True)
     assert x.shape == (3 * 949, 2, 136) and x.dtype == np.float32 and np.isfinite(x).all()
     assert abs(float(x[:949, 0].mean())) < 1e-3      # t_norm column is standardised with its own statistics
+
+
+def test_cli_embedding_path_and_small_model(golden_dir, fasta_files, tmp_path, monkeypatch):
+    """the CLI orchestration around the hot path: --n_clusters 0 (C = 200 output units + HDBSCAN on the latent space,
+    idelucs/__main__.py:75-83, 149-156), the voter ensemble with fuzzy maxima (utils.py:582-602) and model_size='small'
+    (canonical k-mers + myNet, models.py:60-66) run end to end on the device path"""
+    from idelucs_b200 import __main__ as cli
+    monkeypatch.chdir(tmp_path)
+    gt = os.path.join(golden_dir, "Actinopterygii_GT.tsv")
+    base = dict(sequence_file=fasta_files["Actinopterygii"], GT_file=gt, k=6, n_mimics=3, batch_sz=256, optimizer="RMSprop", weight=0.25, lr=1e-3,
+                scheduler="None", plot=False)
+    base["lambda"] = 2.8
+    torch.manual_seed(0); np.random.seed(0)
+    y = cli.run(dict(base, n_clusters=0, n_epochs=4, n_voters=1, model_size="linear"))
+    assert np.asarray(y).shape == (113,)
+    y = cli.run(dict(base, n_clusters=3, n_epochs=4, n_voters=2, model_size="small"))
+    assert np.asarray(y).shape == (113,) and set(np.unique(y)) <= {0, 1, 2}
+    out = [os.path.join(dp, f) for dp, _, fs in os.walk(str(tmp_path)) for f in fs if f == "assignments.tsv"]
+    assert len(out) >= 1 and open(out[0]).readline().strip().split("\t") == ["sequence_id", "assignment", "confidence_score"]
