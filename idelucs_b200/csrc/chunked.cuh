@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(1024) ch_plan_kernel(const ChParams cp) {
 
 // ---- tiles ----
 struct ChSmem {
+    alignas(16) uint32_t tcodes[(CH_TILE_BLOCKS + 2) * 4 + 8];   // the tile's packed bases incl. one context block on each side ...
+    alignas(16) uint32_t tmask[(CH_TILE_BLOCKS + 2) * 2 + 8];    // ... and reset flags (window lookups of the edits hit shared memory)
     uint32_t list[LIST_CAP + 8];
     uint32_t gtabs[STABS][RNG_BLOCK];
     VarDesc svars[SVARS];
@@ -152,8 +154,8 @@ __global__ void __launch_bounds__(CH_NT, 2) ch_tile_kernel(const ChParams cp, co
         const long long seq = p.sidx ? (long long)p.sidx[item] : item;
         const int L = p.len[seq];
         const long long c0 = p.chunk_off[seq];
-        const uint32_t* codes = p.codes + c0 * 4;
-        const uint32_t* nmask = p.nmask + c0 * 2;
+        const uint32_t* gcodes = p.codes + c0 * 4;
+        const uint32_t* gnmask = p.nmask + c0 * 2;
         const uint32_t seq_id = (uint32_t)(p.seq_id0 + seq);
         const int nblocks = (L + RNG_BLOCK - 1) / RNG_BLOCK;
         const long long t_item0 = cp.tile_off[item], t_item1 = cp.tile_off[item + 1];
@@ -171,12 +173,22 @@ __global__ void __launch_bounds__(CH_NT, 2) ch_tile_kernel(const ChParams cp, co
         for (; t < t_end; ++t) {
             const int b0 = (int)(t - t_item0) * CH_TILE_BLOCKS;
             const int b1 = b0 + CH_TILE_BLOCKS < nblocks ? b0 + CH_TILE_BLOCKS : nblocks;
+            // ---- stage the tile (+ one 64-base block of context on each side, + one slack word) ----
+            const int sb0 = b0 > 0 ? b0 - 1 : 0, sb1 = b1 + 1 < nblocks ? b1 + 1 : nblocks;
+            __syncthreads();   // the previous tile's lookups are done
+            for (int i = tid; i < (sb1 - sb0) * 4 + 4; i += CH_NT) sm.tcodes[i] = __ldg(gcodes + sb0 * 4 + i);
+            for (int i = tid; i < (sb1 - sb0) * 2 + 2; i += CH_NT) sm.tmask[i] = __ldg(gnmask + sb0 * 2 + i);
+            __syncthreads();
+            // absolute word indices keep working through these (only staged words are ever dereferenced)
+            const uint32_t* codes = sm.tcodes - sb0 * 4;
+            const uint32_t* nmask = sm.tmask - sb0 * 2;
             // ---- clean window ends of the tile (half-chunks 2 b0 .. 2 b1) ----
             for (int h = 2 * b0 + tid; h < 2 * b1; h += CH_NT) {
-                const uint2 w = __ldg(reinterpret_cast<const uint2*>(codes) + h);
+                const uint2 w = make_uint2(codes[2 * h], codes[2 * h + 1]);
                 count_half<K>(codes, nmask, h, w.x, w.y, [&](uint32_t kmer) { atomicAdd(&hist[kmer], 1); });
             }
-            // ---- dense slots: edits of the tile's blocks (+ one context block on each side) -> +-1 deltas ----
+            // ---- dense slots: edits of the tile's blocks (+ context) -> +-1 deltas.  Bernoulli slots jointly: work item =
+            // ---- (slot, block), rounds of CH_NT items, one list with a segment per slot; explicit lists stay in global memory ----
             int span = b1 - b0;
             for (int s0 = b0; s0 < b1 && nd > 0;) {
                 const int s1 = s0 + span < b1 ? s0 + span : b1;
@@ -186,44 +198,50 @@ __global__ void __launch_bounds__(CH_NT, 2) ch_tile_kernel(const ChParams cp, co
                 const long long hi = (long long)s1 * RNG_BLOCK;
                 int base = 0;
                 bool over = false;
-                for (int d = 0; d < nd; ++d) {
-                    const VarDesc vd = vars[sm.dense_var[d]];
-                    if (vd.kind == KIND_EXPLICIT) { if (tid == 0) sm.seg_off[d] = base; continue; }   // explicit lists stay in global memory
-                    for (int r0 = 0; r0 < nbt; r0 += CH_NT) {   // uniform trip count (CTA scan inside)
-                        const int b = g0 + r0 + tid;
-                        BlockMasks m;
-                        m.a = m.b = m.ch = 0;
-                        if (b < g1) m = block_masks(vd.kind, p.seed, seq_id, (uint32_t)vd.rng_id, b, L, nmask, table(vd.tab1), vd.slope1, table(vd.tab2), vd.slope2);
-                        int total;
-                        const int off = block_exscan<CH_NT>(block_masks_count(m), sm.scan, &total);
-                        if (base + total > LIST_CAP) { over = true; break; }   // uniform
-                        if (r0 == 0 && tid == 0) sm.seg_off[d] = base;
-                        block_masks_write(m, b, codes, sm.list + base + off);
-                        base += total;
+                const int W = nd * nbt;
+                for (int w0 = 0; w0 < W; w0 += CH_NT) {   // uniform trip count (CTA scan inside)
+                    const int w = w0 + tid;
+                    int d = 0, b = -1;
+                    BlockMasks m;
+                    m.a = m.b = m.ch = 0;
+                    if (w < W) {
+                        d = w / nbt;
+                        const VarDesc vd = vars[sm.dense_var[d]];
+                        if (vd.kind != KIND_EXPLICIT) {
+                            b = g0 + (w - d * nbt);
+                            m = block_masks(vd.kind, p.seed, seq_id, (uint32_t)vd.rng_id, b, L, nmask, table(vd.tab1), vd.slope1, table(vd.tab2), vd.slope2);
+                        }
+                        if (w - d * nbt == 0) sm.seg_off[d] = -1;   // set below (first block of the slot)
                     }
-                    if (over) break;
+                    int total;
+                    const int off = block_exscan<CH_NT>(block_masks_count(m), sm.scan, &total);
+                    if (base + total > LIST_CAP) { over = true; break; }   // uniform
+                    if (w < W && w - d * nbt == 0) sm.seg_off[d] = base + off;
+                    if (b >= 0) block_masks_write(m, b, codes, sm.list + base + off);
+                    base += total;
                 }
                 if (over) { span = span > 1 ? span >> 1 : 1; __syncthreads(); continue; }   // fewer blocks at a time (three always fit)
                 if (tid == 0) sm.seg_off[nd] = base;
                 __syncthreads();
+                for (int i = tid; i < base; i += CH_NT) {   // thread <-> edit of any Bernoulli slot
+                    int d = 0;
+                    while (i >= sm.seg_off[d + 1]) ++d;
+                    const int so = sm.seg_off[d], n = sm.seg_off[d + 1] - so;
+                    const int pos = (int)(sm.list[i] >> 3);
+                    int* dh = hist + (1 + d) * CH_F;
+                    if (pos >= lo && pos < hi) apply_entry<K>(codes, nmask, L, sm.list + so, n, i - so, [&](uint32_t kmer, int dd) { atomicAdd(&dh[kmer], dd); });
+                }
                 for (int d = 0; d < nd; ++d) {
                     const VarDesc vd = vars[sm.dense_var[d]];
+                    if (vd.kind != KIND_EXPLICIT) continue;
                     int* dh = hist + (1 + d) * CH_F;
-                    if (vd.kind == KIND_EXPLICIT) {
-                        const long long li = (long long)vd.explicit_idx * p.n_seqs_total + seq;
-                        const uint32_t* glist = p.edits + p.edit_off[li];
-                        const int n = (int)(p.edit_off[li + 1] - p.edit_off[li]);
-                        int a = 0, z = n;   // first entry with pos >= lo
-                        while (a < z) { const int mid = (a + z) >> 1; if ((int)(glist[mid] >> 3) < lo) a = mid + 1; else z = mid; }
-                        for (int i = a + tid; i < n && (long long)(glist[i] >> 3) < hi; i += CH_NT)
-                            apply_entry<K>(codes, nmask, L, glist, n, i, [&](uint32_t kmer, int dd) { atomicAdd(&dh[kmer], dd); });
-                    } else {
-                        const int so = sm.seg_off[d], n = sm.seg_off[d + 1] - so;
-                        for (int i = tid; i < n; i += CH_NT) {
-                            const int pos = (int)(sm.list[so + i] >> 3);
-                            if (pos >= lo && pos < hi) apply_entry<K>(codes, nmask, L, sm.list + so, n, i, [&](uint32_t kmer, int dd) { atomicAdd(&dh[kmer], dd); });
-                        }
-                    }
+                    const long long li = (long long)vd.explicit_idx * p.n_seqs_total + seq;
+                    const uint32_t* glist = p.edits + p.edit_off[li];
+                    const int n = (int)(p.edit_off[li + 1] - p.edit_off[li]);
+                    int a = 0, z = n;   // first entry with pos >= lo
+                    while (a < z) { const int mid = (a + z) >> 1; if ((int)(glist[mid] >> 3) < lo) a = mid + 1; else z = mid; }
+                    for (int i = a + tid; i < n && (long long)(glist[i] >> 3) < hi; i += CH_NT)
+                        apply_entry<K>(codes, nmask, L, glist, n, i, [&](uint32_t kmer, int dd) { atomicAdd(&dh[kmer], dd); });
                 }
                 __syncthreads();   // the list is rewritten by the next span / tile
                 s0 = s1;

@@ -1015,14 +1015,15 @@ namespace idl {
 // K4: column statistics / scaler / standardise
 // ---------------------------------------------------------------------------------------
 constexpr int CS_NT = 128;
-constexpr int CS_ROWS = 2048;  // rows per partial
+// rows per partial: 256 for small matrices (enough CTAs to fill the GPU), more when that would mean over 1024 parts
+static inline long long cs_rows(long long n) { const long long r = (n + 1023) / 1024; return r > 256 ? r : 256; }
 
 template <typename T>
-__global__ void __launch_bounds__(CS_NT) colstats_kernel(const T* __restrict__ x, long long n, int F,
+__global__ void __launch_bounds__(CS_NT) colstats_kernel(const T* __restrict__ x, long long n, int F, long long rows_per_part,
                                                           double* __restrict__ partials, double* __restrict__ part_n) {
     const int col = blockIdx.x * CS_NT + threadIdx.x;
-    const long long r0 = (long long)blockIdx.y * CS_ROWS;
-    const long long r1 = r0 + CS_ROWS < n ? r0 + CS_ROWS : n;
+    const long long r0 = (long long)blockIdx.y * rows_per_part;
+    const long long r1 = r0 + rows_per_part < n ? r0 + rows_per_part : n;
     if (col == 0) part_n[blockIdx.y] = (double)(r1 - r0);
     if (col >= F) return;
     // shifted-data sums (shift = first row of this part): exact zeros for a constant column
@@ -1643,13 +1644,13 @@ int idl_kmer_counts(const uint32_t* d_codes, const uint32_t* d_nmask, const int6
                         d_workspace, workspace_bytes, stream);
 }
 
-int idl_colstats_parts(int64_t n) { return (int)((n + CS_ROWS - 1) / CS_ROWS); }
+int idl_colstats_parts(int64_t n) { return n > 0 ? (int)((n + cs_rows(n) - 1) / cs_rows(n)) : 0; }
 
 int idl_colstats(const void* d_x, int is_f64, int64_t n, int F, double* d_partials, double* d_part_n, void* stream) {
     if (!d_x || !d_partials || !d_part_n || n <= 0 || F <= 0) return set_error(IDL_EINVAL, "idl_colstats: bad argument%s", "");
     const dim3 grid((F + CS_NT - 1) / CS_NT, (unsigned)idl_colstats_parts(n));
-    if (is_f64) colstats_kernel<double><<<grid, CS_NT, 0, (cudaStream_t)stream>>>((const double*)d_x, n, F, d_partials, d_part_n);
-    else colstats_kernel<float><<<grid, CS_NT, 0, (cudaStream_t)stream>>>((const float*)d_x, n, F, d_partials, d_part_n);
+    if (is_f64) colstats_kernel<double><<<grid, CS_NT, 0, (cudaStream_t)stream>>>((const double*)d_x, n, F, cs_rows(n), d_partials, d_part_n);
+    else colstats_kernel<float><<<grid, CS_NT, 0, (cudaStream_t)stream>>>((const float*)d_x, n, F, cs_rows(n), d_partials, d_part_n);
     note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;

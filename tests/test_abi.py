@@ -45,7 +45,7 @@ def test_argument_validation_without_gpu():
     lib = _lib.load()
     assert lib.idl_iid_loss_max_clusters() == 256
     assert lib.idl_iid_loss_workspace_bytes(5) > 0 and lib.idl_iid_loss_workspace_bytes(1000) == 0
-    assert lib.idl_colstats_parts(1) == 1 and lib.idl_colstats_parts(2049) == 2
+    assert lib.idl_colstats_parts(1) == 1 and lib.idl_colstats_parts(257) == 2 and lib.idl_colstats_parts(10 ** 7) <= 1024
     assert lib.idl_profiles_workspace_bytes() > 1024
     # null pointers are rejected before any CUDA call
     rc = lib.idl_kmer_counts(None, None, None, None, 1, 6, None, 0, None, 0, None)
