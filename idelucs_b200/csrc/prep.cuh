@@ -22,11 +22,20 @@
 
 namespace idl {
 
+#ifndef PR_PACKED
+#define PR_PACKED 0                        // 0: int32 bins, 4 CTAs/SM (0.70 ms per 20 000 sequences); 1: uint16-pair histogram + 1024-entry edit list,
+                                           //    39 KB of shared memory, 5 CTAs/SM — measured slower (0.74 ms: packed updates + the 48-register cap)
+#endif
 constexpr int PR_NT = 256;
-constexpr int PR_LIST = 2048;              // edits of all dense slots of one sequence
+constexpr int PR_LIST = PR_PACKED ? 1024 : 2048;   // edits of all dense slots of one sequence
+constexpr int PR_MINB = PR_PACKED ? 5 : 4;
 
 struct PrSmem {
+#if PR_PACKED
+    alignas(16) uint32_t hist[PC_F / 2];      // clean histogram, then slot 0's: two uint16 counters per word
+#else
     alignas(16) int hist[PC_F];               // clean histogram, then slot 0's (packed to uint16 on the way out)
+#endif
     alignas(16) uint32_t sseq[2][PC_SSEQ_W];  // staged sequences (codes | mask): the next item's words arrive (cp.async) while this one is processed
     alignas(16) uint32_t list[PR_LIST + 8];
     alignas(16) uint16_t delta[PC_DELTA];
@@ -50,8 +59,17 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 // counts the windows ending in the 16-base code word u of a staged sequence (idelucs/kmers.pyx:36-47) with shared atomics
 // (ATOMS.POPC.INC); returns how many were counted.  Thread <-> word: a 10 kb sequence is 628 work items (2.5 rounds of 256 threads).
+#if PR_PACKED
+__device__ __forceinline__ void pr_bump(uint32_t* hist, uint32_t kmer, int d) {   // +-1 on a packed counter (the sum of all updates never leaves [0, 65535])
+    if (d > 0) atomicAdd(&hist[kmer >> 1], 1u << ((kmer & 1u) * 16u)); else atomicSub(&hist[kmer >> 1], 1u << ((kmer & 1u) * 16u));
+}
+using PrHist = uint32_t;
+#else
+__device__ __forceinline__ void pr_bump(int* hist, uint32_t kmer, int d) { atomicAdd(&hist[kmer], d); }
+using PrHist = int;
+#endif
 template <int K>
-__device__ __forceinline__ int pr_count_word(const uint32_t* codes, const uint32_t* nmask, int u, int* hist) {
+__device__ __forceinline__ int pr_count_word(const uint32_t* codes, const uint32_t* nmask, int u, PrHist* hist) {
     constexpr uint32_t KMASK = (1u << (2 * K)) - 1u;
     const uint32_t w = codes[u], prev = u > 0 ? codes[u - 1] : 0u;
     const uint32_t m = nmask[u >> 1], mprev = u > 1 ? nmask[(u >> 1) - 1] : 0xFFFFFFFFu;   // sequence start = preceded by resets (kmers.pyx:14)
@@ -62,19 +80,19 @@ __device__ __forceinline__ int pr_count_word(const uint32_t* codes, const uint32
     const uint32_t inv = (uint32_t)(inv64 >> ((u & 1) ? 0 : 16)) & 0xFFFFu;   // bit 15-j = window ending at base j of this word
     if (inv == 0u) {   // the common case: no reset near the word, 16 unconditional updates
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(&hist[funnel_r(w, prev, 30 - 2 * j) & KMASK], 1);
+        for (int j = 0; j < 16; ++j) pr_bump(hist, funnel_r(w, prev, 30 - 2 * j) & KMASK, 1);
         return 16;
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-        if (!((inv >> (15 - j)) & 1u)) atomicAdd(&hist[funnel_r(w, prev, 30 - 2 * j) & KMASK], 1);
+        if (!((inv >> (15 - j)) & 1u)) pr_bump(hist, funnel_r(w, prev, 30 - 2 * j) & KMASK, 1);
     return __popc(~inv & 0xFFFFu);
 }
 
 struct PrItem { int L; long long c0; uint32_t seq_id; };
 
 template <int K>
-__global__ void __launch_bounds__(PR_NT, 4) prep_kernel(const ProfParams p, const __grid_constant__ Plan plan) {
+__global__ void __launch_bounds__(PR_NT, PR_MINB) prep_kernel(const ProfParams p, const __grid_constant__ Plan plan) {
     static_assert(K == PC_K, "the prepare pass is specialised for k = 6");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PrSmem& sm = *reinterpret_cast<PrSmem*>(smem_raw);
@@ -152,7 +170,7 @@ __global__ void __launch_bounds__(PR_NT, 4) prep_kernel(const ProfParams p, cons
             sm.nvalid = 0; sm.n_delta = 0;
             for (int q = 0; q < PC_DENSE; ++q) sm.dtot[q] = 0;
         }
-        for (int i = tid; i < PC_F / 4; i += PR_NT) reinterpret_cast<int4*>(sm.hist)[i] = make_int4(0, 0, 0, 0);
+        for (int i = tid; i < (int)(sizeof(sm.hist) / 16); i += PR_NT) reinterpret_cast<uint4*>(sm.hist)[i] = make_uint4(0u, 0u, 0u, 0u);
         const int L = cur.L;
         const uint32_t seq_id = cur.seq_id;
         const int nchunks = chunks_of(L);
@@ -258,12 +276,12 @@ __global__ void __launch_bounds__(PR_NT, 4) prep_kernel(const ProfParams p, cons
                             if (d[t] & 0x1000u) {
                                 const uint32_t km = d[t] & 0xFFFu;
                                 sm.delta[slot++] = (uint16_t)(km | tag);
-                                if (to_hist) atomicSub(&sm.hist[km], 1);
+                                if (to_hist) pr_bump(sm.hist, km, -1);
                             }
                             if (d[t] & 0x10000000u) {
                                 const uint32_t km = (d[t] >> 16) & 0xFFFu;
                                 sm.delta[slot++] = (uint16_t)(km | tag | 0x8000u);
-                                if (to_hist) atomicAdd(&sm.hist[km], 1);
+                                if (to_hist) pr_bump(sm.hist, km, +1);
                             }
                         }
                         if (dt) atomicAdd(&sm.dtot[jj], dt);
@@ -285,11 +303,15 @@ __global__ void __launch_bounds__(PR_NT, 4) prep_kernel(const ProfParams p, cons
         } else {
             // ---- hand over: slot 0's histogram, the delta list, the totals ----
             const int n_delta = sm.n_delta;
+#if PR_PACKED
+            for (int i = tid; i < PC_F / 8; i += PR_NT) hist_out[(size_t)item * (PC_F / 8) + i] = reinterpret_cast<const uint4*>(sm.hist)[i];
+#else
             for (int i = tid; i < PC_F / 8; i += PR_NT) {   // 8 bins -> one 16-byte store of uint16 counts (every count <= 20 480)
                 const int4 lo = reinterpret_cast<const int4*>(sm.hist)[2 * i], hi = reinterpret_cast<const int4*>(sm.hist)[2 * i + 1];
                 hist_out[(size_t)item * (PC_F / 8) + i] = make_uint4((uint32_t)lo.x | ((uint32_t)lo.y << 16), (uint32_t)lo.z | ((uint32_t)lo.w << 16),
                                                                      (uint32_t)hi.x | ((uint32_t)hi.y << 16), (uint32_t)hi.z | ((uint32_t)hi.w << 16));
             }
+#endif
             const int nq = (n_delta * 2 + 15) >> 4;
             for (int i = tid; i < nq; i += PR_NT) delta_out[(size_t)item * (PC_DELTA / 8) + i] = reinterpret_cast<const uint4*>(sm.delta)[i];
             if (tid == 0) {
