@@ -245,6 +245,62 @@ def d2h_ceiling(dev_buf, host_buf, steps, world, dist, torch):
     return world * dev_buf.numel() * dev_buf.element_size() / dt / 1e9
 
 
+def c3_config(n, world):
+    """the workload description both arms print (the reference arm times a bounded sample of it, stated in its cpu_baseline.sample)"""
+    return {"workload": "synthetic %d sequences x %d bp per GPU, k=%d, n_mimics=%d, featurisation only "
+                        "(BASELINE.json configs[2])" % (n, SEQ_LEN, K, N_MIMICS),
+            "profiles_per_step": world * n * V, "output": "float32 [51, N, 4096] standardised, %.1f GB per GPU per step" % (V * n * F * 4 / 1e9),
+            "cache": "inputs+outputs per step exceed L2 (126 MB) by >100x, no flush needed",
+            "mutation_rates": "transition 1e-2, transversion 5e-3, Random_N 20 (idelucs/utils.py:330-349)"}
+
+
+def real_file_timings(dev):
+    """BASELINE.json configs[0] / configs[1] on the real files that exist in this checkout (Example/Influenza-A.fas, k = 4 / 5 / 6, and
+    Example/Actinopterygii.fas, k = 6; Vertebrata.fas is absent from the reference checkout): AugmentFasta(file, n_mimics=3) end to end
+    through this repo's API (parse, H2D, featurise, D2H of x_train) next to the oracle's single-threaded restatement of the reference
+    function (serial Python transforms + the oracle's vectorised numpy counter, which is faster than a per-record Cython call
+    for these short records)."""
+    import gzip
+    import shutil
+    import tempfile
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import idelucs_oracle as orc
+    from idelucs_b200 import utils as U
+    out = []
+    tmp = tempfile.mkdtemp(prefix="idl_real_")
+    try:
+        for stem, ks in (("Influenza-A", (4, 5, 6)), ("Actinopterygii", (6,))):
+            src = os.path.join(ROOT, "tests", "golden", stem + ".fas.gz")
+            if not os.path.exists(src):
+                continue
+            path = os.path.join(tmp, stem + ".fas")
+            with gzip.open(src, "rb") as fi, open(path, "wb") as fo:
+                shutil.copyfileobj(fi, fo)
+            for k in ks:
+                U._seqset_cache.clear()
+                U.AugmentFasta(path, 3, k=k)                  # warm-up (library load, allocator)
+                ts = []
+                for _ in range(3):
+                    U._seqset_cache.clear()                   # parse + pack again every time, like the reference re-reads the file
+                    torch.cuda.synchronize(dev)
+                    t0 = time.perf_counter()
+                    x = U.AugmentFasta(path, 3, k=k)
+                    ts.append(time.perf_counter() - t0)
+                np.random.seed(0)
+                t0 = time.perf_counter()
+                xr = orc.AugmentFasta(path, 3, k=k)
+                t_cpu = time.perf_counter() - t0
+                n_prof = x.shape[0] // 3 * 4
+                out.append({"file": stem + ".fas", "k": k, "pairs": int(x.shape[0]), "ours_ms": min(ts) * 1e3, "ours_profiles_per_s": n_prof / min(ts),
+                            "cpu_port_ms": t_cpu * 1e3, "cpu_port_profiles_per_s": n_prof / t_cpu, "cpu_cores": 1,
+                            "same_shape": list(x.shape) == list(xr.shape)})
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -459,6 +515,12 @@ def run_ours(args):
             train["cpu_baseline"] = cpu_train_reference(args.cpu_train_pairs, 5, 512, os.cpu_count() or 1)
     if rank != 0:
         return
+    real = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            real = real_file_timings(dev)
+        except Exception as e:  # noqa: BLE001 — a side measurement must not take the bench line down
+            real = {"error": repr(e)}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -470,12 +532,9 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": "profiles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "synthetic %d sequences x %d bp per GPU, k=%d, n_mimics=%d, featurisation only "
-                                   "(BASELINE.json configs[2])" % (n, SEQ_LEN, K, N_MIMICS),
-                       "profiles_per_step": world * n * V, "output": "float32 [51, N, 4096] standardised, %.1f GB per GPU per step"
-                                   % (V * n * F * 4 / 1e9), "cache": "inputs+outputs per step exceed L2 (126 MB) by >100x, no flush needed",
-                       "mutation_rates": "transition 1e-2, transversion 5e-3, Random_N 20 (idelucs/utils.py:330-349)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": n_launches, "roofline": roofline, "cpu_baseline": cpu, "train": train, "fasta_ingest": ingest}
+            "config": c3_config(n, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": n_launches, "roofline": roofline, "cpu_baseline": cpu, "train": train, "fasta_ingest": ingest,
+            "real_files": real}
     emit(line)
 
 
@@ -714,10 +773,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "profiles/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": n * V / value * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic %d sequences x %d bp, k=%d, n_mimics=%d, featurisation only "
-                                   "(bounded sample of BASELINE.json configs[2])" % (n, SEQ_LEN, K, N_MIMICS)},
+            "config": c3_config(args.n_seqs, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": value, "unit": "profiles/s", "cores": cores, "kind": "port",
-                             "sample": "per step: %d cores x %d sequences x 51 passes, oracle restatement of AugmentFasta driving %s"
+                             "sample": "per step a bounded sample of the workload: %d cores x %d synthetic 10 kb sequences x 51 passes (profiles/s "
+                                       "extrapolates: sequences are independent), oracle restatement of AugmentFasta driving %s"
                                        % (cores, args.ref_seqs_per_core, kind)},
             "e2e": {"value": value, "unit": "profiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
