@@ -93,6 +93,65 @@ def cpu_reference(n_seq_per_core, cores):
     return cores * n_seq_per_core * V / busy, busy, wall, res[0][1]
 
 
+def train_breakdown(tr, torch):
+    """device time of the parts of one training step, each captured 20x in its own CUDA graph and replayed (no launch overhead,
+    like the step itself): pair-batch featurisation, MLP forward + backward, the two fused losses, the optimiser step"""
+    from idelucs_b200.LossFunctions import IID_loss, info_nce_loss_stacked, train_losses
+
+    def timed(fn, reps=20, replays=5):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(replays):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / (reps * replays) * 1e3
+
+    x = tr._batch
+    B = x.shape[0] // 2
+    with torch.no_grad():
+        z0, h0 = tr.net(x)
+    z0, h0 = z0.detach().clone().requires_grad_(True), h0.detach().clone().requires_grad_(True)
+
+    def mlp():
+        tr._flat_grad.zero_()
+        z, h = tr.net(x)
+        (z.sum() + h.sum()).backward()
+
+    def iid():
+        z0.grad = None
+        IID_loss(z0[:B], z0[B:], lamb=tr.lamb).backward()
+
+    def nce():
+        h0.grad = None
+        info_nce_loss_stacked(h0, 0.85).backward()
+
+    def both():
+        z0.grad = None; h0.grad = None
+        train_losses(z0, h0, tr.lamb, tr.weight, 0.85).backward()
+
+    out = {"featurise_pair_batch_us": timed(lambda: tr._featurise(tr._ids)), "mlp_forward_backward_us": timed(mlp),
+           "losses_forward_backward_us": timed(both), "iid_loss_alone_us": timed(iid), "info_nce_alone_us": timed(nce)}
+    if tr.world == 1:
+        out["optimizer_step_us"] = timed(tr._optimizer_step)
+    out["note"] = ("each part replayed from its own CUDA graph; in the step the featurisation of the next batch runs on a side stream "
+                   "under the MLP, so the parts add up to more than the step")
+    return out
+
+
 def cpu_train_reference(n_pairs, n_clusters, batch_sz, cores):
     """pairs/s of the reference's training epoch on the host (oracle/train_port.py: idelucs/models.py:113-143 with torch on the
     CPU, torch.set_num_threads(cpu_count - 2) as idelucs/__main__.py:316, DataLoader(shuffle=True, num_workers=4) as
@@ -484,7 +543,8 @@ def run_ours(args):
         st = SeqSet.from_ascii(a, np.arange(nt + 1, dtype=np.int64) * Lt, device=dev)
         st._d_ascii = None
         del a
-        tr = ShardedTrainer(st, k=K, n_clusters=5, n_mimics=N_MIMICS, batch_sz=512, seed=7, seq_id0=rank * nt, world=world)
+        tr = ShardedTrainer(st, k=K, n_clusters=5, n_mimics=N_MIMICS, batch_sz=512, seed=7, seq_id0=rank * nt, world=world,
+                            overlap_featurise_with=os.environ.get("IDL_TRAIN_OVERLAP", "forward"))
         graphed = tr.enable_cuda_graph()   # N > 1: the flat-gradient all-reduce is captured with the step
         for _ in range(10):
             tr.step()
@@ -511,6 +571,13 @@ def run_ours(args):
                            "n_clusters=5, RMSprop, (1-w) InfoNCE + w IIC (BASELINE.json configs[3]); shuffled epochs; batches regenerated "
                            "on a side stream by the mimic kernel; fused InfoNCE / IIC / RMSprop kernels, MLP in PyTorch fp32; "
                            "gradient mean + RMSprop + parameter broadcast as one kernel inside the step's CUDA graph" % (nt * world, world)}
+        peak_gbs, _ = measured_peak()
+        train["hbm_floor_fraction"] = train["pairs_per_s"] / world * 65536 / (peak_gbs * 1e9)   # 2 profiles written + 2 read per pair
+        if rank == 0:
+            try:
+                train["breakdown"] = train_breakdown(tr, torch)
+            except Exception as e:  # noqa: BLE001 — a side measurement must not take the bench line down
+                train["breakdown"] = {"error": repr(e)}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             train["cpu_baseline"] = cpu_train_reference(args.cpu_train_pairs, 5, 512, os.cpu_count() or 1)
     if rank != 0:

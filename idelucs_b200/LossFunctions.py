@@ -1,8 +1,9 @@
 """Loss functions with the reference's names and signatures (idelucs/LossFunctions.py).
 
 ``IID_loss`` / ``compute_joint`` run the fused sm_100a kernel K5 (forward + backward in one launch) through the C ABI.
-``info_nce_loss`` runs the fused InfoNCE kernels (idl_info_nce: normalise, similarity, masked
-log-softmax, cross-entropy and the gradient in three launches) on CUDA tensors."""
+``info_nce_loss`` runs the fused InfoNCE kernels (idl_nce_*: normalise, masked log-softmax +
+cross-entropy + gradient weights, normalisation backward) around two strict-fp32 cuBLAS GEMMs on CUDA tensors."""
+import ctypes
 import sys
 
 import torch
@@ -66,21 +67,33 @@ def compute_joint(x_out, x_tf_out):
 _targets = {}
 
 
+def _info_nce_device(x, temperature):
+    """(loss 0-d tensor, dh [n2, D]) of the stacked latent x (float32, contiguous, CUDA): idl_nce_normalize -> S = fn fn^T (cuBLAS,
+    strict fp32) -> idl_nce_softmax_xent (loss; S becomes W in place) -> dfn = W fn (cuBLAS) -> idl_nce_normalize_backward"""
+    lib = _lib.load()
+    n2, D = x.shape
+    dev = x.device
+    fn = torch.empty_like(x)
+    scratch = torch.empty(3 * n2, dtype=torch.float32, device=dev)     # inv_norm | lse | rowloss
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dh = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr()
+        _lib.check(lib.idl_nce_normalize(_lib.ptr(x), n2, D, _lib.ptr(fn), _lib.ptr(scratch), st))
+        sim = torch.mm(fn, fn.t())
+        _lib.check(lib.idl_nce_softmax_xent(_lib.ptr(sim), n2, float(temperature), ctypes.c_void_p(scratch.data_ptr() + 4 * n2),
+                                            ctypes.c_void_p(scratch.data_ptr() + 8 * n2), _lib.ptr(loss), st))
+        dfn = torch.mm(sim, fn)
+        _lib.check(lib.idl_nce_normalize_backward(_lib.ptr(dfn), _lib.ptr(fn), _lib.ptr(scratch), n2, D, _lib.ptr(dh), st))
+    return loss, dh
+
+
 class _InfoNCE(torch.autograd.Function):
-    """fused CUDA form (idl_info_nce): value and gradient with respect to the stacked latent in three launches"""
+    """fused CUDA form: value and gradient with respect to the stacked latent, computed together in the forward"""
 
     @staticmethod
     def forward(ctx, h, temperature):
-        lib = _lib.load()
-        x = h.detach().contiguous().float()
-        n2, D = x.shape
-        loss = torch.empty((), dtype=torch.float32, device=x.device)
-        dh = torch.empty_like(x)
-        from .featurise import _workspace
-        with torch.cuda.device(x.device):
-            ws = _workspace(x.device, lib.idl_info_nce_workspace_bytes(n2, D), "nce%d_%d" % (n2, D))
-            _lib.check(lib.idl_info_nce(_lib.ptr(x), n2, D, float(temperature), _lib.ptr(loss), _lib.ptr(dh), _lib.ptr(ws), ws.numel(),
-                                        _lib.stream_ptr()))
+        loss, dh = _info_nce_device(h.detach().contiguous().float(), temperature)
         ctx.save_for_backward(dh)
         return loss
 
@@ -88,6 +101,42 @@ class _InfoNCE(torch.autograd.Function):
     def backward(ctx, grad_out):
         (dh,) = ctx.saved_tensors
         return grad_out * dh, None
+
+
+class _TrainLosses(torch.autograd.Function):
+    """(1 - w) info_nce_loss + w IID_loss of one stacked forward (idelucs/models.py:128) as ONE autograd node: the two fused
+    loss paths run back to back on the stacked outputs (no slicing copies, no per-loss autograd bookkeeping) and leave the
+    gradients with respect to z and h ready."""
+
+    @staticmethod
+    def forward(ctx, z, h, lamb, weight, temperature, EPS):
+        lib = _lib.load()
+        zz = z.detach().contiguous().float()
+        n2, C = zz.shape
+        B = n2 // 2
+        nce, dh = _info_nce_device(h.detach().contiguous().float(), temperature)
+        iid = torch.empty((), dtype=torch.float32, device=zz.device)
+        dz = torch.empty_like(zz)
+        with torch.cuda.device(zz.device):
+            ws = _ws(zz.device, C)
+            half = 4 * B * C   # bytes: rows B.. of z are the second view
+            _lib.check(lib.idl_iid_loss(_lib.ptr(zz), ctypes.c_void_p(zz.data_ptr() + half), B, C, float(lamb), float(EPS), _lib.ptr(iid), None,
+                                        _lib.ptr(dz), ctypes.c_void_p(dz.data_ptr() + half), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        dz.mul_(weight)
+        dh.mul_(1.0 - weight)
+        ctx.save_for_backward(dz, dh)
+        return (1.0 - weight) * nce + weight * iid
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dz, dh = ctx.saved_tensors
+        return grad_out * dz, grad_out * dh, None, None, None, None
+
+
+def train_losses(z, h, lamb, weight, temperature=0.85, EPS=sys.float_info.epsilon):
+    """the training loss of idelucs/models.py:128 for one stacked forward: z [2B, C] cluster probabilities, h [2B, D] latent
+    (rows 0..B-1 = 'true' view)"""
+    return _TrainLosses.apply(z, h, lamb, weight, temperature, EPS)
 
 
 def _info_nce_torch(h, temperature):
@@ -105,9 +154,9 @@ def _info_nce_torch(h, temperature):
 
 
 def info_nce_loss_stacked(h, temperature):
-    """info_nce_loss on the two views already stacked as one [2n, d] tensor (rows 0..n-1 = first view).  CUDA tensors with a
-    latent width of 32 / 64 / 128 (the reference's encoders have 64) take the fused kernels; anything else the PyTorch form."""
-    if h.is_cuda and h.dim() == 2 and h.shape[1] in (32, 64, 128) and h.shape[0] % 2 == 0 and h.shape[0] >= 2:
+    """info_nce_loss on the two views already stacked as one [2n, d] tensor (rows 0..n-1 = first view).  CUDA tensors take the
+    fused kernels around two cuBLAS GEMMs; CPU tensors the PyTorch form (host-side tests only)."""
+    if h.is_cuda and h.dim() == 2 and h.shape[0] % 2 == 0 and h.shape[0] >= 2:
         return _InfoNCE.apply(h, temperature)
     return _info_nce_torch(h, temperature)
 

@@ -59,8 +59,9 @@ PROTOTYPES = {
     "idl_scaler_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "idl_standardize_f32": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
     "idl_standardize_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
-    "idl_info_nce_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "idl_info_nce": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "idl_nce_normalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "idl_nce_softmax_xent": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "idl_nce_normalize_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "idl_rmsprop_step": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float, c_void_p]),
     "idl_rmsprop_allreduce_step": (c_int, [c_void_p, c_void_p, c_u64, c_u64, c_void_p, c_i64, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p]),
     "idl_fasta_scan": (c_int, [c_void_p, c_i64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),

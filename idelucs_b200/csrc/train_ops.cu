@@ -1,10 +1,12 @@
 // idelucs_b200 — the small latency-bound pieces of the training step that sit between the hot-path kernels and the
 // PyTorch/cuBLAS MLP (idelucs/models.py:113-143), each one launch instead of a dozen framework kernels:
 //
-//   * idl_info_nce      InfoNCE / NT-Xent of idelucs/LossFunctions.py:65-98 on the stacked latent [2B, D]: row normalisation,
-//                       the 2B x 2B similarity (never materialised: D = 64, the whole contraction is 67 MFLOP), self-masked
-//                       log-sum-exp, cross-entropy against the other view, and the closed-form gradient back to the latent —
-//                       three launches (normalise / log-sum-exp / gradient), fixed-order reductions (run-to-run identical)
+//   * idl_nce_*         InfoNCE / NT-Xent of idelucs/LossFunctions.py:65-98 on the stacked latent [2B, D], around two strict-fp32
+//                       cuBLAS GEMMs issued by the caller (similarity fn fn^T and gradient W fn — dense contractions stay
+//                       library calls): F.normalize; self-masked log-sum-exp + cross-entropy against the other view; the
+//                       weights W = (P + P^T - 2 Y) / (2B T) written over the similarity in place; the normalisation's
+//                       backward.  Four launches of ours + two GEMMs instead of ~25 framework kernels and three mask gathers;
+//                       fixed-order reductions (run-to-run identical)
 //   * iid_loss_small    the IIC loss (LossFunctions.py:20-62) for C <= 16 clusters in ONE ordinary CTA (no cooperative launch,
 //                       no grid barriers): the headline configuration has C = 5, i.e. a 5 x 5 joint
 //   * idl_rmsprop_step  torch.optim.RMSprop's update (alpha, eps, weight_decay; no momentum, not centred — what
@@ -23,8 +25,6 @@ namespace idl {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int NCE_NT = 256;          // 8 warps: warp <-> row
 constexpr int NCE_RB = NCE_NT / 32;  // rows per CTA
-constexpr int NCE_TJ = 32;           // rows of the other operand per tile (lane <-> row)
-constexpr int NCE_MAXD = 128;
 
 // F.normalize(x, dim=1): x / max(||x||_2, 1e-12)
 __global__ void __launch_bounds__(NCE_NT) nce_normalize_kernel(const float* __restrict__ h, int n2, int D, float* __restrict__ fn,
@@ -41,126 +41,68 @@ __global__ void __launch_bounds__(NCE_NT) nce_normalize_kernel(const float* __re
     if (lane == 0) inv_norm[row] = inv;
 }
 
-// lse_i = log sum_{j != i} exp(fn_i . fn_j / T) and the row's loss term lse_i - fn_i . fn_pos(i) / T.
-// |s| <= 1/T, so exp(s) needs no running maximum (T = 0.85: e^-1.18 .. e^1.18).
-template <int D>
-__global__ void __launch_bounds__(NCE_NT) nce_lse_kernel(const float* __restrict__ fn, int n2, float inv_t, float* __restrict__ lse,
+// Row pass over the similarity matrix S = fn fn^T (one strict-fp32 cuBLAS GEMM, 2B x 2B x D): lse_i = log sum_{j != i} exp(S_ij / T)
+// and the row's loss term lse_i - S_i,pos(i) / T.  Warp <-> row, coalesced reads.  |S_ij / T| <= 1 / T, so exp needs no running
+// maximum (T = 0.85: e^-1.18 .. e^1.18).
+__global__ void __launch_bounds__(NCE_NT) nce_lse_kernel(const float* __restrict__ S, int n2, float inv_t, float* __restrict__ lse,
                                                           float* __restrict__ rowloss) {
-    __shared__ float si[NCE_RB][D];
-    __shared__ float sj[NCE_TJ][D + 1];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int i = blockIdx.x * NCE_RB + w;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * NCE_RB + (threadIdx.x >> 5);
+    if (i >= n2) return;
     const int half = n2 >> 1;
-    for (int q = tid; q < NCE_RB * D; q += NCE_NT) {
-        const int r = q / D, d = q - r * D;
-        const int row = blockIdx.x * NCE_RB + r;
-        si[r][d] = row < n2 ? fn[(size_t)row * D + d] : 0.f;
-    }
-    float sum = 0.f, spos = 0.f;
     const int pos = i < half ? i + half : i - half;
-    for (int j0 = 0; j0 < n2; j0 += NCE_TJ) {
-        __syncthreads();
-        for (int q = tid; q < NCE_TJ * D; q += NCE_NT) {
-            const int r = q / D, d = q - r * D;
-            sj[r][d] = j0 + r < n2 ? fn[(size_t)(j0 + r) * D + d] : 0.f;
-        }
-        __syncthreads();
-        const int j = j0 + lane;
-        float s = 0.f;
-#pragma unroll 16
-        for (int d = 0; d < D; ++d) s = fmaf(si[w][d], sj[lane][d], s);
-        s *= inv_t;
-        if (j < n2 && j != i && i < n2) {
-            sum += __expf(s) * 1.0f;
-            if (j == pos) spos = s;
-        }
-    }
-    // fixed-order warp reduction: lanes 0..31 summed by a shuffle tree (same tree every run)
+    const float* row = S + (size_t)i * n2;
+    float sum = 0.f;
+    for (int j = lane; j < n2; j += 32)
+        if (j != i) sum += __expf(row[j] * inv_t);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); spos += __shfl_xor_sync(0xffffffffu, spos, o); }
-    if (lane == 0 && i < n2) {
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);   // fixed tree: the same sum every run
+    if (lane == 0) {
         const float l = logf(sum);
         lse[i] = l;
-        rowloss[i] = l - spos;
+        rowloss[i] = l - row[pos] * inv_t;
     }
 }
 
-// d loss / d h: dfn_i = (1 / (n2 T)) [ sum_{j != i} (P_ij + P_ji) fn_j - 2 fn_pos(i) ],  P_ij = exp(s_ij - lse_i);
-// then through the normalisation: dh_i = inv_i (dfn_i - fn_i (fn_i . dfn_i)).  Block 0 also reduces the loss.
-template <int D>
-__global__ void __launch_bounds__(NCE_NT) nce_grad_kernel(const float* __restrict__ fn, const float* __restrict__ inv_norm, const float* __restrict__ lse,
-                                                           const float* __restrict__ rowloss, int n2, float inv_t, float* __restrict__ loss,
-                                                           float* __restrict__ dh) {
-    __shared__ float si[NCE_RB][D];
-    __shared__ float sj[NCE_TJ][D + 1];
-    __shared__ float slse[NCE_TJ];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int i = blockIdx.x * NCE_RB + w;
+// In place: S_ij -> W_ij = (1 / (n2 T)) (P_ij + P_ji - 2 [j == pos(i)]),  P_ij = exp(S_ij / T - lse_i), W_ii = 0, so that
+// d loss / d fn = W fn (a second GEMM).  W is symmetric because S is.  Block 0 also reduces the loss (mean of the row terms).
+__global__ void __launch_bounds__(256) nce_weights_kernel(float* __restrict__ S, const float* __restrict__ lse, const float* __restrict__ rowloss,
+                                                           int n2, float inv_t, float* __restrict__ loss) {
+    const float c = inv_t / (float)n2;
     const int half = n2 >> 1;
-    for (int q = tid; q < NCE_RB * D; q += NCE_NT) {
-        const int r = q / D, d = q - r * D;
-        const int row = blockIdx.x * NCE_RB + r;
-        si[r][d] = row < n2 ? fn[(size_t)row * D + d] : 0.f;
-    }
-    const float lse_i = i < n2 ? lse[i] : 0.f;
-    const int pos = i < half ? i + half : i - half;
-    float acc[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) acc[d] = 0.f;
-    for (int j0 = 0; j0 < n2; j0 += NCE_TJ) {
-        __syncthreads();
-        for (int q = tid; q < NCE_TJ * D; q += NCE_NT) {
-            const int r = q / D, d = q - r * D;
-            sj[r][d] = j0 + r < n2 ? fn[(size_t)(j0 + r) * D + d] : 0.f;
+    const long long total = (long long)n2 * n2;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / n2), j = (int)(e - (long long)i * n2);
+        const float s = S[e] * inv_t;
+        float w = 0.f;
+        if (j != i) {
+            w = __expf(s - lse[i]) + __expf(s - lse[j]);
+            const int pos = i < half ? i + half : i - half;
+            if (j == pos) w -= 2.f;
         }
-        if (tid < NCE_TJ) slse[tid] = j0 + tid < n2 ? lse[j0 + tid] : 0.f;
-        __syncthreads();
-        const int j = j0 + lane;
-        float s = 0.f;
-#pragma unroll 16
-        for (int d = 0; d < D; ++d) s = fmaf(si[w][d], sj[lane][d], s);
-        s *= inv_t;
-        float wgt = 0.f;
-        if (j < n2 && j != i && i < n2) {
-            wgt = __expf(s - lse_i) + __expf(s - slse[lane]);
-            if (j == pos) wgt -= 2.f;
-        }
-#pragma unroll
-        for (int d = 0; d < D; ++d) acc[d] = fmaf(wgt, sj[lane][d], acc[d]);
+        S[e] = w * c;
     }
-    // reduce the lanes' partial vectors (fixed tree), lane d % 32 keeps dimension d
-    float mine[(D + 31) / 32];
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-        float v = acc[d];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((d & 31) == lane) mine[d >> 5] = v;
-    }
-    if (i < n2) {
-        const float scale = inv_t / (float)n2;
-        float dot = 0.f;
-#pragma unroll
-        for (int q = 0; q < (D + 31) / 32; ++q) {
-            const int d = q * 32 + lane;
-            if (d < D) { mine[q] *= scale; dot = fmaf(si[w][d], mine[q], dot); }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        const float inv = inv_norm[i];
-#pragma unroll
-        for (int q = 0; q < (D + 31) / 32; ++q) {
-            const int d = q * 32 + lane;
-            if (d < D) dh[(size_t)i * D + d] = inv * (mine[q] - si[w][d] * dot);
-        }
-    }
-    if (blockIdx.x == 0 && w == 0 && loss) {   // mean of the row terms, fixed order
+    if (blockIdx.x == 0 && threadIdx.x < 32 && loss) {
         float l = 0.f;
-        for (int r = lane; r < n2; r += 32) l += rowloss[r];
+        for (int r = threadIdx.x; r < n2; r += 32) l += rowloss[r];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-        if (lane == 0) *loss = l / (float)n2;
+        if (threadIdx.x == 0) *loss = l / (float)n2;
     }
+}
+
+// through F.normalize: dh_i = inv_i (dfn_i - fn_i (fn_i . dfn_i))
+__global__ void __launch_bounds__(NCE_NT) nce_normalize_backward_kernel(const float* __restrict__ dfn, const float* __restrict__ fn,
+                                                                         const float* __restrict__ inv_norm, int n2, int D, float* __restrict__ dh) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * NCE_RB + (threadIdx.x >> 5);
+    if (row >= n2) return;
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32) dot = fmaf(fn[(size_t)row * D + d], dfn[(size_t)row * D + d], dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float inv = inv_norm[row];
+    for (int d = lane; d < D; d += 32) dh[(size_t)row * D + d] = inv * (dfn[(size_t)row * D + d] - fn[(size_t)row * D + d] * dot);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -385,40 +327,28 @@ using namespace idl;
 
 extern "C" {
 
-size_t idl_info_nce_workspace_bytes(int n2, int D) {
-    if (n2 < 2 || D < 1 || D > NCE_MAXD) return 0;
-    return sizeof(float) * ((size_t)n2 * D + 3 * (size_t)n2) + 64;
+int idl_nce_normalize(const float* d_h, int n2, int D, float* d_fn, float* d_inv_norm, void* stream) {
+    if (!d_h || !d_fn || !d_inv_norm || n2 < 1 || D < 1) return set_error(IDL_EINVAL, "idl_nce_normalize: bad argument%s", "");
+    nce_normalize_kernel<<<(n2 + NCE_RB - 1) / NCE_RB, NCE_NT, 0, (cudaStream_t)stream>>>(d_h, n2, D, d_fn, d_inv_norm); note_launch();
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
 }
 
-int idl_info_nce(const float* d_h, int n2, int D, float temperature, float* d_loss, float* d_dh, void* d_workspace, size_t workspace_bytes,
-                 void* stream) {
-    if (!d_h || !d_workspace || n2 < 2 || (n2 & 1) || !(temperature > 0.f)) return set_error(IDL_EINVAL, "idl_info_nce: bad argument%s", "");
-    if (D != 32 && D != 64 && D != 128) return set_error(IDL_EUNSUPPORTED, "idl_info_nce: latent width must be 32, 64 or 128%s (got %lld)", "", D);
-    if (workspace_bytes < idl_info_nce_workspace_bytes(n2, D)) return set_error(IDL_EINVAL, "idl_info_nce: workspace too small%s", "");
+int idl_nce_softmax_xent(float* d_sim, int n2, float temperature, float* d_lse, float* d_rowloss, float* d_loss, void* stream) {
+    if (!d_sim || !d_lse || !d_rowloss || n2 < 2 || (n2 & 1) || !(temperature > 0.f)) return set_error(IDL_EINVAL, "idl_nce_softmax_xent: bad argument%s", "");
     cudaStream_t st = (cudaStream_t)stream;
-    float* fn = reinterpret_cast<float*>(d_workspace);
-    float* inv = fn + (size_t)n2 * D;
-    float* lse = inv + n2;
-    float* rowloss = lse + n2;
-    const int grid = (n2 + NCE_RB - 1) / NCE_RB;
     const float inv_t = 1.0f / temperature;
-    nce_normalize_kernel<<<grid, NCE_NT, 0, st>>>(d_h, n2, D, fn, inv); note_launch();
-    switch (D) {
-        case 32: nce_lse_kernel<32><<<grid, NCE_NT, 0, st>>>(fn, n2, inv_t, lse, rowloss); break;
-        case 64: nce_lse_kernel<64><<<grid, NCE_NT, 0, st>>>(fn, n2, inv_t, lse, rowloss); break;
-        default: nce_lse_kernel<128><<<grid, NCE_NT, 0, st>>>(fn, n2, inv_t, lse, rowloss); break;
-    }
-    note_launch();
-    if (d_dh) {
-        switch (D) {
-            case 32: nce_grad_kernel<32><<<grid, NCE_NT, 0, st>>>(fn, inv, lse, rowloss, n2, inv_t, d_loss, d_dh); break;
-            case 64: nce_grad_kernel<64><<<grid, NCE_NT, 0, st>>>(fn, inv, lse, rowloss, n2, inv_t, d_loss, d_dh); break;
-            default: nce_grad_kernel<128><<<grid, NCE_NT, 0, st>>>(fn, inv, lse, rowloss, n2, inv_t, d_loss, d_dh); break;
-        }
-        note_launch();
-    } else if (d_loss) {
-        return set_error(IDL_EINVAL, "idl_info_nce: the loss is reduced by the gradient kernel; pass d_dh%s", "");
-    }
+    nce_lse_kernel<<<(n2 + NCE_RB - 1) / NCE_RB, NCE_NT, 0, st>>>(d_sim, n2, inv_t, d_lse, d_rowloss); note_launch();
+    long long grid = ((long long)n2 * n2 + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    nce_weights_kernel<<<(unsigned)grid, 256, 0, st>>>(d_sim, d_lse, d_rowloss, n2, inv_t, d_loss); note_launch();
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
+}
+
+int idl_nce_normalize_backward(const float* d_dfn, const float* d_fn, const float* d_inv_norm, int n2, int D, float* d_dh, void* stream) {
+    if (!d_dfn || !d_fn || !d_inv_norm || !d_dh || n2 < 1 || D < 1) return set_error(IDL_EINVAL, "idl_nce_normalize_backward: bad argument%s", "");
+    nce_normalize_backward_kernel<<<(n2 + NCE_RB - 1) / NCE_RB, NCE_NT, 0, (cudaStream_t)stream>>>(d_dfn, d_fn, d_inv_norm, n2, D, d_dh); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }

@@ -152,7 +152,7 @@ def prepare(seqset, k, variants, seed=0, seq_id0=0, pseudocount=1, want_stats=Tr
 
 def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_off=None, out_stride=None,
              mean=None, scale=None, sidx=None, sel=None, S=None, edit_lists=None, seq_id0=0, pseudocount=None,
-             accumulate=False, status=None, prepared=None, chunked=None):
+             accumulate=False, status=None, prepared=None, chunked=None, max_long=None):
     """Run K2+K3.  Default output: tensor [S, n_items, 4^k] (variant-major) of the out_kind's
     dtype.  See include/idelucs_b200.h::idl_profiles for the argument meaning.  ``prepared`` (from ``prepare`` with the
     same SeqSet / variants / seed / seq_id0) routes float32 outputs through idl_profiles_prepared (k = 6 fast path).  Sets with
@@ -191,6 +191,8 @@ def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_o
             return out
         # long sequences (>= 65 536 bases, k = 6): tiles shared by the whole grid instead of one CTA per sequence
         n_long = int((seqset.lengths >= LONG_MIN).sum()) if (k == 6 and sidx is None and chunked is not False) else 0
+        if n_long > 0 and max_long is not None:
+            n_long = int(max_long)   # (tests: a scratch sized for fewer long items than there are makes the device fall back)
         if n_long > 0:
             nbytes = lib.idl_profiles_chunked_bytes(n_items, n_long, varr, nv, S)
             if nbytes > 0:

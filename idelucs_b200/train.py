@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 from . import featurise as ft
-from .LossFunctions import IID_loss, info_nce_loss, info_nce_loss_stacked
+from .LossFunctions import train_losses
 from .PytorchUtils import NetLinear
 from .models import weights_init
 
@@ -30,7 +30,8 @@ class ShardedTrainer(object):
     The parameters of the network are views into one flat buffer, so the optimiser and the collectives see one tensor."""
 
     def __init__(self, seqset, k=6, n_clusters=5, n_mimics=50, batch_sz=512, lamb=2.8, weight=0.25, lr=1e-3, seed=0,
-                 seq_id0=0, world=1, materialize_bytes=0, alpha=0.99, eps=1e-8, weight_decay=0.01, use_symmetric_memory=True):
+                 seq_id0=0, world=1, materialize_bytes=0, alpha=0.99, eps=1e-8, weight_decay=0.01, use_symmetric_memory=True,
+                 overlap_featurise_with="forward"):
         from .utils import PairBatchLoader
         self.dev = seqset.device
         self.world = world
@@ -76,6 +77,7 @@ class ShardedTrainer(object):
         self._shard = (n + pad) // world if self._mode == "symm" else n + pad
         self._sq = torch.zeros(self._shard, dtype=torch.float32, device=self.dev)
         self.lr, self.alpha, self.eps, self.weight_decay = lr, alpha, eps, weight_decay
+        self.overlap_featurise_with = overlap_featurise_with
         self.lamb, self.weight, self.batch_sz = lamb, weight, batch_sz
         self.gen = torch.Generator(device=self.dev).manual_seed(seed * 1000003 + seq_id0 + 1)
         self._graph = None
@@ -188,17 +190,24 @@ class ShardedTrainer(object):
         if self._batch is None:
             self._batch = self._featurise(self._ids).clone()
         main = torch.cuda.current_stream(self.dev)
-        # ---- side stream: batch t+1 (ids in self._ids) into a fresh buffer ----
-        self._side.wait_stream(main)
-        with torch.cuda.stream(self._side):
-            nxt = self._featurise(self._ids)
+        # ---- side stream: batch t+1 (ids in self._ids) into a fresh buffer.  One rank: under the forward / backward pass (small
+        # GEMMs leave most SMs idle).  Several ranks: under the optimiser step, whose kernel waits on NVLink, not on SMs ----
+        late = self.world > 1 and self.overlap_featurise_with == "optimizer"
+        nxt = None
+        if not late:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                nxt = self._featurise(self._ids)
         # ---- main stream: step t on self._batch ----
         x = self._batch
-        B = x.shape[0] // 2
         self._flat_grad.zero_()
         z, h = self.net(x)      # one pass over the stacked [2B, F] batch: same per-row math as the reference's two forwards
-        loss = (1 - self.weight) * info_nce_loss_stacked(h, 0.85) + self.weight * IID_loss(z[:B], z[B:], lamb=self.lamb)
+        loss = train_losses(z, h, self.lamb, self.weight, 0.85)   # (1 - w) InfoNCE + w IIC, one autograd node (models.py:128)
         loss.backward()
+        if late:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                nxt = self._featurise(self._ids)
         self._optimizer_step()
         main.wait_stream(self._side)
         self._batch.copy_(nxt)   # (static buffer: the graph's next replay reads it)

@@ -238,13 +238,17 @@ int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb,
                  void* stream);
 
 /* F2 — replaces info_nce_loss (idelucs/LossFunctions.py:65-98; weight 1 - w = 0.75 of the training loss, models.py:128) on the
- * two views stacked as one [n2 = 2B, D] float32 matrix (rows 0..B-1 = first view): F.normalize, the n2 x n2 similarity / temperature
- * (never materialised), the self-masked log-softmax and the cross-entropy against the other view — value into d_loss, gradient
- * with respect to d_h into d_dh [n2, D] (required: the gradient kernel also reduces the loss).  D in {32, 64, 128}; n2 even.
- * d_workspace: idl_info_nce_workspace_bytes(n2, D).  Three launches, fixed-order reductions. */
-size_t idl_info_nce_workspace_bytes(int n2, int D);
-int idl_info_nce(const float* d_h, int n2, int D, float temperature, float* d_loss, float* d_dh, void* d_workspace, size_t workspace_bytes,
-                 void* stream);
+ * two views stacked as one [n2 = 2B, D] float32 matrix (rows 0..B-1 = first view).  The two dense contractions stay library GEMMs
+ * issued by the caller (strict fp32): S = fn fn^T and d loss / d fn = W fn.  Around them:
+ *   idl_nce_normalize           fn = F.normalize(h) (x / max(||x||, 1e-12)), d_inv_norm[n2] = the factors
+ *   idl_nce_softmax_xent        d_sim [n2, n2] holds S on entry; the loss (self-masked log-softmax of S / temperature, cross-entropy
+ *                               against the other view, mean over rows) goes to d_loss, and S is overwritten IN PLACE by
+ *                               W = (P + P^T - 2 Y) / (n2 T) (zero diagonal); d_lse, d_rowloss: n2 floats of scratch each
+ *   idl_nce_normalize_backward  dh = inv_norm (dfn - fn (fn . dfn)) per row
+ * Fixed-order reductions: results are run-to-run identical. */
+int idl_nce_normalize(const float* d_h, int n2, int D, float* d_fn, float* d_inv_norm, void* stream);
+int idl_nce_softmax_xent(float* d_sim, int n2, float temperature, float* d_lse, float* d_rowloss, float* d_loss, void* stream);
+int idl_nce_normalize_backward(const float* d_dfn, const float* d_fn, const float* d_inv_norm, int n2, int D, float* d_dh, void* stream);
 
 /* Optimiser step of the data-parallel consumer (idelucs/models.py:86 torch.optim.RMSprop(lr, weight_decay=0.01); momentum 0,
  * not centred) on a flat float32 shard, one elementwise pass: g = grad * grad_scale + weight_decay * p;

@@ -184,6 +184,13 @@ def test_chunked_path_many_genomes_equals_generic_and_oracle(ft, SeqSet):
     for i in idx:   # (_oracle_counts numbers its sequences from seq_id0: one call per item with the true id)
         w = _oracle_counts([seqs[i]], 6, 5, variants, seq_id0=100 + i)[:, 0]
         assert np.array_equal(a[:, i].cpu().numpy(), w), i
+    # a scratch sized for fewer long items than the set holds: the plan kernel notices and the generic kernel computes them
+    c = ft.profiles(ss, 6, variants, out_kind=ft.OUT_COUNTS_I32, seed=5, seq_id0=100, max_long=3)
+    assert torch.equal(c, b)
+    # selection of slots per item (sel) through the chunked path
+    sel = torch.stack([torch.zeros(ss.n, dtype=torch.int32), torch.arange(ss.n, dtype=torch.int32) % 5 + 1], dim=1).cuda().contiguous()
+    d = ft.profiles(ss, 6, variants, out_kind=ft.OUT_COUNTS_I32, seed=5, seq_id0=100, sel=sel)
+    assert torch.equal(d[0], b[0]) and torch.equal(d[1], b[(torch.arange(ss.n) % 5 + 1).cuda(), torch.arange(ss.n).cuda()])
     x, sc, _ = U.augment_device(ss, 3, k=6, seed=9)
     f = ft.profiles(ss, 6, ft.mimic_schedule(3), out_kind=ft.OUT_FREQ_F32, seed=9, chunked=False)
     scg = ft.Scaler.fit(f[0])
