@@ -124,15 +124,16 @@ def can_prepare(seqset, k, variants, n_items=None):
             and not any(v.kind == KIND_EXPLICIT for v in variants))
 
 
-def prepare(seqset, k, variants, seed=0, seq_id0=0, pseudocount=1, want_stats=True):
-    """idl_profiles_prepare over the whole SeqSet: ONE pass that generates the Bernoulli mimics' histogram deltas for the
-    profile pass (``profiles(..., prepared=...)``) and the scaler statistics of variants[0]."""
+def prepare(seqset, k, variants, seed=0, seq_id0=0, pseudocount=1, want_stats=True, sidx=None, buf=None):
+    """idl_profiles_prepare over the SeqSet (or the items ``sidx``): ONE pass that generates the Bernoulli mimics' histogram
+    deltas for the profile pass (``profiles(..., prepared=...)``) and the scaler statistics of variants[0]."""
     lib = _lib.load()
     device = seqset.device
     F = 4 ** k
-    n = seqset.n
+    n = seqset.n if sidx is None else int(sidx.numel())
     nbytes = lib.idl_prepare_bytes(n)
-    buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
     max_parts = 2048
     parts = torch.empty((max_parts, 2, F), dtype=torch.float64, device=device) if want_stats else None
     part_n = torch.zeros((max_parts,), dtype=torch.float64, device=device) if want_stats else None
@@ -142,12 +143,15 @@ def prepare(seqset, k, variants, seed=0, seq_id0=0, pseudocount=1, want_stats=Tr
     with torch.cuda.device(device):
         ws = _workspace(device, lib.idl_profiles_workspace_bytes(), "prof")
         _lib.check(lib.idl_profiles_prepare(_lib.ptr(seqset.codes), _lib.ptr(seqset.nmask), _lib.ptr(seqset.chunk_off), _lib.ptr(seqset.len),
-                                            seqset.n, None, n, int(seq_id0), k, varr, len(variants), ctypes.c_uint64(seed & (2 ** 64 - 1)),
-                                            int(pseudocount), _lib.ptr(buf), nbytes, _lib.ptr(parts), _lib.ptr(part_n), max_parts,
+                                            seqset.n, _lib.ptr(sidx), n, int(seq_id0), k, varr, len(variants), ctypes.c_uint64(seed & (2 ** 64 - 1)),
+                                            int(pseudocount), _lib.ptr(buf), buf.numel(), _lib.ptr(parts), _lib.ptr(part_n), max_parts,
                                             ctypes.byref(n_parts), _lib.ptr(status), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     if want_stats:
         parts, part_n = parts[: n_parts.value], part_n[: n_parts.value]
-    return Prepared(buf, parts, part_n, (id(seqset), k, seed, seq_id0, pseudocount, len(variants)))
+    return Prepared(buf, parts, part_n, (id(seqset), k, seed, seq_id0, pseudocount, len(variants)) if sidx is None else None)
+
+
+STATS_SLAB = 131072   # sequences per prepare call when only the statistics are wanted (2.4 GB of scratch, reused)
 
 
 def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_off=None, out_stride=None,
@@ -251,7 +255,19 @@ def profile_stats(seqset, k, variant, seed=0, seq_id0=0, edit_lists=None, group=
     inside the featurisation kernels (no [N, 4^k] matrix is written or re-read).  Equivalent to
     ``Scaler.fit(profiles(seqset, k, [variant], OUT_FREQ_F32)[0], group)``."""
     if fast and edit_lists is None and can_prepare(seqset, k, [variant]):
-        return prepare(seqset, k, [variant], seed=seed, seq_id0=seq_id0, pseudocount=pseudocount).scaler(group)
+        if seqset.n <= STATS_SLAB:
+            return prepare(seqset, k, [variant], seed=seed, seq_id0=seq_id0, pseudocount=pseudocount).scaler(group)
+        # big sets (configs[3]: 10^6 sequences): slab by slab through one reused scratch buffer; the parts are merged in slab order
+        parts, part_n, buf = [], [], None
+        for lo in range(0, seqset.n, STATS_SLAB):
+            idx = torch.arange(lo, min(lo + STATS_SLAB, seqset.n), dtype=torch.int32, device=seqset.device)
+            pr = prepare(seqset, k, [variant], seed=seed, seq_id0=seq_id0, pseudocount=pseudocount, sidx=idx, buf=buf)
+            buf = pr.buf
+            parts.append(pr.parts.clone()); part_n.append(pr.part_n.clone())
+        parts, part_n = torch.cat(parts), torch.cat(part_n)
+        if group is not None:
+            parts, part_n = gather_partials(parts, part_n, group)
+        return Scaler.from_partials(parts, part_n)
     lib = _lib.load()
     device = seqset.device
     F = 4 ** k

@@ -415,6 +415,12 @@ def test_prepared_stats_equal_generic_and_matrix_fit(ft, SeqSet):
             assert float(((other.mean32 - b.mean32).abs() / other.mean32.abs()).max()) < 2e-7
         c = ft.profile_stats(ss, 6, spec, seed=17, seq_id0=3)
         assert torch.equal(b.mean64, c.mean64) and torch.equal(b.scale64, c.scale64)      # run-to-run identical
+        slab, ft.STATS_SLAB = ft.STATS_SLAB, 600                                          # slab-wise statistics of big sets (items through sidx)
+        try:
+            d = ft.profile_stats(ss, 6, spec, seed=17, seq_id0=3)
+        finally:
+            ft.STATS_SLAB = slab
+        assert torch.allclose(d.mean64, b.mean64, rtol=1e-13, atol=0) and torch.allclose(d.scale64, b.scale64, rtol=1e-9, atol=0)
         # float64 sums of the float32 frequencies on a small set
         s = ft.profile_stats(few, 6, spec, seed=17)
         xf = ft.profiles(few, 6, [spec], out_kind=ft.OUT_FREQ_F32, seed=17)[0].double().cpu().numpy()
