@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libidelucs_b200.so")
+# (IDELUCS_B200_LIB: a differently built library, e.g. the -DIDL_DEVTOOLS variant the profiling tools use)
+LIB_PATH = os.environ.get("IDELUCS_B200_LIB") or os.path.join(_HERE, "lib", "libidelucs_b200.so")
 
 IDL_OK = 0
 KIND_CLEAN, KIND_TRANSITION, KIND_TRANSVERSION, KIND_BOTH, KIND_RANDOM_N, KIND_EXPLICIT = range(6)
