@@ -1044,26 +1044,27 @@ __global__ void scaler_finalize_kernel(const double* __restrict__ partials, cons
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= F) return;
     double na = 0.0, ma = 0.0, M2 = 0.0;
-    for (int g0 = 0; g0 < n_parts; g0 += 8) {  // Chan et al. pairwise merge, fixed order; the loads of 8 parts are issued together
-        double nbv[8], mbv[8], Mbv[8];
+    constexpr int U = 16;
+    for (int g0 = 0; g0 < n_parts; g0 += U) {  // Chan et al. pairwise merge, fixed order; the loads of U parts are issued together
+        double nbv[U], mbv[U], Mbv[U];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int g = g0 + u < n_parts ? g0 + u : n_parts - 1;
             nbv[u] = g0 + u < n_parts ? part_n[g] : 0.0;
             mbv[u] = partials[((long long)g * 2 + 0) * F + col];
             Mbv[u] = partials[((long long)g * 2 + 1) * F + col];
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-        const double nb = nbv[u];
-        if (nb <= 0.0) continue;
-        const double mb = mbv[u];
-        const double Mb = Mbv[u];
-        const double nt = na + nb;
-        const double delta = mb - ma;
-        ma = ma + delta * (nb / nt);
-        M2 = M2 + Mb + delta * delta * (na * nb / nt);
-        na = nt;
+        for (int u = 0; u < U; ++u) {
+            const double nb = nbv[u];
+            if (nb <= 0.0) continue;
+            const double mb = mbv[u];
+            const double Mb = Mbv[u];
+            const double nt = na + nb;
+            const double delta = mb - ma;
+            ma = ma + delta * (nb / nt);
+            M2 = M2 + Mb + delta * delta * (na * nb / nt);
+            na = nt;
         }
     }
     double var = na > 0.0 ? M2 / na : 0.0;
