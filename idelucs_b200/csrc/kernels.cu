@@ -1599,7 +1599,10 @@ int idl_profiles_prepare(const uint32_t* d_codes, const uint32_t* d_nmask, const
     if (grid > n_items) grid = n_items;
     prep_kernel<PC_K><<<(unsigned)grid, PR_NT, sizeof(PrSmem), st>>>(p, hp.plan); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
-    if (!d_partials) return IDL_OK;
+    if (!d_partials) {   // no statistics wanted: nobody consumes the "left to the generic kernel" marks of this call (the prepared records keep them)
+        IDL_CUDA_CHECK(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t)n_items, st));
+        return IDL_OK;
+    }
     // ---- statistics of slot 0: column sums over the prepared rows + the generic kernel for the items the prepare pass left out ----
     int parts = sm_count() * 2;
     if (parts > n_items) parts = (int)n_items;
