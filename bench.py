@@ -143,8 +143,32 @@ def train_breakdown(tr, torch):
         z0.grad = None; h0.grad = None
         train_losses(z0, h0, tr.lamb, tr.weight, 0.85).backward()
 
+    def torch_ops():
+        # the same two losses as plain PyTorch ops (the reference's formulation, idelucs/LossFunctions.py:20-98, with the boolean-mask
+        # assignments / gathers replaced by their graph-capturable equivalents clamp and a -inf diagonal), for comparison
+        import sys as _sys
+        z0.grad = None; h0.grad = None
+        x1, x2 = z0[:B], z0[B:]
+        pij = (x1.unsqueeze(2) * x2.unsqueeze(1)).sum(dim=0)
+        pij = (pij + pij.t()) / 2.
+        pij = pij / pij.sum()
+        k = pij.shape[0]
+        eps = _sys.float_info.epsilon
+        pi = pij.sum(dim=1).view(k, 1).expand(k, k).clamp(min=eps)
+        pj = pij.sum(dim=0).view(1, k).expand(k, k).clamp(min=eps)
+        pc = pij.clamp(min=eps)
+        iid_t = (-pc * (torch.log(pc) - tr.lamb * torch.log(pj) - tr.lamb * torch.log(pi))).sum()
+        f = torch.nn.functional.normalize(h0, dim=1)
+        logits = (f @ f.t()) / 0.85
+        logits.fill_diagonal_(float("-inf"))
+        n2 = logits.shape[0]
+        tgt = (torch.arange(n2, device=logits.device) + n2 // 2) % n2
+        nce_t = torch.nn.functional.cross_entropy(logits, tgt)
+        ((1 - tr.weight) * nce_t + tr.weight * iid_t).backward()
+
     out = {"featurise_pair_batch_us": timed(lambda: tr._featurise(tr._ids)), "mlp_forward_backward_us": timed(mlp),
-           "losses_forward_backward_us": timed(both), "iid_loss_alone_us": timed(iid), "info_nce_alone_us": timed(nce)}
+           "losses_forward_backward_us": timed(both), "iid_loss_alone_us": timed(iid), "info_nce_alone_us": timed(nce),
+           "losses_as_pytorch_ops_us": timed(torch_ops)}
     if tr.world == 1:
         out["optimizer_step_us"] = timed(tr._optimizer_step)
     out["note"] = ("each part replayed from its own CUDA graph; in the step the featurisation of the next batch runs on a side stream "
