@@ -111,9 +111,10 @@ __global__ void __launch_bounds__(NCE_NT) nce_normalize_backward_kernel(const fl
 constexpr int IS_NT = 512;
 constexpr int IS_MAXC = 16;
 
-__global__ void __launch_bounds__(IS_NT) iid_loss_small_kernel(const float* __restrict__ z1, const float* __restrict__ z2, int B, int C, float lamb,
+__global__ void __launch_bounds__(IS_NT) iid_loss_small_kernel(const float* __restrict__ gz1, const float* __restrict__ gz2, int B, int C, float lamb,
                                                                 float eps, float* __restrict__ loss, float* __restrict__ joint,
-                                                                float* __restrict__ dz1, float* __restrict__ dz2) {
+                                                                float* __restrict__ dz1, float* __restrict__ dz2, int staged) {
+    extern __shared__ __align__(16) float zs[];             // staged: z1 | z2 (2 B C floats) — every later access hits shared memory
     __shared__ float part[IS_NT / 32][IS_MAXC * IS_MAXC];   // per-warp partial S
     __shared__ float S[IS_MAXC][IS_MAXC + 1];               // S, then Ssym
     __shared__ float dS[IS_MAXC][IS_MAXC + 1];
@@ -121,16 +122,25 @@ __global__ void __launch_bounds__(IS_NT) iid_loss_small_kernel(const float* __re
     __shared__ float red[4];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int np = C * C;
+    const float* z1 = gz1;
+    const float* z2 = gz2;
+    if (staged) {   // coalesced, fully pipelined loads instead of a latency chain of dependent row reads
+        const int n = B * C;
+        for (int i = tid; i < n; i += IS_NT) { zs[i] = __ldg(gz1 + i); zs[n + i] = __ldg(gz2 + i); }
+        __syncthreads();
+        z1 = zs; z2 = zs + n;
+    }
     // ---- S_ij = sum_b z1[b,i] z2[b,j] (LossFunctions.py:54-58): warp <-> rows b = w, w+16, ...; lane <-> pairs ----
     {
         float a[IS_MAXC * IS_MAXC / 32];
 #pragma unroll
         for (int q = 0; q < IS_MAXC * IS_MAXC / 32; ++q) a[q] = 0.f;
+#pragma unroll 4
         for (int b = w; b < B; b += IS_NT / 32) {
 #pragma unroll
             for (int q = 0; q < IS_MAXC * IS_MAXC / 32; ++q) {
                 const int pr = lane + 32 * q;
-                if (pr < np) { const int i = pr / C, j = pr - i * C; a[q] = fmaf(__ldg(z1 + (size_t)b * C + i), __ldg(z2 + (size_t)b * C + j), a[q]); }
+                if (pr < np) { const int i = pr / C, j = pr - i * C; a[q] = fmaf(z1[(size_t)b * C + i], z2[(size_t)b * C + j], a[q]); }
             }
         }
 #pragma unroll
@@ -211,8 +221,8 @@ __global__ void __launch_bounds__(IS_NT) iid_loss_small_kernel(const float* __re
         float a1 = 0.f, a2 = 0.f;
         for (int j = 0; j < C; ++j) {
             const float d = dS[c][j];
-            a1 = fmaf(__ldg(z2 + (size_t)b * C + j), d, a1);
-            a2 = fmaf(__ldg(z1 + (size_t)b * C + j), d, a2);
+            a1 = fmaf(z2[(size_t)b * C + j], d, a1);
+            a2 = fmaf(z1[(size_t)b * C + j], d, a2);
         }
         if (dz1) dz1[q] = a1;
         if (dz2) dz2[q] = a2;
@@ -316,7 +326,20 @@ __global__ void __launch_bounds__(256) rmsprop_allreduce_kernel(const PeerPtrs g
 // C <= 16: called by idl_iid_loss (iid_loss.cu)
 int iid_loss_small_launch(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float* d_loss, float* d_joint, float* d_dz1,
                           float* d_dz2, void* stream) {
-    iid_loss_small_kernel<<<1, IS_NT, 0, (cudaStream_t)stream>>>(d_z1, d_z2, B, C, lamb, eps, d_loss, d_joint, d_dz1, d_dz2); note_launch();
+    // both inputs staged in shared memory when they fit (B = 512, C = 5: 20 KB; up to 160 KB)
+    size_t smem = sizeof(float) * 2 * (size_t)B * C;
+    int staged = 1;
+    if (smem > 160 * 1024) { smem = 0; staged = 0; }
+    if (smem > 24 * 1024) {   // (18.5 KB of static shared memory ride along: opt in before the sum passes 48 KB)
+        static bool configured[64] = {false};
+        int dev = 0;
+        IDL_CUDA_CHECK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
+            IDL_CUDA_CHECK(cudaFuncSetAttribute(iid_loss_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            if (dev >= 0 && dev < 64) configured[dev] = true;
+        }
+    }
+    iid_loss_small_kernel<<<1, IS_NT, smem, (cudaStream_t)stream>>>(d_z1, d_z2, B, C, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, staged); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }
