@@ -1039,34 +1039,82 @@ __global__ void __launch_bounds__(CS_NT) colstats_kernel(const T* __restrict__ x
     partials[((long long)blockIdx.y * 2 + 1) * F + col] = s2 - s1 * s1 / m;  // M2 of the part
 }
 
-__global__ void scaler_finalize_kernel(const double* __restrict__ partials, const double* __restrict__ part_n, int n_parts,
-                                       int F, double* mean64, double* var64, double* scale64, float* mean32, float* scale32) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= F) return;
-    double na = 0.0, ma = 0.0, M2 = 0.0;
-    constexpr int U = 16;
-    for (int g0 = 0; g0 < n_parts; g0 += U) {  // Chan et al. pairwise merge, fixed order; the loads of U parts are issued together
-        double nbv[U], mbv[U], Mbv[U];
+// Merge of the (rows, mean, M2) parts in index order (Chan et al.), one lane per column.  The chain over the parts is
+// sequential per column and only 4^k columns exist, so a thread-per-column loop is bound by the latency of its own loads
+// (0.10 ms for 592 parts at k = 6).  Here a CTA owns SF_COLS columns: all its threads fetch the next SF_PCH parts' rows (empty
+// parts are skipped) while warp 0 runs the recurrence on the current ones out of shared memory; the weights nb / (na + nb) and
+// na * nb / (na + nb) depend on the row counts alone and are computed once per part.  Same operations in the same order per
+// column as the plain loop (bit-identical results).
+constexpr int SF_COLS = 32, SF_NT = 256, SF_PCH = 64;
+constexpr int SF_LD = SF_PCH * SF_COLS * 2 / 2 / SF_NT;   // double2 loads per thread and chunk
+__global__ void __launch_bounds__(SF_NT) scaler_finalize_kernel(const double* __restrict__ partials, const double* __restrict__ part_n, int n_parts,
+                                                                int F, double* mean64, double* var64, double* scale64, float* mean32, float* scale32) {
+    __shared__ __align__(16) double s_row[SF_PCH][2][SF_COLS];   // [part][mean | M2][column]
+    __shared__ double s_nb[SF_PCH], s_w1[SF_PCH], s_w2[SF_PCH];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int col0 = blockIdx.x * SF_COLS;
+    const bool vec_ok = (F % 2 == 0) && (col0 + SF_COLS <= F);
+    double2 pre[SF_LD];
+    auto fetch = [&](int g0) {   // rows of parts g0 .. g0 + SF_PCH - 1 -> registers (empty parts and the range past the end: not loaded)
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int g = g0 + u < n_parts ? g0 + u : n_parts - 1;
-            nbv[u] = g0 + u < n_parts ? part_n[g] : 0.0;
-            mbv[u] = partials[((long long)g * 2 + 0) * F + col];
-            Mbv[u] = partials[((long long)g * 2 + 1) * F + col];
+        for (int r = 0; r < SF_LD; ++r) {
+            const int unit = r * SF_NT + tid;
+            const int part = unit / SF_COLS, w = unit % SF_COLS;   // SF_COLS double2 units per part: SF_COLS / 2 of the mean row, SF_COLS / 2 of the M2 row
+            const int which = w / (SF_COLS / 2), c = (w % (SF_COLS / 2)) * 2;
+            const int g = g0 + part;
+            pre[r] = make_double2(0.0, 0.0);
+            if (g < n_parts && part_n[g] > 0.0) {
+                const double* src = partials + ((long long)g * 2 + which) * F + col0 + c;
+                if (vec_ok) pre[r] = *reinterpret_cast<const double2*>(src);
+                else { if (col0 + c < F) pre[r].x = src[0]; if (col0 + c + 1 < F) pre[r].y = src[1]; }
+            }
         }
+    };
+    double ma = 0.0, M2 = 0.0, na_carry = 0.0;
+    fetch(0);
+    for (int g0 = 0; g0 < n_parts; g0 += SF_PCH) {
+        const int m = n_parts - g0 < SF_PCH ? n_parts - g0 : SF_PCH;
+        __syncthreads();   // the previous chunk's chain is done
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const double nb = nbv[u];
-            if (nb <= 0.0) continue;
-            const double mb = mbv[u];
-            const double Mb = Mbv[u];
-            const double nt = na + nb;
-            const double delta = mb - ma;
-            ma = ma + delta * (nb / nt);
-            M2 = M2 + Mb + delta * delta * (na * nb / nt);
-            na = nt;
+        for (int r = 0; r < SF_LD; ++r) {
+            const int unit = r * SF_NT + tid;
+            const int part = unit / SF_COLS, w = unit % SF_COLS;
+            *reinterpret_cast<double2*>(&s_row[part][w / (SF_COLS / 2)][(w % (SF_COLS / 2)) * 2]) = pre[r];
+        }
+        if (tid < 32) {   // rows merged before each part: a scan of row counts (integers: exact in any order), then the weights
+            const int i0 = 2 * lane, i1 = 2 * lane + 1;
+            double v0 = i0 < m ? part_n[g0 + i0] : 0.0, v1 = i1 < m ? part_n[g0 + i1] : 0.0;
+            v0 = v0 > 0.0 ? v0 : 0.0; v1 = v1 > 0.0 ? v1 : 0.0;
+            const double sum2 = v0 + v1;
+            double inc = sum2;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const double na0 = na_carry + (inc - sum2), na1 = na0 + v0;
+            s_nb[i0] = v0; s_nb[i1] = v1;
+            { const double nt = na0 + v0; s_w1[i0] = v0 / nt; s_w2[i0] = na0 * v0 / nt; }
+            { const double nt = na1 + v1; s_w1[i1] = v1 / nt; s_w2[i1] = na1 * v1 / nt; }
+            na_carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        __syncthreads();
+        if (g0 + SF_PCH < n_parts) fetch(g0 + SF_PCH);   // in flight during the chain below
+        if (tid < 32) {
+            for (int i = 0; i < m; ++i) {
+                if (!(s_nb[i] > 0.0)) continue;
+                const double mb = s_row[i][0][lane];
+                const double Mb = s_row[i][1][lane];
+                const double w1 = s_w1[i], w2 = s_w2[i];
+                const double delta = mb - ma;
+                ma = ma + delta * w1;
+                M2 = M2 + Mb + delta * delta * w2;
+            }
         }
     }
+    const int col = col0 + lane;
+    if (tid >= 32 || col >= F) return;
+    const double na = na_carry;
     double var = na > 0.0 ? M2 / na : 0.0;
     if (var < 0.0) var = 0.0;
     // sklearn/preprocessing/_data.py::_is_constant_feature (float64 eps) -> scale 1
@@ -1608,8 +1656,13 @@ int idl_profiles_prepare(const uint32_t* d_codes, const uint32_t* d_nmask, const
     if (parts > n_items) parts = (int)n_items;
     const int rows_per_part = (int)((n_items + parts - 1) / parts);
     parts = (int)((n_items + rows_per_part - 1) / rows_per_part);
-    colstats16_kernel<<<dim3(PC_F / 4 / CS16_NT, (unsigned)parts), CS16_NT, 0, st>>>(reinterpret_cast<const unsigned char*>(d_prep), n_items, rows_per_part,
-                                                                                   pseudocount, d_partials, d_part_n); note_launch();
+    if (pseudocount > 0)   // every frequency is a positive normal float
+        colstats16_kernel<true><<<dim3(PC_F / 4 / CS16_NT, (unsigned)parts), CS16_NT, 0, st>>>(reinterpret_cast<const unsigned char*>(d_prep), n_items, rows_per_part,
+                                                                                             pseudocount, d_partials, d_part_n);
+    else
+        colstats16_kernel<false><<<dim3(PC_F / 4 / CS16_NT, (unsigned)parts), CS16_NT, 0, st>>>(reinterpret_cast<const unsigned char*>(d_prep), n_items, rows_per_part,
+                                                                                              pseudocount, d_partials, d_part_n);
+    note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     p.only_deferred = 1;
     p.S = 1; p.n_vars = 1;
@@ -1663,7 +1716,7 @@ int idl_colstats(const void* d_x, int is_f64, int64_t n, int F, double* d_partia
 int idl_scaler_finalize(const double* d_partials, const double* d_part_n, int n_parts, int F, double* d_mean64,
                         double* d_var64, double* d_scale64, float* d_mean32, float* d_scale32, void* stream) {
     if (!d_partials || !d_part_n || n_parts <= 0 || F <= 0) return set_error(IDL_EINVAL, "idl_scaler_finalize: bad argument%s", "");
-    scaler_finalize_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_partials, d_part_n, n_parts, F, d_mean64, d_var64,
+    scaler_finalize_kernel<<<(F + SF_COLS - 1) / SF_COLS, SF_NT, 0, (cudaStream_t)stream>>>(d_partials, d_part_n, n_parts, F, d_mean64, d_var64,
                                                                               d_scale64, d_mean32, d_scale32); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;

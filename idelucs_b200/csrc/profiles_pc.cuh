@@ -38,7 +38,10 @@ constexpr int PC_NBLD = 256;       // builder threads (warps 0..7)
 constexpr int PC_NFIX = 224;       // fix threads (warps 8..14); warp 15 lane 0 is the store thread
 constexpr int PC_NBUF = 4;         // 16 KB row buffers
 constexpr int PC_NOTH = 1;         // row buffers that take the "other" jobs (dense rows, minority window totals) while the rest stream the main total
-constexpr int PC_INFL = PC_NBUF - 2;   // bulk copies kept in flight (of the other two buffers one is being fixed, one is ready)
+#ifndef PC_INFL_N
+#define PC_INFL_N (PC_NBUF - 2)
+#endif
+constexpr int PC_INFL = PC_INFL_N;   // bulk copies kept in flight besides the one just issued
 constexpr int PC_FIXW = PC_NFIX / 32;   // fix warps: each owns a 4 KB scratch (biased uint8 deltas) and handles whole jobs
 constexpr int PC_SCRW = 1024;      // words of one fix-warp scratch (four bins per word)
 constexpr uint32_t PC_BIAS4 = 0x80808080u;

@@ -20,12 +20,16 @@ def main():
     V = len(variants)
     out = torch.empty((V, n, F), dtype=torch.float32, device="cuda")
     off = [v * n * F for v in range(V)]
+    stride = F
+    if os.environ.get("ITEM_MAJOR"):   # [N, V, F] instead of [V, N, F]
+        off = [v * F for v in range(V)]
+        stride = V * F
     mean = torch.rand(F, device="cuda") * 1e-3
     scale = torch.rand(F, device="cuda") * 1e-4 + 1e-5
     for name, kind, vs in (("48 random_n std", ft.OUT_STD_F32, variants[3:]), ("all %d std" % V, ft.OUT_STD_F32, variants)):
         nv = len(vs)
         prep = ft.prepare(ss, k, vs, seed=1) if ft.can_prepare(ss, k, vs) else None   # the k = 6 fast path reads the prepared deltas
-        fn = lambda: ft.profiles(ss, k, vs, out_kind=kind, seed=1, out=out, out_off=off[:nv], out_stride=F, mean=mean, scale=scale, prepared=prep)
+        fn = lambda: ft.profiles(ss, k, vs, out_kind=kind, seed=1, out=out, out_off=off[:nv], out_stride=stride, mean=mean, scale=scale, prepared=prep)
         fn(); torch.cuda.synchronize()
         ts = []
         for _ in range(3):
