@@ -67,9 +67,10 @@ def compute_joint(x_out, x_tf_out):
 _targets = {}
 
 
-def _info_nce_device(x, temperature):
-    """(loss 0-d tensor, dh [n2, D]) of the stacked latent x (float32, contiguous, CUDA): idl_nce_normalize -> S = fn fn^T (cuBLAS,
-    strict fp32) -> idl_nce_softmax_xent (loss; S becomes W in place) -> dfn = W fn (cuBLAS) -> idl_nce_normalize_backward"""
+def _info_nce_device(x, temperature, grad_scale=1.0):
+    """(loss 0-d tensor, grad_scale * dh [n2, D]) of the stacked latent x (float32, contiguous, CUDA): idl_nce_normalize -> S = fn fn^T
+    (cuBLAS, strict fp32) -> idl_nce_softmax_xent_scaled (loss; S becomes grad_scale * W in place) -> dfn = W fn (cuBLAS) ->
+    idl_nce_normalize_backward"""
     lib = _lib.load()
     n2, D = x.shape
     dev = x.device
@@ -81,11 +82,34 @@ def _info_nce_device(x, temperature):
         st = _lib.stream_ptr()
         _lib.check(lib.idl_nce_normalize(_lib.ptr(x), n2, D, _lib.ptr(fn), _lib.ptr(scratch), st))
         sim = torch.mm(fn, fn.t())
-        _lib.check(lib.idl_nce_softmax_xent(_lib.ptr(sim), n2, float(temperature), ctypes.c_void_p(scratch.data_ptr() + 4 * n2),
-                                            ctypes.c_void_p(scratch.data_ptr() + 8 * n2), _lib.ptr(loss), st))
+        _lib.check(lib.idl_nce_softmax_xent_scaled(_lib.ptr(sim), n2, float(temperature), float(grad_scale),
+                                                   ctypes.c_void_p(scratch.data_ptr() + 4 * n2), ctypes.c_void_p(scratch.data_ptr() + 8 * n2),
+                                                   _lib.ptr(loss), st))
         dfn = torch.mm(sim, fn)
         _lib.check(lib.idl_nce_normalize_backward(_lib.ptr(dfn), _lib.ptr(fn), _lib.ptr(scratch), n2, D, _lib.ptr(dh), st))
     return loss, dh
+
+
+def train_losses_and_grads(z, h, lamb, weight, temperature=0.85, EPS=sys.float_info.epsilon):
+    """(1 - w) info_nce_loss + w IID_loss of one stacked forward (idelucs/models.py:128) WITH its gradients, no autograd node:
+    returns (loss, dLoss/dz, dLoss/dh).  The weights ride inside the kernels (idl_nce_softmax_xent_scaled, idl_iid_loss_scaled, the
+    latter also combines the two loss values), so between the MLP's forward and its backward there are our four kernels, the IIC
+    kernel and two GEMMs — no framework kernel.  A trainer seeds the backward pass with
+    ``torch.autograd.backward((z, h), (dz, dh))``."""
+    lib = _lib.load()
+    zz = z.detach().contiguous().float()
+    n2, C = zz.shape
+    B = n2 // 2
+    nce, dh = _info_nce_device(h.detach().contiguous().float(), temperature, grad_scale=1.0 - weight)
+    loss = torch.empty((), dtype=torch.float32, device=zz.device)
+    dz = torch.empty_like(zz)
+    with torch.cuda.device(zz.device):
+        ws = _ws(zz.device, C)
+        half = 4 * B * C   # bytes: rows B.. of z are the second view
+        _lib.check(lib.idl_iid_loss_scaled(_lib.ptr(zz), ctypes.c_void_p(zz.data_ptr() + half), B, C, float(lamb), float(EPS), float(weight),
+                                           float(weight), _lib.ptr(nce), float(1.0 - weight), _lib.ptr(loss), None, _lib.ptr(dz),
+                                           ctypes.c_void_p(dz.data_ptr() + half), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return loss, dz, dh
 
 
 class _InfoNCE(torch.autograd.Function):
@@ -110,22 +134,9 @@ class _TrainLosses(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, h, lamb, weight, temperature, EPS):
-        lib = _lib.load()
-        zz = z.detach().contiguous().float()
-        n2, C = zz.shape
-        B = n2 // 2
-        nce, dh = _info_nce_device(h.detach().contiguous().float(), temperature)
-        iid = torch.empty((), dtype=torch.float32, device=zz.device)
-        dz = torch.empty_like(zz)
-        with torch.cuda.device(zz.device):
-            ws = _ws(zz.device, C)
-            half = 4 * B * C   # bytes: rows B.. of z are the second view
-            _lib.check(lib.idl_iid_loss(_lib.ptr(zz), ctypes.c_void_p(zz.data_ptr() + half), B, C, float(lamb), float(EPS), _lib.ptr(iid), None,
-                                        _lib.ptr(dz), ctypes.c_void_p(dz.data_ptr() + half), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
-        dz.mul_(weight)
-        dh.mul_(1.0 - weight)
+        loss, dz, dh = train_losses_and_grads(z, h, lamb, weight, temperature, EPS)
         ctx.save_for_backward(dz, dh)
-        return (1.0 - weight) * nce + weight * iid
+        return loss
 
     @staticmethod
     def backward(ctx, grad_out):

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "idl_standardize_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
     "idl_nce_normalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "idl_nce_softmax_xent": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "idl_nce_softmax_xent_scaled": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "idl_nce_normalize_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "idl_rmsprop_step": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float, c_void_p]),
     "idl_rmsprop_allreduce_step": (c_int, [c_void_p, c_void_p, c_u64, c_u64, c_void_p, c_i64, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p]),
@@ -71,6 +72,8 @@ PROTOTYPES = {
     "idl_iid_loss_workspace_bytes": (c_size_t, [c_int]),
     "idl_iid_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_void_p]),
+    "idl_iid_loss_scaled": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p, c_float, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None
@@ -95,7 +98,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.idl_abi_version() != 2:
+    if lib.idl_abi_version() != 3:
         raise IdelucsB200Error("ABI version mismatch")
     _lib = lib
     return lib

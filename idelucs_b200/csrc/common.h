@@ -12,7 +12,7 @@ void note_launch();
 // IIC loss for C <= 16 in one ordinary CTA (train_ops.cu)
 constexpr int IID_SMALL_MAXC = 16;
 int iid_loss_small_launch(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float* d_loss, float* d_joint, float* d_dz1,
-                          float* d_dz2, void* stream);
+                          float* d_dz2, void* stream, float gscale, float loss_w, const float* d_add, float add_w);
 }  // namespace idl
 
 #define IDL_CUDA_CHECK(expr)                                                                             \

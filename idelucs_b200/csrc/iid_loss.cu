@@ -32,6 +32,8 @@ struct LossParams {
     const float* z2;
     int B, C, nt, npairs;
     float lamb, eps;
+    float gscale, loss_w, add_w;   // gradient scale; loss written = loss_w * loss + add_w * (*add)
+    const float* add;
     float* loss;
     float* joint;
     float* dz1;
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(LNT) iid_loss_kernel(const LossParams p) {
     if (blockIdx.x == 0 && tid == 0 && p.loss) {
         float l = 0.f;
         for (int q = 0; q < p.npairs; ++q) l += p.partLoss[q];
-        *p.loss = l;                                           // :44
+        *p.loss = p.add ? p.loss_w * l + p.add_w * (*p.add) : p.loss_w * l;   // :44 (and the caller's weighting)
     }
     if (!p.dz1 && !p.dz2) return;                              // uniform over the grid
     // g_i = lamb * (sum_j Pc_ij) / pic_i for unclamped marginals: the loss holds
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(LNT) iid_loss_kernel(const LossParams p) {
     for (int q = 0; q < p.npairs; ++q) gp += p.partAP[q];      // <A, P>
     if (writer) {
         const float G = Aij + sVec[0][gi] + sVec[0][gj];
-        const float d = (G - gp) / T;                          // dL/dSsym; dS = (dSsym + dSsym^T)/2 = dSsym (symmetric)
+        const float d = p.gscale * (G - gp) / T;               // dL/dSsym; dS = (dSsym + dSsym^T)/2 = dSsym (symmetric)
         p.dS[(size_t)gi * C + gj] = d;
         p.dS[(size_t)gj * C + gi] = d;
     }
@@ -247,17 +249,20 @@ size_t idl_iid_loss_workspace_bytes(int C) {
     return sizeof(float) * (3 * npairs + 2 * nt * LMAXC + (size_t)C * C) + 64;
 }
 
-int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float* d_loss,
-                 float* d_joint, float* d_dz1, float* d_dz2, void* d_workspace, size_t workspace_bytes, void* stream) {
+int idl_iid_loss_scaled(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float grad_scale, float loss_weight,
+                        const float* d_add, float add_weight, float* d_loss, float* d_joint, float* d_dz1, float* d_dz2, void* d_workspace,
+                        size_t workspace_bytes, void* stream) {
     if (!d_z1 || !d_z2 || !d_workspace || B < 1 || C < 1) return set_error(IDL_EINVAL, "idl_iid_loss: bad argument%s", "");
     if (C > LMAXC) return set_error(IDL_EUNSUPPORTED, "idl_iid_loss: n_clusters > 256 not supported%s (got %lld)", "", C);
     if (workspace_bytes < idl_iid_loss_workspace_bytes(C)) return set_error(IDL_EINVAL, "idl_iid_loss: workspace too small%s", "");
     // the usual configurations (n_clusters = 3 .. 12) have a joint of at most 16 x 16: one ordinary CTA, no grid barriers
-    if (C <= IID_SMALL_MAXC) return iid_loss_small_launch(d_z1, d_z2, B, C, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, stream);
+    if (C <= IID_SMALL_MAXC)
+        return iid_loss_small_launch(d_z1, d_z2, B, C, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, stream, grad_scale, loss_weight, d_add, add_weight);
     LossParams p;
     p.z1 = d_z1; p.z2 = d_z2; p.B = B; p.C = C;
     p.nt = (C + LT - 1) / LT; p.npairs = p.nt * (p.nt + 1) / 2;
     p.lamb = lamb; p.eps = eps; p.loss = d_loss; p.joint = d_joint; p.dz1 = d_dz1; p.dz2 = d_dz2;
+    p.gscale = grad_scale; p.loss_w = loss_weight; p.add = d_add; p.add_w = add_weight;
     float* w = reinterpret_cast<float*>(d_workspace);
     p.partT = w; w += p.npairs;
     p.partLoss = w; w += p.npairs;
@@ -269,6 +274,12 @@ int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb,
     IDL_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)iid_loss_kernel, dim3(p.npairs), dim3(LNT), args, 0, (cudaStream_t)stream));
     note_launch();
     return IDL_OK;
+}
+
+int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float* d_loss,
+                 float* d_joint, float* d_dz1, float* d_dz2, void* d_workspace, size_t workspace_bytes, void* stream) {
+    return idl_iid_loss_scaled(d_z1, d_z2, B, C, lamb, eps, 1.0f, 1.0f, nullptr, 0.0f, d_loss, d_joint, d_dz1, d_dz2, d_workspace, workspace_bytes,
+                               stream);
 }
 
 }  // extern "C"

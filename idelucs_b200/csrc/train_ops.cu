@@ -15,6 +15,7 @@
 //                       all-gather them
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdint.h>
 
 #include "common.h"
 
@@ -64,23 +65,68 @@ __global__ void __launch_bounds__(NCE_NT) nce_lse_kernel(const float* __restrict
     }
 }
 
-// In place: S_ij -> W_ij = (1 / (n2 T)) (P_ij + P_ji - 2 [j == pos(i)]),  P_ij = exp(S_ij / T - lse_i), W_ii = 0, so that
-// d loss / d fn = W fn (a second GEMM).  W is symmetric because S is.  Block 0 also reduces the loss (mean of the row terms).
+// In place: S_ij -> W_ij = (g / (n2 T)) (P_ij + P_ji - 2 [j == pos(i)]),  P_ij = exp(S_ij / T - lse_i), W_ii = 0, so that
+// g d loss / d fn = W fn (a second GEMM; g = the caller's weight of this loss).  W is symmetric because S is.  CTA <-> NCE_WR rows,
+// thread <-> four columns (n2 % 4 == 0; a scalar kernel takes other sizes).  Block 0 also reduces the loss (mean of the row terms).
+constexpr int NCE_WR = 4;
 __global__ void __launch_bounds__(256) nce_weights_kernel(float* __restrict__ S, const float* __restrict__ lse, const float* __restrict__ rowloss,
-                                                           int n2, float inv_t, float* __restrict__ loss) {
-    const float c = inv_t / (float)n2;
+                                                           int n2, float inv_t, float gscale, float* __restrict__ loss) {
+    const float c = gscale * inv_t / (float)n2;
     const int half = n2 >> 1;
-    const long long total = (long long)n2 * n2;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(e / n2), j = (int)(e - (long long)i * n2);
-        const float s = S[e] * inv_t;
+    const int n4 = n2 >> 2;
+    const int r0 = blockIdx.x * NCE_WR;
+    for (int q = threadIdx.x; q < n4; q += 256) {
+        const int j0 = q * 4;
+        const float4 lj = *reinterpret_cast<const float4*>(lse + j0);
+#pragma unroll
+        for (int r = 0; r < NCE_WR; ++r) {
+            const int i = r0 + r;
+            if (i >= n2) break;
+            float4* cell = reinterpret_cast<float4*>(S + (size_t)i * n2) + q;
+            const float4 sv = *cell;
+            const float li = lse[i];
+            const int pos = i < half ? i + half : i - half;
+            const float s[4] = {sv.x * inv_t, sv.y * inv_t, sv.z * inv_t, sv.w * inv_t};
+            const float l4[4] = {lj.x, lj.y, lj.z, lj.w};
+            float w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + e;
+                w[e] = 0.f;
+                if (j != i) {
+                    w[e] = __expf(s[e] - li) + __expf(s[e] - l4[e]);
+                    if (j == pos) w[e] -= 2.f;
+                }
+                w[e] *= c;
+            }
+            *cell = make_float4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32 && loss) {
+        float l = 0.f;
+        for (int r = threadIdx.x; r < n2; r += 32) l += rowloss[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        if (threadIdx.x == 0) *loss = l / (float)n2;
+    }
+}
+
+// (n2 not a multiple of 4: element-wise)
+__global__ void __launch_bounds__(256) nce_weights_scalar_kernel(float* __restrict__ S, const float* __restrict__ lse, const float* __restrict__ rowloss,
+                                                                  int n2, float inv_t, float gscale, float* __restrict__ loss) {
+    const float c = gscale * inv_t / (float)n2;
+    const int half = n2 >> 1;
+    const int i = blockIdx.x;
+    const int pos = i < half ? i + half : i - half;
+    const float li = lse[i];
+    for (int j = threadIdx.x; j < n2; j += 256) {
+        const float s = S[(size_t)i * n2 + j] * inv_t;
         float w = 0.f;
         if (j != i) {
-            w = __expf(s - lse[i]) + __expf(s - lse[j]);
-            const int pos = i < half ? i + half : i - half;
+            w = __expf(s - li) + __expf(s - lse[j]);
             if (j == pos) w -= 2.f;
         }
-        S[e] = w * c;
+        S[(size_t)i * n2 + j] = w * c;
     }
     if (blockIdx.x == 0 && threadIdx.x < 32 && loss) {
         float l = 0.f;
@@ -113,7 +159,8 @@ constexpr int IS_MAXC = 16;
 
 __global__ void __launch_bounds__(IS_NT) iid_loss_small_kernel(const float* __restrict__ gz1, const float* __restrict__ gz2, int B, int C, float lamb,
                                                                 float eps, float* __restrict__ loss, float* __restrict__ joint,
-                                                                float* __restrict__ dz1, float* __restrict__ dz2, int staged) {
+                                                                float* __restrict__ dz1, float* __restrict__ dz2, int staged, float gscale,
+                                                                float loss_w, const float* __restrict__ add, float add_w) {
     extern __shared__ __align__(16) float zs[];             // staged: z1 | z2 (2 B C floats) — every later access hits shared memory
     __shared__ float part[IS_NT / 32][IS_MAXC * IS_MAXC];   // per-warp partial S
     __shared__ float S[IS_MAXC][IS_MAXC + 1];               // S, then Ssym
@@ -208,12 +255,12 @@ __global__ void __launch_bounds__(IS_NT) iid_loss_small_kernel(const float* __re
         for (int g = 0; g < IS_NT / 32; ++g) { l += part[g][0]; ap += part[g][1]; }
         float gp = ap;
         for (int i = 0; i < C; ++i) gp += 2.f * gvec[i] * marg[i];
-        if (loss) *loss = l;
+        if (loss) *loss = add ? loss_w * l + add_w * (*add) : loss_w * l;
         red[1] = gp;
     }
     __syncthreads();
     if (!dz1 && !dz2) return;
-    if (tid < np) dS[pi][pj] = (Aij + gvec[pi] + gvec[pj] - red[1]) / T;   // dL/dSsym (symmetric)
+    if (tid < np) dS[pi][pj] = gscale * (Aij + gvec[pi] + gvec[pj] - red[1]) / T;   // dL/dSsym (symmetric), times the caller's weight
     __syncthreads();
     // ---- dz1[b,i] = sum_j z2[b,j] dS[i,j];  dz2[b,j] = sum_i z1[b,i] dS[i,j] ----
     for (int q = tid; q < B * C; q += IS_NT) {
@@ -323,10 +370,177 @@ __global__ void __launch_bounds__(256) rmsprop_allreduce_kernel(const PeerPtrs g
     __threadfence_system();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// IIC loss, C <= 8 (the headline configurations: n_clusters = 3 .. 8): ONE CTA, thread <-> batch row, two CTA barriers.
+// A row's 2 C probabilities stay in registers from the joint to the gradient (B <= 512: one row per thread; more rows are
+// re-read through L1); the C x C outer products are summed over the warp with a transpose-reduce (31 shuffles per 32 pairs, every
+// lane ends with one pair's total) and over the warps by warp 0, which then does the whole C x C algebra (LossFunctions.py:28-44
+// and its derivative) with warp shuffles alone.  Fixed-order sums (run-to-run identical).  gscale multiplies the gradients,
+// and the loss written is loss_w * loss + add_w * (*add) — the caller's weighting of idelucs/models.py:128 without extra launches.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int IR_NT = 512;
+
+template <int NV>
+__device__ __forceinline__ float transpose_reduce(float (&v)[NV], int lane) {   // NV = 32: lane l returns sum over the warp of v[l]
+    static_assert(NV == 32, "one pair slot per lane");
+#pragma unroll
+    for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < n / 2; ++k) {
+            const float send = up ? v[k] : v[k + n / 2];
+            const float keep = up ? v[k + n / 2] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ float warp_total(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int C>
+__global__ void __launch_bounds__(IR_NT) iid_loss_reg_kernel(const float* __restrict__ gz1, const float* __restrict__ gz2, int B, float lamb, float eps,
+                                                              float* __restrict__ loss, float* __restrict__ joint, float* __restrict__ dz1,
+                                                              float* __restrict__ dz2, float gscale, float loss_w, const float* __restrict__ add,
+                                                              float add_w) {
+    constexpr int NP = C * C, NG = (NP + 31) / 32;        // pairs, groups of 32 pair slots
+    __shared__ float part[IR_NT / 32][NG * 32];
+    __shared__ float Sm[C][C + 1], dS[C][C + 1], marg[C], gvec[C];
+    __shared__ float sT;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    float z1[C], z2[C];
+    // ---- S_ij = sum_b z1[b,i] z2[b,j] (LossFunctions.py:54-58) ----
+    {
+        float acc[NG][32];
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int q = 0; q < 32; ++q) acc[g][q] = 0.f;
+        for (int b = tid; b < B; b += IR_NT) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) { z1[c] = __ldg(gz1 + (size_t)b * C + c); z2[c] = __ldg(gz2 + (size_t)b * C + c); }
+#pragma unroll
+            for (int i = 0; i < C; ++i)
+#pragma unroll
+                for (int j = 0; j < C; ++j) acc[(i * C + j) / 32][(i * C + j) % 32] = fmaf(z1[i], z2[j], acc[(i * C + j) / 32][(i * C + j) % 32]);
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) part[w][g * 32 + lane] = transpose_reduce<32>(acc[g], lane);
+    }
+    __syncthreads();
+    if (w == 0) {
+        int pi[NG], pj[NG];
+        bool ok[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const int pr = g * 32 + lane;
+            ok[g] = pr < NP;
+            pi[g] = ok[g] ? pr / C : 0; pj[g] = ok[g] ? pr % C : 0;
+            float sacc = 0.f;
+#pragma unroll
+            for (int q = 0; q < IR_NT / 32; ++q) sacc += part[q][pr];   // fixed order
+            if (ok[g]) Sm[pi[g]][pj[g]] = sacc;
+        }
+        __syncwarp();
+        // symmetrise, normalise (:59-60)
+        float ssym[NG], P[NG], tsum = 0.f;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { ssym[g] = ok[g] ? (Sm[pi[g]][pj[g]] + Sm[pj[g]][pi[g]]) * 0.5f : 0.f; tsum += ssym[g]; }
+        const float T = warp_total(tsum);
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { P[g] = ssym[g] / T; if (ok[g]) { Sm[pi[g]][pj[g]] = P[g]; if (joint) joint[pi[g] * C + pj[g]] = P[g]; } }
+        __syncwarp();
+        // marginals before clamping, the clamp's correction (:28-38)
+        if (lane < C) {
+            float m = 0.f, c = 0.f;
+#pragma unroll
+            for (int j = 0; j < C; ++j) { const float v = Sm[lane][j]; m += v; if (v < eps) c += eps - v; }
+            marg[lane] = m;
+            gvec[lane] = m < eps ? 0.f : lamb * (m + c) / m;
+        }
+        __syncwarp();
+        float term = 0.f, ap = 0.f, A[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            A[g] = 0.f;
+            if (ok[g]) {
+                const bool cl = P[g] < eps;
+                const float Pc = cl ? eps : P[g];
+                const float mi = marg[pi[g]], mj = marg[pj[g]];
+                const float pic = mi < eps ? eps : mi, pjc = mj < eps ? eps : mj;
+                const float inner = logf(Pc) - lamb * logf(pjc) - lamb * logf(pic);
+                term += -Pc * inner;
+                A[g] = cl ? 0.f : (-inner - 1.f);
+                ap += A[g] * P[g];
+            }
+        }
+        const float l = warp_total(term);
+        float gp = warp_total(ap);
+#pragma unroll
+        for (int i = 0; i < C; ++i) gp += 2.f * gvec[i] * marg[i];
+        if (lane == 0) {
+            if (loss) *loss = add ? loss_w * l + add_w * (*add) : loss_w * l;
+            sT = T;
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+            if (ok[g]) dS[pi[g]][pj[g]] = gscale * (A[g] + gvec[pi[g]] + gvec[pj[g]] - gp) / T;   // dL/dSsym (symmetric)
+    }
+    if (!dz1 && !dz2) return;
+    __syncthreads();
+    // ---- dz1[b,i] = sum_j z2[b,j] dS[i,j];  dz2[b,i] = sum_j z1[b,j] dS[i,j] ----
+    float d[C][C];
+#pragma unroll
+    for (int i = 0; i < C; ++i)
+#pragma unroll
+        for (int j = 0; j < C; ++j) d[i][j] = dS[i][j];
+    for (int b = tid; b < B; b += IR_NT) {
+        if (B > IR_NT) {   // (with at most one row per thread it is still in registers)
+#pragma unroll
+            for (int c = 0; c < C; ++c) { z1[c] = __ldg(gz1 + (size_t)b * C + c); z2[c] = __ldg(gz2 + (size_t)b * C + c); }
+        }
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < C; ++j) { a1 = fmaf(z2[j], d[i][j], a1); a2 = fmaf(z1[j], d[i][j], a2); }
+            if (dz1) dz1[(size_t)b * C + i] = a1;
+            if (dz2) dz2[(size_t)b * C + i] = a2;
+        }
+    }
+}
+
+template <int C>
+static void iid_reg_launch(const float* z1, const float* z2, int B, float lamb, float eps, float* loss, float* joint, float* dz1, float* dz2,
+                           float gscale, float loss_w, const float* add, float add_w, cudaStream_t st) {
+    iid_loss_reg_kernel<C><<<1, IR_NT, 0, st>>>(z1, z2, B, lamb, eps, loss, joint, dz1, dz2, gscale, loss_w, add, add_w);
+}
+
 // C <= 16: called by idl_iid_loss (iid_loss.cu)
 int iid_loss_small_launch(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float* d_loss, float* d_joint, float* d_dz1,
-                          float* d_dz2, void* stream) {
-    // both inputs staged in shared memory when they fit (B = 512, C = 5: 20 KB; up to 160 KB)
+                          float* d_dz2, void* stream, float gscale, float loss_w, const float* d_add, float add_w) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C <= 8) {
+        switch (C) {
+            case 1: iid_reg_launch<1>(d_z1, d_z2, B, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, gscale, loss_w, d_add, add_w, st); break;
+            case 2: iid_reg_launch<2>(d_z1, d_z2, B, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, gscale, loss_w, d_add, add_w, st); break;
+            case 3: iid_reg_launch<3>(d_z1, d_z2, B, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, gscale, loss_w, d_add, add_w, st); break;
+            case 4: iid_reg_launch<4>(d_z1, d_z2, B, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, gscale, loss_w, d_add, add_w, st); break;
+            case 5: iid_reg_launch<5>(d_z1, d_z2, B, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, gscale, loss_w, d_add, add_w, st); break;
+            case 6: iid_reg_launch<6>(d_z1, d_z2, B, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, gscale, loss_w, d_add, add_w, st); break;
+            case 7: iid_reg_launch<7>(d_z1, d_z2, B, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, gscale, loss_w, d_add, add_w, st); break;
+            default: iid_reg_launch<8>(d_z1, d_z2, B, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, gscale, loss_w, d_add, add_w, st); break;
+        }
+        note_launch();
+        IDL_CUDA_CHECK(cudaGetLastError());
+        return IDL_OK;
+    }
+    // both inputs staged in shared memory when they fit (up to 160 KB)
     size_t smem = sizeof(float) * 2 * (size_t)B * C;
     int staged = 1;
     if (smem > 160 * 1024) { smem = 0; staged = 0; }
@@ -339,7 +553,7 @@ int iid_loss_small_launch(const float* d_z1, const float* d_z2, int B, int C, fl
             if (dev >= 0 && dev < 64) configured[dev] = true;
         }
     }
-    iid_loss_small_kernel<<<1, IS_NT, smem, (cudaStream_t)stream>>>(d_z1, d_z2, B, C, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, staged); note_launch();
+    iid_loss_small_kernel<<<1, IS_NT, smem, st>>>(d_z1, d_z2, B, C, lamb, eps, d_loss, d_joint, d_dz1, d_dz2, staged, gscale, loss_w, d_add, add_w); note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }
@@ -357,16 +571,22 @@ int idl_nce_normalize(const float* d_h, int n2, int D, float* d_fn, float* d_inv
     return IDL_OK;
 }
 
-int idl_nce_softmax_xent(float* d_sim, int n2, float temperature, float* d_lse, float* d_rowloss, float* d_loss, void* stream) {
+int idl_nce_softmax_xent_scaled(float* d_sim, int n2, float temperature, float grad_scale, float* d_lse, float* d_rowloss, float* d_loss, void* stream) {
     if (!d_sim || !d_lse || !d_rowloss || n2 < 2 || (n2 & 1) || !(temperature > 0.f)) return set_error(IDL_EINVAL, "idl_nce_softmax_xent: bad argument%s", "");
     cudaStream_t st = (cudaStream_t)stream;
     const float inv_t = 1.0f / temperature;
     nce_lse_kernel<<<(n2 + NCE_RB - 1) / NCE_RB, NCE_NT, 0, st>>>(d_sim, n2, inv_t, d_lse, d_rowloss); note_launch();
-    long long grid = ((long long)n2 * n2 + 255) / 256;
-    if (grid > 148 * 8) grid = 148 * 8;
-    nce_weights_kernel<<<(unsigned)grid, 256, 0, st>>>(d_sim, d_lse, d_rowloss, n2, inv_t, d_loss); note_launch();
+    if ((n2 & 3) == 0 && (reinterpret_cast<uintptr_t>(d_sim) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_lse) & 15) == 0)
+        nce_weights_kernel<<<(n2 + NCE_WR - 1) / NCE_WR, 256, 0, st>>>(d_sim, d_lse, d_rowloss, n2, inv_t, grad_scale, d_loss);
+    else
+        nce_weights_scalar_kernel<<<n2, 256, 0, st>>>(d_sim, d_lse, d_rowloss, n2, inv_t, grad_scale, d_loss);
+    note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
+}
+
+int idl_nce_softmax_xent(float* d_sim, int n2, float temperature, float* d_lse, float* d_rowloss, float* d_loss, void* stream) {
+    return idl_nce_softmax_xent_scaled(d_sim, n2, temperature, 1.0f, d_lse, d_rowloss, d_loss, stream);
 }
 
 int idl_nce_normalize_backward(const float* d_dfn, const float* d_fn, const float* d_inv_norm, int n2, int D, float* d_dh, void* stream) {

@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 from . import featurise as ft
-from .LossFunctions import train_losses
+from .LossFunctions import train_losses_and_grads
 from .PytorchUtils import NetLinear
 from .models import weights_init
 
@@ -202,8 +202,10 @@ class ShardedTrainer(object):
         x = self._batch
         self._flat_grad.zero_()
         z, h = self.net(x)      # one pass over the stacked [2B, F] batch: same per-row math as the reference's two forwards
-        loss = train_losses(z, h, self.lamb, self.weight, 0.85)   # (1 - w) InfoNCE + w IIC, one autograd node (models.py:128)
-        loss.backward()
+        # (1 - w) InfoNCE + w IIC (models.py:128) and its gradients with respect to z and h straight from the fused kernels (the
+        # weights ride inside them); the MLP's backward pass is seeded with those — no framework kernel between forward and backward
+        loss, dz, dh = train_losses_and_grads(z, h, self.lamb, self.weight, 0.85)
+        torch.autograd.backward((z, h), (dz, dh))
         if late:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
@@ -211,7 +213,7 @@ class ShardedTrainer(object):
         self._optimizer_step()
         main.wait_stream(self._side)
         self._batch.copy_(nxt)   # (static buffer: the graph's next replay reads it)
-        return loss.detach()
+        return loss
 
     @torch.no_grad()
     def predict(self, seqset, k=6, batch=4096):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define IDL_ABI_VERSION 2
+#define IDL_ABI_VERSION 3
 
 enum {
     IDL_OK = 0,
@@ -236,6 +236,13 @@ size_t idl_iid_loss_workspace_bytes(int C);
 int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float* d_loss,
                  float* d_joint, float* d_dz1, float* d_dz2, void* d_workspace, size_t workspace_bytes,
                  void* stream);
+/* the same with the caller's weighting folded in (idelucs/models.py:128: loss = (1 - w) info_nce + w IID_loss): the gradients are
+ * multiplied by grad_scale and d_loss receives loss_weight * loss + add_weight * (*d_add) (d_add: a device float written earlier
+ * on the same stream, e.g. the InfoNCE loss; NULL = nothing added) — the whole training loss and its gradients without
+ * a single framework kernel between the two fused losses. */
+int idl_iid_loss_scaled(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float grad_scale, float loss_weight,
+                        const float* d_add, float add_weight, float* d_loss, float* d_joint, float* d_dz1, float* d_dz2, void* d_workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* F2 — replaces info_nce_loss (idelucs/LossFunctions.py:65-98; weight 1 - w = 0.75 of the training loss, models.py:128) on the
  * two views stacked as one [n2 = 2B, D] float32 matrix (rows 0..B-1 = first view).  The two dense contractions stay library GEMMs
@@ -248,6 +255,10 @@ int idl_iid_loss(const float* d_z1, const float* d_z2, int B, int C, float lamb,
  * Fixed-order reductions: results are run-to-run identical. */
 int idl_nce_normalize(const float* d_h, int n2, int D, float* d_fn, float* d_inv_norm, void* stream);
 int idl_nce_softmax_xent(float* d_sim, int n2, float temperature, float* d_lse, float* d_rowloss, float* d_loss, void* stream);
+/* the same with W multiplied by grad_scale (the weight 1 - w of this loss in idelucs/models.py:128), so that the gradient
+ * leaves the kernels already weighted; d_loss still receives the unweighted loss */
+int idl_nce_softmax_xent_scaled(float* d_sim, int n2, float temperature, float grad_scale, float* d_lse, float* d_rowloss, float* d_loss,
+                                void* stream);
 int idl_nce_normalize_backward(const float* d_dfn, const float* d_fn, const float* d_inv_norm, int n2, int D, float* d_dh, void* stream);
 
 /* Optimiser step of the data-parallel consumer (idelucs/models.py:86 torch.optim.RMSprop(lr, weight_decay=0.01); momentum 0,

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
         assert name in _lib.PROTOTYPES, "no ctypes prototype for " + name
     assert sorted(_lib.PROTOTYPES) == declared
-    assert lib.idl_abi_version() == 2
+    assert lib.idl_abi_version() == 3
 
 
 def test_geometric_table_matches_oracle():

@@ -5,6 +5,8 @@ import hashlib
 import json
 import os
 
+import sys
+
 import numpy as np
 import pytest
 
@@ -543,6 +545,44 @@ def test_iid_loss_small_kernel_equals_tiled_kernel_and_oracle():
     wl, wd1, wd2 = orc.IID_loss_grad(z1.detach().cpu().numpy(), z2.detach().cpu().numpy(), lamb=2.8)
     assert abs(loss.item() - wl) < 1e-5
     assert np.abs(z1.grad.cpu().numpy() - wd1).max() < 1e-4 * max(np.abs(wd1).max(), 1e-12)
+
+
+def test_weighted_training_loss_and_seeded_gradients():
+    """train_losses_and_grads (idl_nce_softmax_xent_scaled + idl_iid_loss_scaled: the weights of idelucs/models.py:128 inside the
+    kernels, the combined loss written by the IIC kernel) == (1 - w) info_nce + w IID_loss of the reference formulation in
+    float64 and its autograd gradients — register kernel (C <= 8; one and several rows per thread), single-CTA kernel (C <= 16),
+    tiled kernel (C = 200), odd batch sizes (the scalar weights kernel)"""
+    from idelucs_b200.LossFunctions import train_losses_and_grads, train_losses
+    torch.manual_seed(11)
+    for B, C, w, lamb in ((512, 5, 0.25, 2.8), (96, 3, 0.25, 2.8), (700, 5, 0.4, 2.5), (1300, 8, 0.25, 2.8), (333, 7, 0.1, 1.0), (512, 2, 0.9, 2.8),
+                          (256, 12, 0.25, 2.8), (512, 200, 0.25, 2.8), (301, 1, 0.5, 2.0)):
+        z = torch.softmax(torch.randn(2 * B, C, device="cuda") * 2, 1).requires_grad_(True)
+        h = torch.randn(2 * B, 64, device="cuda").requires_grad_(True)
+        zd, hd = z.detach().double().requires_grad_(True), h.detach().double().requires_grad_(True)
+        want = (1 - w) * _ref_style_info_nce(hd[:B], hd[B:], 0.85) + w * _ref_iid64(zd[:B], zd[B:], lamb)
+        gz, gh = torch.autograd.grad(want, (zd, hd))
+        loss, dz, dh = train_losses_and_grads(z, h, lamb, w, 0.85)
+        assert abs(loss.item() - want.item()) < 2e-5, (B, C, loss.item(), want.item())
+        assert float((dz.double() - gz).abs().max()) < 1e-4 * float(gz.abs().max()) + 1e-9, (B, C)
+        assert float((dh.double() - gh).abs().max()) < 1e-4 * float(gh.abs().max()) + 1e-9, (B, C)
+        # the autograd node built on the same kernels, and a second run (fixed-order reductions)
+        l2 = train_losses(z, h, lamb, w, 0.85)
+        az, ah = torch.autograd.grad(l2, (z, h))
+        assert l2.item() == loss.item() and torch.equal(az, dz) and torch.equal(ah, dh)
+
+
+def _ref_iid64(x_out, x_tf_out, lamb, EPS=sys.float_info.epsilon):
+    """idelucs/LossFunctions.py:20-62 in float64 torch ops (the yardstick of the test above)"""
+    k = x_out.shape[1]
+    p_i_j = (x_out.unsqueeze(2) * x_tf_out.unsqueeze(1)).sum(dim=0)
+    p_i_j = (p_i_j + p_i_j.t()) / 2.0
+    p_i_j = p_i_j / p_i_j.sum()
+    p_i = p_i_j.sum(dim=1).view(k, 1).expand(k, k)
+    p_j = p_i_j.sum(dim=0).view(1, k).expand(k, k)
+    p_i_j = torch.where(p_i_j < EPS, torch.full_like(p_i_j, EPS), p_i_j)
+    p_j = torch.where(p_j < EPS, torch.full_like(p_j, EPS), p_j)
+    p_i = torch.where(p_i < EPS, torch.full_like(p_i, EPS), p_i)
+    return (-p_i_j * (torch.log(p_i_j) - lamb * torch.log(p_j) - lamb * torch.log(p_i))).sum()
 
 
 def test_rmsprop_step_matches_torch():
