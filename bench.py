@@ -96,7 +96,7 @@ def cpu_reference(n_seq_per_core, cores):
 def train_breakdown(tr, torch):
     """device time of the parts of one training step, each captured 20x in its own CUDA graph and replayed (no launch overhead,
     like the step itself): pair-batch featurisation, MLP forward + backward, the two fused losses, the optimiser step"""
-    from idelucs_b200.LossFunctions import IID_loss, info_nce_loss_stacked, train_losses
+    from idelucs_b200.LossFunctions import IID_loss, info_nce_loss_stacked, train_losses_and_grads
 
     def timed(fn, reps=20, replays=5):
         s = torch.cuda.Stream()
@@ -126,10 +126,17 @@ def train_breakdown(tr, torch):
         z0, h0 = tr.net(x)
     z0, h0 = z0.detach().clone().requires_grad_(True), h0.detach().clone().requires_grad_(True)
 
-    def mlp():
+    gz, gh = torch.ones_like(z0), torch.ones_like(h0)
+
+    def mlp():            # as the step issues it: first Linear through train._FirstLinear, backward seeded with given gradients
+        tr._grad_tail.zero_()
+        z, h = tr._forward(x)
+        torch.autograd.backward((z, h), (gz, gh))
+
+    def mlp_plain():      # the plain nn.Module forward + autograd backward into the flat gradient buffer, for comparison
         tr._flat_grad.zero_()
         z, h = tr.net(x)
-        (z.sum() + h.sum()).backward()
+        torch.autograd.backward((z, h), (gz, gh))
 
     def iid():
         z0.grad = None
@@ -139,9 +146,8 @@ def train_breakdown(tr, torch):
         h0.grad = None
         info_nce_loss_stacked(h0, 0.85).backward()
 
-    def both():
-        z0.grad = None; h0.grad = None
-        train_losses(z0, h0, tr.lamb, tr.weight, 0.85).backward()
+    def both():           # as the step issues them: values + gradients from the fused kernels, no autograd node
+        train_losses_and_grads(z0, h0, tr.lamb, tr.weight, 0.85)
 
     def torch_ops():
         # the same two losses as plain PyTorch ops (the reference's formulation, idelucs/LossFunctions.py:20-98, with the boolean-mask
@@ -166,7 +172,7 @@ def train_breakdown(tr, torch):
         nce_t = torch.nn.functional.cross_entropy(logits, tgt)
         ((1 - tr.weight) * nce_t + tr.weight * iid_t).backward()
 
-    out = {"featurise_pair_batch_us": timed(lambda: tr._featurise(tr._ids)), "mlp_forward_backward_us": timed(mlp),
+    out = {"featurise_pair_batch_us": timed(lambda: tr._featurise(tr._ids)), "mlp_forward_backward_us": timed(mlp), "mlp_as_plain_module_us": timed(mlp_plain),
            "losses_forward_backward_us": timed(both), "iid_loss_alone_us": timed(iid), "info_nce_alone_us": timed(nce),
            "losses_as_pytorch_ops_us": timed(torch_ops)}
     if tr.world == 1:

@@ -65,6 +65,7 @@ def compute_joint(x_out, x_tf_out):
 
 
 _targets = {}
+_NCE_SPLIT = 8   # inner-dimension split of the W fn contraction (tools/mlp_probe.py)
 
 
 def _info_nce_device(x, temperature, grad_scale=1.0):
@@ -85,8 +86,14 @@ def _info_nce_device(x, temperature, grad_scale=1.0):
         _lib.check(lib.idl_nce_softmax_xent_scaled(_lib.ptr(sim), n2, float(temperature), float(grad_scale),
                                                    ctypes.c_void_p(scratch.data_ptr() + 4 * n2), ctypes.c_void_p(scratch.data_ptr() + 8 * n2),
                                                    _lib.ptr(loss), st))
-        dfn = torch.mm(sim, fn)
-        _lib.check(lib.idl_nce_normalize_backward(_lib.ptr(dfn), _lib.ptr(fn), _lib.ptr(scratch), n2, D, _lib.ptr(dh), st))
+        # dfn = W fn: [n2, n2] x [n2, D] has n2 * D / tile outputs only — split over the inner dimension into ONE batched GEMM
+        # (18 -> 6 us at n2 = 1024, D = 64); the normalisation's backward adds the parts
+        ns = _NCE_SPLIT if n2 % _NCE_SPLIT == 0 and n2 >= 256 else 1
+        if ns > 1:
+            dfn = torch.bmm(sim.view(n2, ns, n2 // ns).transpose(0, 1), fn.view(ns, n2 // ns, D))
+        else:
+            dfn = torch.mm(sim, fn)
+        _lib.check(lib.idl_nce_normalize_backward_parts(_lib.ptr(dfn), ns, _lib.ptr(fn), _lib.ptr(scratch), n2, D, _lib.ptr(dh), st))
     return loss, dh
 
 

@@ -138,17 +138,33 @@ __global__ void __launch_bounds__(256) nce_weights_scalar_kernel(float* __restri
 }
 
 // through F.normalize: dh_i = inv_i (dfn_i - fn_i (fn_i . dfn_i))
-__global__ void __launch_bounds__(NCE_NT) nce_normalize_backward_kernel(const float* __restrict__ dfn, const float* __restrict__ fn,
+// dfn arrives as n_parts partial products (a split-K GEMM issued by the caller as one batched GEMM: W has 2B x 2B entries but the
+// product only 2B x D, so a single GEMM leaves most SMs idle); the parts are added in index order here.
+__global__ void __launch_bounds__(NCE_NT) nce_normalize_backward_kernel(const float* __restrict__ dfn, int n_parts, const float* __restrict__ fn,
                                                                          const float* __restrict__ inv_norm, int n2, int D, float* __restrict__ dh) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * NCE_RB + (threadIdx.x >> 5);
     if (row >= n2) return;
+    const size_t part = (size_t)n2 * D;
+    float g[4];   // D <= 128
     float dot = 0.f;
-    for (int d = lane; d < D; d += 32) dot = fmaf(fn[(size_t)row * D + d], dfn[(size_t)row * D + d], dot);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int d = lane + 32 * q;
+        g[q] = 0.f;
+        if (d < D) {
+            for (int p = 0; p < n_parts; ++p) g[q] += dfn[p * part + (size_t)row * D + d];
+            dot = fmaf(fn[(size_t)row * D + d], g[q], dot);
+        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
     const float inv = inv_norm[row];
-    for (int d = lane; d < D; d += 32) dh[(size_t)row * D + d] = inv * (dfn[(size_t)row * D + d] - fn[(size_t)row * D + d] * dot);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int d = lane + 32 * q;
+        if (d < D) dh[(size_t)row * D + d] = inv * (g[q] - fn[(size_t)row * D + d] * dot);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -589,11 +605,19 @@ int idl_nce_softmax_xent(float* d_sim, int n2, float temperature, float* d_lse, 
     return idl_nce_softmax_xent_scaled(d_sim, n2, temperature, 1.0f, d_lse, d_rowloss, d_loss, stream);
 }
 
-int idl_nce_normalize_backward(const float* d_dfn, const float* d_fn, const float* d_inv_norm, int n2, int D, float* d_dh, void* stream) {
-    if (!d_dfn || !d_fn || !d_inv_norm || !d_dh || n2 < 1 || D < 1) return set_error(IDL_EINVAL, "idl_nce_normalize_backward: bad argument%s", "");
-    nce_normalize_backward_kernel<<<(n2 + NCE_RB - 1) / NCE_RB, NCE_NT, 0, (cudaStream_t)stream>>>(d_dfn, d_fn, d_inv_norm, n2, D, d_dh); note_launch();
+int idl_nce_normalize_backward_parts(const float* d_dfn_parts, int n_parts, const float* d_fn, const float* d_inv_norm, int n2, int D, float* d_dh,
+                                     void* stream) {
+    if (!d_dfn_parts || !d_fn || !d_inv_norm || !d_dh || n2 < 1 || D < 1 || n_parts < 1)
+        return set_error(IDL_EINVAL, "idl_nce_normalize_backward: bad argument%s", "");
+    if (D > 128) return set_error(IDL_EUNSUPPORTED, "idl_nce_normalize_backward: latent width > 128 not supported%s (got %lld)", "", D);
+    nce_normalize_backward_kernel<<<(n2 + NCE_RB - 1) / NCE_RB, NCE_NT, 0, (cudaStream_t)stream>>>(d_dfn_parts, n_parts, d_fn, d_inv_norm, n2, D, d_dh);
+    note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
+}
+
+int idl_nce_normalize_backward(const float* d_dfn, const float* d_fn, const float* d_inv_norm, int n2, int D, float* d_dh, void* stream) {
+    return idl_nce_normalize_backward_parts(d_dfn, 1, d_fn, d_inv_norm, n2, D, d_dh, stream);
 }
 
 int idl_rmsprop_step(float* d_param, const float* d_grad, float* d_square_avg, int64_t n, float lr, float alpha, float eps, float weight_decay,

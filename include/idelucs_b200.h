@@ -260,6 +260,11 @@ int idl_nce_softmax_xent(float* d_sim, int n2, float temperature, float* d_lse, 
 int idl_nce_softmax_xent_scaled(float* d_sim, int n2, float temperature, float grad_scale, float* d_lse, float* d_rowloss, float* d_loss,
                                 void* stream);
 int idl_nce_normalize_backward(const float* d_dfn, const float* d_fn, const float* d_inv_norm, int n2, int D, float* d_dh, void* stream);
+/* the same with dfn given as n_parts partial products [n_parts, n2, D] (the caller splits the W fn contraction over its inner
+ * dimension into one batched GEMM — a [n2, n2] x [n2, D] product alone has too few output tiles to fill the GPU); the parts are
+ * added in index order */
+int idl_nce_normalize_backward_parts(const float* d_dfn_parts, int n_parts, const float* d_fn, const float* d_inv_norm, int n2, int D,
+                                     float* d_dh, void* stream);
 
 /* Optimiser step of the data-parallel consumer (idelucs/models.py:86 torch.optim.RMSprop(lr, weight_decay=0.01); momentum 0,
  * not centred) on a flat float32 shard, one elementwise pass: g = grad * grad_scale + weight_decay * p;

@@ -571,6 +571,27 @@ def test_weighted_training_loss_and_seeded_gradients():
         assert l2.item() == loss.item() and torch.equal(az, dz) and torch.equal(ah, dh)
 
 
+def test_first_linear_split_equals_nn_linear():
+    """train._FirstLinear (inner-dimension split of the first Linear's forward GEMM, weight gradient written into its slice of a flat
+    buffer) against nn.Linear + autograd on the same weights: same output, same gradients (float32 summation order aside)"""
+    from idelucs_b200.train import _FirstLinear
+    torch.manual_seed(5)
+    lin = torch.nn.Linear(4096, 512).cuda()
+    x = torch.randn(1024, 4096, device="cuda") * 3
+    dy = torch.randn(1024, 512, device="cuda")
+    want = lin(x)
+    want.backward(dy)
+    flat = torch.full((512 * 4096 + 512,), 7.0, device="cuda")           # stale contents must be overwritten, not accumulated
+    gw, gb = flat[:512 * 4096].view(512, 4096), flat[512 * 4096:]
+    for ns in (1, 4, 8):
+        flat.fill_(7.0)
+        got = _FirstLinear.apply(x, lin.weight, lin.bias, gw, gb, ns)
+        got.backward(dy)
+        assert float((got - want).abs().max()) < 1e-3 * float(want.abs().max())
+        assert float((gw - lin.weight.grad).abs().max()) < 1e-4 * float(lin.weight.grad.abs().max())
+        assert float((gb - lin.bias.grad).abs().max()) < 1e-4 * float(lin.bias.grad.abs().max())
+
+
 def _ref_iid64(x_out, x_tf_out, lamb, EPS=sys.float_info.epsilon):
     """idelucs/LossFunctions.py:20-62 in float64 torch ops (the yardstick of the test above)"""
     k = x_out.shape[1]

@@ -52,6 +52,26 @@ def main():
                                             ctypes.c_void_p(scratch.data_ptr() + 8 * n2), _lib.ptr(loss), st()))
     def mm2():
         torch.mm(sim, fn_, out=dfn)
+    fn_t = fn_.t().contiguous(); dfn_t = torch.empty(D, n2, device=dev)
+    def mm2_t():      # W symmetric: (fn^T W)^T
+        torch.mm(fn_.t(), sim, out=dfn_t)
+    def mm2_tc():
+        torch.mm(fn_t, sim, out=dfn_t)
+    def mm2_nt():
+        torch.mm(sim, fn_t.t(), out=dfn)
+    def mm2_split():  # K split in 4 by hand: [4, n2, n2/4] x [4, n2/4, D] -> sum
+        a = sim.view(n2, 4, n2 // 4).transpose(0, 1)
+        b = fn_.view(4, n2 // 4, D)
+        torch.bmm(a, b).sum(0)
+    def make_split(ns):
+        a = sim.view(n2, ns, n2 // ns).transpose(0, 1)
+        b = fn_.view(ns, n2 // ns, D)
+        o = torch.empty(ns, n2, D, device=dev)
+        return lambda: torch.bmm(a, b, out=o)
+    splits = [("bmm split-K %d (no sum)" % ns, make_split(ns)) for ns in (2, 4, 8, 16, 32)]
+    def lse_only():
+        _lib.check(lib.idl_nce_softmax_xent(_lib.ptr(sim), n2, 0.85, ctypes.c_void_p(scratch.data_ptr() + 4 * n2),
+                                            ctypes.c_void_p(scratch.data_ptr() + 8 * n2), None, st()))
     def nbwd():
         _lib.check(lib.idl_nce_normalize_backward(_lib.ptr(dfn), _lib.ptr(fn_), _lib.ptr(scratch), n2, D, _lib.ptr(dh), st()))
     zr = z.clone().requires_grad_(True); hr = h.clone().requires_grad_(True)
@@ -61,8 +81,8 @@ def main():
     def empty():
         loss.add_(1.0)
     norm(); mm1()
-    for name, f in (("tiny torch kernel (add_)", empty), ("idl_iid_loss (fwd + grad)", iid), ("idl_nce_normalize", norm), ("mm sim", mm1),
-                    ("idl_nce_softmax_xent", xent), ("mm dfn", mm2), ("idl_nce_normalize_backward", nbwd), ("train_losses fwd + bwd", both)):
+    for name, f in splits + [("tiny torch kernel (add_)", empty), ("idl_iid_loss (fwd + grad)", iid), ("idl_nce_normalize", norm), ("mm sim", mm1),
+                    ("idl_nce_softmax_xent", xent), ("mm dfn", mm2), ("mm dfn as (fn^T W)", mm2_t), ("mm dfn as (fn_t contiguous) W", mm2_tc), ("mm dfn NT", mm2_nt), ("mm dfn split-K bmm", mm2_split), ("idl_nce_normalize_backward", nbwd), ("train_losses fwd + bwd", both)]:
         print("%-32s %7.2f us" % (name, graph_time(f)), flush=True)
 
 
