@@ -80,6 +80,7 @@ struct ProfParams {
     const int64_t* out_off;
     long long out_stride;
     int pseudocount, accumulate;
+    int cta_cap;                      // host side: at most this many CTAs per SM for the generic kernel (0 = as many as fit)
     const float* mean;
     const float* scale;
     const float* rscale;  // 1/scale (IEEE), computed into the workspace by rscale_kernel
@@ -1263,6 +1264,7 @@ static int launch_profiles(const ProfParams& p, const Plan& plan, cudaStream_t s
     int per_sm = 0;
     IDL_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
     if (per_sm < 1) return set_error(IDL_ECUDA, "profiles kernel does not fit on an SM%s", "");
+    if (p.cta_cap > 0 && per_sm > p.cta_cap) per_sm = p.cta_cap;   // the caller wants room left on every SM (a concurrent stream)
     long long grid = (long long)sm_count() * per_sm;
     if (grid > p.n_items) grid = p.n_items;
     if (grid < 1) grid = 1;
@@ -1388,7 +1390,7 @@ static void fill_params(ProfParams& p, const uint32_t* d_codes, const uint32_t* 
     p.seed = seed; p.gtab = reinterpret_cast<const uint32_t*>(ws + WS_GTAB);
     p.edit_off = d_edit_off; p.edits = d_edits; p.out = d_out;
     p.out_off = reinterpret_cast<const int64_t*>(ws + WS_OUTOFF);
-    p.out_stride = out_stride; p.pseudocount = pseudocount; p.accumulate = accumulate;
+    p.out_stride = out_stride; p.pseudocount = pseudocount; p.accumulate = accumulate & 1; p.cta_cap = (accumulate >> 8) & 0xFF;
     p.mean = d_mean; p.scale = d_scale; p.status = d_status;
     p.rscale = reinterpret_cast<const float*>(ws + WS_RSCALE);
     p.work_counter = reinterpret_cast<unsigned long long*>(ws);
@@ -1448,7 +1450,7 @@ static int profiles_impl(const uint32_t* d_codes, const uint32_t* d_nmask, const
         return set_error(IDL_EINVAL, "idl_profiles: n_variants / S out of range%s", "");
     if (!d_sel && S != n_variants) return set_error(IDL_EINVAL, "idl_profiles: S must equal n_variants without d_sel%s", "");
     if (out_kind == IDL_OUT_STD_F32 && (!d_mean || !d_scale)) return set_error(IDL_EINVAL, "idl_profiles: mean/scale required%s", "");
-    if (accumulate && out_kind != IDL_OUT_COUNTS_I32) return set_error(IDL_EINVAL, "idl_profiles: accumulate only for counts%s", "");
+    if ((accumulate & 1) && out_kind != IDL_OUT_COUNTS_I32) return set_error(IDL_EINVAL, "idl_profiles: accumulate only for counts%s", "");
     if (n_items <= 0) return IDL_OK;
     const int F = 1 << (2 * k);
     if (k >= 1 && F >= 4 && (out_stride % 4 != 0)) return set_error(IDL_EINVAL, "idl_profiles: out_stride must be a multiple of 4%s", "");

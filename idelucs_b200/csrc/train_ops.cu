@@ -293,6 +293,21 @@ __global__ void __launch_bounds__(IS_NT) iid_loss_small_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Pair ids -> what the mimic kernel's selection mode wants (idelucs/utils.py:370-389: row r of x_train is sequence r mod N with
+// mimic r div N + 1 on the 'modified' side and slot 0 on the 'true' side): item = sequence index, sel = (0, mimic).  One launch
+// instead of ten framework kernels of index arithmetic at the head of every training step.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pair_selection_kernel(const long long* __restrict__ pair_ids, int n, long long n_seqs, int* __restrict__ sidx, int* __restrict__ sel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long id = pair_ids[i];
+    const long long m = id / n_seqs;
+    sidx[i] = (int)(id - m * n_seqs);
+    sel[2 * i] = 0;
+    sel[2 * i + 1] = (int)m + 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // RMSprop (torch.optim.RMSprop, momentum = 0, centered = False): g = grad * gscale + wd * p; v = alpha v + (1 - alpha) g^2;
 // p -= lr * g / (sqrt(v) + eps)
 // ---------------------------------------------------------------------------------------------------------------
@@ -618,6 +633,16 @@ int idl_nce_normalize_backward_parts(const float* d_dfn_parts, int n_parts, cons
 
 int idl_nce_normalize_backward(const float* d_dfn, const float* d_fn, const float* d_inv_norm, int n2, int D, float* d_dh, void* stream) {
     return idl_nce_normalize_backward_parts(d_dfn, 1, d_fn, d_inv_norm, n2, D, d_dh, stream);
+}
+
+int idl_pair_selection(const int64_t* d_pair_ids, int n, int64_t n_seqs, int32_t* d_sidx, int32_t* d_sel, void* stream) {
+    if (!d_pair_ids || !d_sidx || !d_sel || n < 0 || n_seqs < 1) return set_error(IDL_EINVAL, "idl_pair_selection: bad argument%s", "");
+    if (n == 0) return IDL_OK;
+    pair_selection_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(d_pair_ids), n, (long long)n_seqs, d_sidx,
+                                                                            d_sel);
+    note_launch();
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
 }
 
 int idl_rmsprop_step(float* d_param, const float* d_grad, float* d_square_avg, int64_t n, float lr, float alpha, float eps, float weight_decay,

@@ -156,11 +156,12 @@ STATS_SLAB = 131072   # sequences per prepare call when only the statistics are 
 
 def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_off=None, out_stride=None,
              mean=None, scale=None, sidx=None, sel=None, S=None, edit_lists=None, seq_id0=0, pseudocount=None,
-             accumulate=False, status=None, prepared=None, chunked=None, max_long=None):
+             accumulate=False, status=None, prepared=None, chunked=None, max_long=None, cta_cap=0):
     """Run K2+K3.  Default output: tensor [S, n_items, 4^k] (variant-major) of the out_kind's
     dtype.  See include/idelucs_b200.h::idl_profiles for the argument meaning.  ``prepared`` (from ``prepare`` with the
     same SeqSet / variants / seed / seq_id0) routes float32 outputs through idl_profiles_prepared (k = 6 fast path).  Sets with
-    sequences of >= 65 536 bases go through idl_profiles_chunked (k = 6; chunked=False forces the generic kernel)."""
+    sequences of >= 65 536 bases go through idl_profiles_chunked (k = 6; chunked=False forces the generic kernel).  ``cta_cap`` > 0
+    caps the generic kernel at that many CTAs per SM (room for a concurrent stream)."""
     lib = _lib.load()
     device = seqset.device
     F = 4 ** k
@@ -212,7 +213,7 @@ def profiles(seqset, k, variants, out_kind=OUT_FREQ_F32, seed=0, out=None, out_o
             _lib.ptr(seqset.codes), _lib.ptr(seqset.nmask), _lib.ptr(seqset.chunk_off), _lib.ptr(seqset.len), seqset.n,
             _lib.ptr(sidx), n_items, int(seq_id0), k, varr, nv, _lib.ptr(sel), S, ctypes.c_uint64(seed & (2 ** 64 - 1)),
             _lib.ptr(d_eoff), _lib.ptr(d_ent), out_kind, _lib.ptr(out), offs, int(out_stride), int(pseudocount),
-            1 if accumulate else 0, _lib.ptr(mean), _lib.ptr(scale), _lib.ptr(status), _lib.ptr(ws), ws.numel(),
+            (1 if accumulate else 0) | ((int(cta_cap) & 0xFF) << 8), _lib.ptr(mean), _lib.ptr(scale), _lib.ptr(status), _lib.ptr(ws), ws.numel(),
             _lib.stream_ptr()))
     return out
 

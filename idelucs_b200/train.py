@@ -200,9 +200,9 @@ class ShardedTrainer(object):
         self._cursor += self.batch_sz
         return ids
 
-    def _featurise(self, ids):
+    def _featurise(self, ids, cta_cap=0):
         """pair batch as one stacked [2B, F] tensor (rows 0..B-1 = 'true' side)"""
-        batch = self.loader.batch(ids)
+        batch = self.loader.batch(ids, cta_cap=cta_cap)
         if "both" in batch:
             return batch["both"]
         return torch.cat((batch["true"], batch["modified"]), 0)
@@ -227,19 +227,25 @@ class ShardedTrainer(object):
         if self._batch is None:
             self._batch = self._featurise(self._ids).clone()
         main = torch.cuda.current_stream(self.dev)
-        # ---- side stream: batch t+1 (ids in self._ids) into a fresh buffer.  One rank: under the forward / backward pass (small
-        # GEMMs leave most SMs idle).  Several ranks: under the optimiser step, whose kernel waits on NVLink, not on SMs ----
+        # ---- side stream: batch t+1 (ids in self._ids) into a fresh buffer.  One rank: under the MIDDLE of the step — the two big
+        # GEMMs of the first layer (forward at the start, weight gradient at the end) fill every SM's register file, and a
+        # featurisation kernel launched beside them only delays them (measured: 28 us of idle main stream); between them sit ~160 us
+        # of small GEMMs, losses and elementwise kernels that leave the SMs mostly empty.  The kernel is capped at one CTA per SM so
+        # that those small kernels still find room.  Several ranks: under the optimiser step, whose kernel waits on NVLink, not on SMs ----
         late = self.world > 1 and self.overlap_featurise_with == "optimizer"
         nxt = None
-        if not late:
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                nxt = self._featurise(self._ids)
         # ---- main stream: step t on self._batch ----
         x = self._batch
         self._grad_tail.zero_()   # (the first layer's gradients are overwritten by _FirstLinear, everything else accumulates)
         # one pass over the stacked [2B, F] batch: same per-row math as the reference's two forwards
-        z, h = self._forward(x)
+        lin1 = self.net.layers[0]
+        a1 = _FirstLinear.apply(x, lin1.weight, lin1.bias, lin1.weight.grad, lin1.bias.grad, self.first_layer_split)
+        if not late:
+            self._side.wait_stream(main)          # (after the first layer's forward GEMM)
+            with torch.cuda.stream(self._side):
+                nxt = self._featurise(self._ids, cta_cap=1)
+        h = self.net.layers[1:](a1)
+        z = self.net.classifier(h)
         # (1 - w) InfoNCE + w IIC (models.py:128) and its gradients with respect to z and h straight from the fused kernels (the
         # weights ride inside them); the MLP's backward pass is seeded with those — no framework kernel between forward and backward
         loss, dz, dh = train_losses_and_grads(z, h, self.lamb, self.weight, 0.85)

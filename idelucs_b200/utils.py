@@ -13,6 +13,7 @@ import os
 import numpy as np
 import torch
 
+from . import _lib
 from . import featurise as ft
 from .seqset import SeqSet, read_fasta_raw
 
@@ -284,16 +285,23 @@ class PairBatchLoader(object):
     def __len__(self):
         return self.n_pairs // self.batch_size if self.drop_last else (self.n_pairs + self.batch_size - 1) // self.batch_size
 
-    def batch(self, pair_ids):
+    def batch(self, pair_ids, cta_cap=0):
         """pair id = (mimic-1) * N + sequence  (the reference's mimic-major row order)"""
         n = self.ss.n
-        mim = torch.div(pair_ids, n, rounding_mode="floor") + 1
-        sidx = pair_ids - (mim - 1) * n
         if self.profiles is not None:
+            mim = torch.div(pair_ids, n, rounding_mode="floor") + 1
+            sidx = pair_ids - (mim - 1) * n
             return {"true": self.profiles[0][sidx], "modified": self.profiles[mim, sidx]}
-        sel = torch.stack([torch.zeros_like(mim), mim], dim=1).to(torch.int32).contiguous()
-        out = ft.profiles(self.ss, self.k, self.variants, out_kind=ft.OUT_STD_F32, seed=self.seed, sidx=sidx.to(torch.int32),
-                          sel=sel, mean=self.scaler.mean32, scale=self.scaler.scale32, seq_id0=self.seq_id0)
+        # regenerated batch: item = sequence, slots (0, mimic) — the index arithmetic is one launch (idl_pair_selection)
+        B = int(pair_ids.numel())
+        sidx = torch.empty(B, dtype=torch.int32, device=pair_ids.device)
+        sel = torch.empty((B, 2), dtype=torch.int32, device=pair_ids.device)
+        ids = pair_ids if (pair_ids.dtype == torch.int64 and pair_ids.is_contiguous()) else pair_ids.to(torch.int64).contiguous()
+        lib = _lib.load()
+        with torch.cuda.device(pair_ids.device):
+            _lib.check(lib.idl_pair_selection(_lib.ptr(ids), B, n, _lib.ptr(sidx), _lib.ptr(sel), _lib.stream_ptr()))
+        out = ft.profiles(self.ss, self.k, self.variants, out_kind=ft.OUT_STD_F32, seed=self.seed, sidx=sidx,
+                          sel=sel, mean=self.scaler.mean32, scale=self.scaler.scale32, seq_id0=self.seq_id0, cta_cap=cta_cap)
         return {"true": out[0], "modified": out[1], "both": out.view(-1, out.shape[-1])}   # 'both' = the two sides stacked, no copy
 
     def __iter__(self):

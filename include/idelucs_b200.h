@@ -107,7 +107,8 @@ size_t idl_profiles_workspace_bytes(void);
  * val 0..3 = set A/C/G/T, 4 = set N; position-sorted and unique per list; positions < 2^29, which also bounds the length of
  * sequences that take a non-clean variant — clean counting accepts any length < 2^31), n_seqs_total =
  * number of sequences the CSR is indexed over.  d_mean/d_scale: float32[4^k] for
- * IDL_OUT_STD_F32.  accumulate != 0 (COUNTS only) adds into d_out like kmers.pyx does.
+ * IDL_OUT_STD_F32.  accumulate: bit 0 set (COUNTS only) adds into d_out like kmers.pyx does; bits 8..15 = n > 0 caps the generic
+ * kernel at n CTAs per SM (a caller that overlaps the call with other work on another stream leaves room for it; 0 = fill the GPU).
  * d_status int32[n_items] (optional, zero on entry): scratch flags of the fast kernels (bit 1 marks items handed to the generic
  * kernel inside a call; clear again when the work is done).  No rate or length makes a mutation get dropped: edit lists that
  * do not fit on chip are generated in smaller tiles.
@@ -265,6 +266,11 @@ int idl_nce_normalize_backward(const float* d_dfn, const float* d_fn, const floa
  * added in index order */
 int idl_nce_normalize_backward_parts(const float* d_dfn_parts, int n_parts, const float* d_fn, const float* d_inv_norm, int n2, int D,
                                      float* d_dh, void* stream);
+
+/* Row ids of the reference's x_train (idelucs/utils.py:321-389: row r = sequence r mod N paired with mimic r div N + 1) -> the
+ * arguments of idl_profiles' selection mode for one batch: d_sidx[n] = sequence index, d_sel[n, 2] = (0, mimic slot).  Replaces the
+ * index arithmetic AugmentedDataset.__getitem__ does per item. */
+int idl_pair_selection(const int64_t* d_pair_ids, int n, int64_t n_seqs, int32_t* d_sidx, int32_t* d_sel, void* stream);
 
 /* Optimiser step of the data-parallel consumer (idelucs/models.py:86 torch.optim.RMSprop(lr, weight_decay=0.01); momentum 0,
  * not centred) on a flat float32 shard, one elementwise pass: g = grad * grad_scale + weight_decay * p;
