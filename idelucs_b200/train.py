@@ -24,7 +24,7 @@ class _FirstLinear(torch.autograd.Function):
     its slice of the flat gradient buffer (no zero-fill and no accumulate pass over 8.4 MB) and needs no input gradient."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gw_out, gb_out, n_split):
+    def forward(ctx, x, weight, bias, gw_out, gb_out, n_split, side=None):
         M, K = x.shape
         N = weight.shape[0]
         if n_split > 1 and K % n_split == 0:
@@ -34,15 +34,22 @@ class _FirstLinear(torch.autograd.Function):
         else:
             out = torch.addmm(bias, x, weight.t())
         ctx.save_for_backward(x)
-        ctx.gw_out, ctx.gb_out = gw_out, gb_out
+        ctx.gw_out, ctx.gb_out, ctx.side = gw_out, gb_out, side
         return out
 
     @staticmethod
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
-        torch.mm(dy.t(), x, out=ctx.gw_out)
-        torch.sum(dy, 0, out=ctx.gb_out)
-        return None, None, None, None, None, None
+        if ctx.side is not None:   # the bias gradient (a column sum) runs beside the weight-gradient GEMM; the caller joins the streams
+            main = torch.cuda.current_stream(dy.device)
+            ctx.side.wait_stream(main)
+            with torch.cuda.stream(ctx.side):
+                torch.sum(dy, 0, out=ctx.gb_out)
+            torch.mm(dy.t(), x, out=ctx.gw_out)
+        else:
+            torch.mm(dy.t(), x, out=ctx.gw_out)
+            torch.sum(dy, 0, out=ctx.gb_out)
+        return None, None, None, None, None, None, None
 
 
 class ShardedTrainer(object):
@@ -239,7 +246,7 @@ class ShardedTrainer(object):
         self._grad_tail.zero_()   # (the first layer's gradients are overwritten by _FirstLinear, everything else accumulates)
         # one pass over the stacked [2B, F] batch: same per-row math as the reference's two forwards
         lin1 = self.net.layers[0]
-        a1 = _FirstLinear.apply(x, lin1.weight, lin1.bias, lin1.weight.grad, lin1.bias.grad, self.first_layer_split)
+        a1 = _FirstLinear.apply(x, lin1.weight, lin1.bias, lin1.weight.grad, lin1.bias.grad, self.first_layer_split, self._side)
         if not late:
             self._side.wait_stream(main)          # (after the first layer's forward GEMM)
             with torch.cuda.stream(self._side):
@@ -254,9 +261,19 @@ class ShardedTrainer(object):
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 nxt = self._featurise(self._ids)
+        if late:
+            self._optimizer_step()
+            main.wait_stream(self._side)
+            self._batch.copy_(nxt)   # (static buffer: the graph's next replay reads it)
+            return loss
+        # the hand-over of batch t+1 into the static buffer (16 MB) rides on the side stream beside the optimiser step: x's last
+        # reader (the first layer's weight-gradient GEMM) is done, the featurisation and the bias gradient are earlier on that stream
+        main.wait_event(self._side.record_event())   # the bias gradient of the first layer, before the optimiser reads it
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self._batch.copy_(nxt)
         self._optimizer_step()
         main.wait_stream(self._side)
-        self._batch.copy_(nxt)   # (static buffer: the graph's next replay reads it)
         return loss
 
     @torch.no_grad()
