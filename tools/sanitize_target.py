@@ -39,10 +39,15 @@ def main():
         assert torch.equal(a, b)
         print("long ok")
     if which in ("all", "loss"):
-        for C in (5, 40):
-            z1 = torch.softmax(torch.randn(96, C, device="cuda"), 1).requires_grad_(True)
-            z2 = torch.softmax(torch.randn(96, C, device="cuda"), 1).requires_grad_(True)
+        for B, C in ((96, 5), (700, 8), (96, 12), (96, 40)):   # register kernel (one / several rows per thread), single-CTA kernel, tiled kernel
+            z1 = torch.softmax(torch.randn(B, C, device="cuda"), 1).requires_grad_(True)
+            z2 = torch.softmax(torch.randn(B, C, device="cuda"), 1).requires_grad_(True)
             IID_loss(z1, z2, lamb=2.8).backward()
+        from idelucs_b200.LossFunctions import train_losses_and_grads
+        for B, C in ((512, 5), (37, 3)):   # weighted path: vectorised / scalar weights kernel, split / single gradient GEMM
+            z = torch.softmax(torch.randn(2 * B, C, device="cuda"), 1)
+            h = torch.randn(2 * B, 64, device="cuda")
+            train_losses_and_grads(z, h, 2.8, 0.25, 0.85)
         h1 = torch.randn(64, 64, device="cuda", requires_grad=True)
         h2 = torch.randn(64, 64, device="cuda", requires_grad=True)
         info_nce_loss(h1, h2, 0.85).backward()
@@ -50,7 +55,11 @@ def main():
         lib = _lib.load()
         p, g, v = torch.randn(1000, device="cuda"), torch.randn(1000, device="cuda"), torch.zeros(1000, device="cuda")
         _lib.check(lib.idl_rmsprop_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(v), 1000, 1e-3, 0.99, 1e-8, 0.01, 1.0, _lib.stream_ptr()))
+        ids = torch.randint(0, 5000, (300,), device="cuda")
+        sidx = torch.empty(300, dtype=torch.int32, device="cuda"); sel = torch.empty((300, 2), dtype=torch.int32, device="cuda")
+        _lib.check(lib.idl_pair_selection(_lib.ptr(ids), 300, 100, _lib.ptr(sidx), _lib.ptr(sel), _lib.stream_ptr()))
         torch.cuda.synchronize()
+        assert torch.equal(sidx.long(), ids % 100) and torch.equal(sel[:, 1].long(), ids // 100 + 1)
         print("loss ok")
 
 
