@@ -17,24 +17,55 @@ def _ws(device, C):
     return _workspace(device, _lib.load().idl_iid_loss_workspace_bytes(C), "loss%d" % C)
 
 
+_IID_GEMM_MIN_C = 17   # above the single-CTA kernels' range: contractions as library GEMMs + idl_iid_joint_algebra
+
+
+def _iid_device(z1, z2, lamb, EPS, want_grad=True, want_joint=False, grad_scale=1.0, loss_weight=1.0, add=None, add_weight=0.0,
+                dz1=None, dz2=None):
+    """IIC loss of float32 contiguous CUDA [B, C] tensors (may be the two halves of one stacked tensor): (loss, joint, dz1, dz2).
+    C <= 16: one launch (idl_iid_loss_scaled: register-resident / single-CTA kernels).  Larger C (the 200 output units of the
+    embedding path): S = z1^T z2, dz1 = z2 dS, dz2 = z1 dS as three small strict-fp32 GEMMs around idl_iid_joint_algebra — 20 us
+    instead of 52 us for the cooperative tiled kernel the C ABI's idl_iid_loss uses on its own."""
+    lib = _lib.load()
+    B, C = z1.shape
+    dev = z1.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    joint = torch.empty((C, C), dtype=torch.float32, device=dev) if want_joint else None
+    if want_grad:
+        dz1 = torch.empty_like(z1) if dz1 is None else dz1
+        dz2 = torch.empty_like(z2) if dz2 is None else dz2
+    else:
+        dz1 = dz2 = None
+    with torch.cuda.device(dev):
+        if C < _IID_GEMM_MIN_C:
+            ws = _ws(dev, C)
+            _lib.check(lib.idl_iid_loss_scaled(_lib.ptr(z1), _lib.ptr(z2), B, C, float(lamb), float(EPS), float(grad_scale), float(loss_weight),
+                                               _lib.ptr(add), float(add_weight), _lib.ptr(loss), _lib.ptr(joint), _lib.ptr(dz1), _lib.ptr(dz2),
+                                               _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        else:
+            S = torch.mm(z1.t(), z2)
+            S = S + S.t()          # the algebra kernel reads the symmetrised joint row by row
+            dS = torch.empty_like(S) if want_grad else None
+            scratch = torch.empty(6 * C, dtype=torch.float32, device=dev)
+            _lib.check(lib.idl_iid_joint_algebra(_lib.ptr(S), C, float(lamb), float(EPS), float(grad_scale), float(loss_weight), _lib.ptr(add),
+                                                 float(add_weight), _lib.ptr(loss), _lib.ptr(joint), _lib.ptr(dS), _lib.ptr(scratch),
+                                                 _lib.stream_ptr()))
+            if want_grad:
+                torch.mm(z2, dS, out=dz1)
+                torch.mm(z1, dS, out=dz2)
+    return loss, joint, dz1, dz2
+
+
 class _IIDLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_out, x_tf_out, lamb, EPS):
-        lib = _lib.load()
         if not x_out.is_cuda:
             raise _lib.IdelucsB200Error("IID_loss: tensors must be on a CUDA device (no CPU fallback)")
         z1 = x_out.detach().contiguous().float()
         z2 = x_tf_out.detach().contiguous().float()
-        B, C = z1.shape
-        assert z2.shape == (B, C)
-        loss = torch.empty((), dtype=torch.float32, device=z1.device)
+        assert z2.shape == z1.shape
         need_grad = x_out.requires_grad or x_tf_out.requires_grad
-        dz1 = torch.empty_like(z1) if need_grad else None
-        dz2 = torch.empty_like(z2) if need_grad else None
-        with torch.cuda.device(z1.device):
-            ws = _ws(z1.device, C)
-            _lib.check(lib.idl_iid_loss(_lib.ptr(z1), _lib.ptr(z2), B, C, float(lamb), float(EPS), _lib.ptr(loss), None,
-                                        _lib.ptr(dz1), _lib.ptr(dz2), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        loss, _, dz1, dz2 = _iid_device(z1, z2, lamb, EPS, want_grad=need_grad)
         if need_grad:
             ctx.save_for_backward(dz1, dz2)
         return loss
@@ -52,16 +83,9 @@ def IID_loss(x_out, x_tf_out, lamb=1.0, EPS=sys.float_info.epsilon):
 
 def compute_joint(x_out, x_tf_out):
     """idelucs/LossFunctions.py:49-62 — symmetrised, normalised joint [C, C] (no autograd)."""
-    lib = _lib.load()
     z1 = x_out.detach().contiguous().float()
     z2 = x_tf_out.detach().contiguous().float()
-    B, C = z1.shape
-    joint = torch.empty((C, C), dtype=torch.float32, device=z1.device)
-    with torch.cuda.device(z1.device):
-        ws = _ws(z1.device, C)
-        _lib.check(lib.idl_iid_loss(_lib.ptr(z1), _lib.ptr(z2), B, C, 1.0, float(sys.float_info.epsilon), None,
-                                    _lib.ptr(joint), None, None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
-    return joint
+    return _iid_device(z1, z2, 1.0, sys.float_info.epsilon, want_grad=False, want_joint=True)[1]
 
 
 _targets = {}
@@ -108,14 +132,9 @@ def train_losses_and_grads(z, h, lamb, weight, temperature=0.85, EPS=sys.float_i
     n2, C = zz.shape
     B = n2 // 2
     nce, dh = _info_nce_device(h.detach().contiguous().float(), temperature, grad_scale=1.0 - weight)
-    loss = torch.empty((), dtype=torch.float32, device=zz.device)
     dz = torch.empty_like(zz)
-    with torch.cuda.device(zz.device):
-        ws = _ws(zz.device, C)
-        half = 4 * B * C   # bytes: rows B.. of z are the second view
-        _lib.check(lib.idl_iid_loss_scaled(_lib.ptr(zz), ctypes.c_void_p(zz.data_ptr() + half), B, C, float(lamb), float(EPS), float(weight),
-                                           float(weight), _lib.ptr(nce), float(1.0 - weight), _lib.ptr(loss), None, _lib.ptr(dz),
-                                           ctypes.c_void_p(dz.data_ptr() + half), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    loss, _, _, _ = _iid_device(zz[:B], zz[B:], lamb, EPS, grad_scale=weight, loss_weight=weight, add=nce, add_weight=1.0 - weight,
+                                dz1=dz[:B], dz2=dz[B:])
     return loss, dz, dh
 
 

@@ -74,6 +74,8 @@ PROTOTYPES = {
     "idl_iid_loss_workspace_bytes": (c_size_t, [c_int]),
     "idl_iid_loss": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_void_p]),
+    "idl_iid_joint_algebra": (c_int, [c_void_p, c_int, c_float, c_float, c_float, c_float, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
     "idl_iid_loss_scaled": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p, c_float, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }

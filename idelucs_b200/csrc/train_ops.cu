@@ -552,6 +552,97 @@ static void iid_reg_launch(const float* z1, const float* z2, int B, float lamb, 
     iid_loss_reg_kernel<C><<<1, IR_NT, 0, st>>>(z1, z2, B, lamb, eps, loss, joint, dz1, dz2, gscale, loss_w, add, add_w);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// IIC loss from a given S2 = S + S^T, S = z1^T z2 (any C): the C x C algebra of LossFunctions.py:28-44, :59-60 and its derivative.
+// For large C (C = 200 of the embedding path) the contractions around it (S = z1^T z2, dz1 = z2 dS, dz2 = z1 dS) are small dense
+// GEMMs and stay library calls issued by the caller, like InfoNCE's; these kernels replace the cooperative tiled kernel (three
+// grid barriers, 52 us at C = 200) on that path.  Four dependent launches, warp <-> row of the (symmetrised: coalesced row reads
+// only) joint, the few global scalars (T, loss, <A, P>) re-derived by every warp from per-row partials in a fixed order — a single
+// CTA doing the same work takes 65 us (instruction-bound on one SM).
+// scratch: 6 C floats = rowsum | marg | gvec | lgm | rowterm | rowap
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int IA_NT = 256, IA_RPB = IA_NT / 32;
+
+__device__ __forceinline__ float ordered_total(const float* __restrict__ x, int n, int lane) {   // the same value in every warp that calls it
+    float t = 0.f;
+    for (int i = lane; i < n; i += 32) t += x[i];
+    return warp_total(t);
+}
+
+__global__ void __launch_bounds__(IA_NT) iid_alg_rowsum_kernel(const float* __restrict__ S2, int C, float* __restrict__ scratch) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * IA_RPB + (threadIdx.x >> 5);
+    if (i >= C) return;
+    float t = 0.f;
+    for (int j = lane; j < C; j += 32) t += 0.5f * S2[(size_t)i * C + j];   // (S + S^T) / 2 (:59)
+    t = warp_total(t);
+    if (lane == 0) scratch[i] = t;
+}
+
+__global__ void __launch_bounds__(IA_NT) iid_alg_marginal_kernel(const float* __restrict__ S2, int C, float lamb, float eps, float* __restrict__ scratch,
+                                                                 float* __restrict__ joint) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * IA_RPB + (threadIdx.x >> 5);
+    if (i >= C) return;
+    const float T = ordered_total(scratch, C, lane);
+    float m = 0.f, c = 0.f;
+    for (int j = lane; j < C; j += 32) {   // normalise (:60); marginal before clamping and the clamp's correction (:28-38)
+        const float P = 0.5f * S2[(size_t)i * C + j] / T;
+        m += P;
+        if (P < eps) c += eps - P;
+        if (joint) joint[(size_t)i * C + j] = P;
+    }
+    m = warp_total(m); c = warp_total(c);
+    if (lane == 0) {
+        scratch[C + i] = m;
+        scratch[2 * C + i] = m < eps ? 0.f : lamb * (m + c) / m;
+        scratch[3 * C + i] = lamb * logf(m < eps ? eps : m);
+    }
+}
+
+__global__ void __launch_bounds__(IA_NT) iid_alg_terms_kernel(const float* __restrict__ S2, int C, float eps, float* __restrict__ scratch) {
+    const int lane = threadIdx.x & 31, i = blockIdx.x * IA_RPB + (threadIdx.x >> 5);
+    if (i >= C) return;
+    const float T = ordered_total(scratch, C, lane);
+    const float* lgm = scratch + 3 * C;
+    const float li = lgm[i];
+    float term = 0.f, ap = 0.f;
+    for (int j = lane; j < C; j += 32) {   // entropy terms (:40-44) and <A, P>, A = d term / d P (0 where clamped)
+        const float P = 0.5f * S2[(size_t)i * C + j] / T;
+        const bool cl = P < eps;
+        const float Pc = cl ? eps : P;
+        const float inner = logf(Pc) - lgm[j] - li;
+        term += -Pc * inner;
+        if (!cl) ap += (-inner - 1.f) * P;
+    }
+    term = warp_total(term); ap = warp_total(ap);
+    if (lane == 0) { scratch[4 * C + i] = term; scratch[5 * C + i] = ap; }
+}
+
+__global__ void __launch_bounds__(IA_NT) iid_alg_grad_kernel(const float* __restrict__ S2, int C, float eps, float gscale, float loss_w,
+                                                             const float* __restrict__ add, float add_w, const float* __restrict__ scratch,
+                                                             float* __restrict__ loss, float* __restrict__ dS) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, i = blockIdx.x * IA_RPB + w;
+    if (blockIdx.x == 0 && w == 0 && loss) {
+        const float l = ordered_total(scratch + 4 * C, C, lane);
+        if (lane == 0) *loss = add ? loss_w * l + add_w * (*add) : loss_w * l;
+    }
+    if (i >= C || !dS) return;
+    const float T = ordered_total(scratch, C, lane);
+    const float* marg = scratch + C;
+    const float* gvec = scratch + 2 * C;
+    const float* lgm = scratch + 3 * C;
+    float gm = 0.f;
+    for (int q = lane; q < C; q += 32) gm += 2.f * gvec[q] * marg[q];
+    const float gp = ordered_total(scratch + 5 * C, C, lane) + warp_total(gm);
+    const float li = lgm[i], gi = gvec[i], sc = gscale / T;
+    for (int j = lane; j < C; j += 32) {
+        const float P = 0.5f * S2[(size_t)i * C + j] / T;
+        const bool cl = P < eps;
+        const float inner = logf(cl ? eps : P) - lgm[j] - li;
+        const float A = cl ? 0.f : (-inner - 1.f);
+        dS[(size_t)i * C + j] = sc * (A + gi + gvec[j] - gp);   // dL/dS_sym (symmetric), times the caller's weight
+    }
+}
+
 // C <= 16: called by idl_iid_loss (iid_loss.cu)
 int iid_loss_small_launch(const float* d_z1, const float* d_z2, int B, int C, float lamb, float eps, float* d_loss, float* d_joint, float* d_dz1,
                           float* d_dz2, void* stream, float gscale, float loss_w, const float* d_add, float add_w) {
@@ -633,6 +724,21 @@ int idl_nce_normalize_backward_parts(const float* d_dfn_parts, int n_parts, cons
 
 int idl_nce_normalize_backward(const float* d_dfn, const float* d_fn, const float* d_inv_norm, int n2, int D, float* d_dh, void* stream) {
     return idl_nce_normalize_backward_parts(d_dfn, 1, d_fn, d_inv_norm, n2, D, d_dh, stream);
+}
+
+int idl_iid_joint_algebra(const float* d_S2, int C, float lamb, float eps, float grad_scale, float loss_weight, const float* d_add, float add_weight,
+                          float* d_loss, float* d_joint, float* d_dS, float* d_scratch, void* stream) {
+    if (!d_S2 || !d_scratch || C < 1) return set_error(IDL_EINVAL, "idl_iid_joint_algebra: bad argument%s", "");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (C + IA_RPB - 1) / IA_RPB;
+    iid_alg_rowsum_kernel<<<grid, IA_NT, 0, st>>>(d_S2, C, d_scratch); note_launch();
+    iid_alg_marginal_kernel<<<grid, IA_NT, 0, st>>>(d_S2, C, lamb, eps, d_scratch, d_joint); note_launch();
+    if (d_loss || d_dS) {
+        iid_alg_terms_kernel<<<grid, IA_NT, 0, st>>>(d_S2, C, eps, d_scratch); note_launch();
+        iid_alg_grad_kernel<<<grid, IA_NT, 0, st>>>(d_S2, C, eps, grad_scale, loss_weight, d_add, add_weight, d_scratch, d_loss, d_dS); note_launch();
+    }
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
 }
 
 int idl_pair_selection(const int64_t* d_pair_ids, int n, int64_t n_seqs, int32_t* d_sidx, int32_t* d_sel, void* stream) {

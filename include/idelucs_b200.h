@@ -245,6 +245,13 @@ int idl_iid_loss_scaled(const float* d_z1, const float* d_z2, int B, int C, floa
                         const float* d_add, float add_weight, float* d_loss, float* d_joint, float* d_dz1, float* d_dz2, void* d_workspace,
                         size_t workspace_bytes, void* stream);
 
+/* The C x C part of the same loss for callers that issue its three contractions as library GEMMs (worth it for large C, e.g. the
+ * 200 output units of the n_clusters = 0 path): d_S2 = S + S^T with S = z1^T z2, [C, C] row-major, on entry; outputs (each optional):
+ * d_loss (weighted and combined like idl_iid_loss_scaled), d_joint [C, C], d_dS [C, C] = grad_scale * dLoss/dS_sym (symmetric), from
+ * which dLoss/dz1 = z2 dS and dLoss/dz2 = z1 dS.  d_scratch: 6 C floats.  Four small launches, fixed-order reductions, any C. */
+int idl_iid_joint_algebra(const float* d_S2, int C, float lamb, float eps, float grad_scale, float loss_weight, const float* d_add,
+                          float add_weight, float* d_loss, float* d_joint, float* d_dS, float* d_scratch, void* stream);
+
 /* F2 — replaces info_nce_loss (idelucs/LossFunctions.py:65-98; weight 1 - w = 0.75 of the training loss, models.py:128) on the
  * two views stacked as one [n2 = 2B, D] float32 matrix (rows 0..B-1 = first view).  The two dense contractions stay library GEMMs
  * issued by the caller (strict fp32): S = fn fn^T and d loss / d fn = W fn.  Around them:

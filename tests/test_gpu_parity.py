@@ -571,6 +571,37 @@ def test_weighted_training_loss_and_seeded_gradients():
         assert l2.item() == loss.item() and torch.equal(az, dz) and torch.equal(ah, dh)
 
 
+def test_iid_tiled_kernel_equals_gemm_route_and_oracle():
+    """C > 16: the Python layer issues the three contractions as GEMMs around idl_iid_joint_algebra; the C ABI's own idl_iid_loss
+    keeps the cooperative tiled kernel.  Both against the oracle's closed form (loss, joint, gradients), incl. the weighting."""
+    import ctypes
+    from idelucs_b200 import _lib
+    from idelucs_b200.LossFunctions import _iid_device, _ws
+    lib = _lib.load()
+    rng = np.random.default_rng(21)
+    for B, C, lamb in ((512, 200, 2.8), (96, 17, 1.0), (300, 64, 2.5), (64, 256, 2.8)):
+        z1 = torch.softmax(torch.from_numpy(rng.normal(size=(B, C)).astype(np.float32) * 3), 1).cuda()
+        z2 = torch.softmax(torch.from_numpy(rng.normal(size=(B, C)).astype(np.float32) * 3), 1).cuda()
+        wl, wd1, wd2 = orc.IID_loss_grad(z1.cpu().numpy(), z2.cpu().numpy(), lamb=lamb)
+        wj = orc.compute_joint(z1.cpu().numpy(), z2.cpu().numpy())
+        m = max(np.abs(wd1).max(), np.abs(wd2).max())
+        add = torch.tensor(0.5, device="cuda")
+        # GEMM route (what IID_loss / train_losses take)
+        loss, joint, d1, d2 = _iid_device(z1, z2, lamb, sys.float_info.epsilon, want_joint=True, grad_scale=0.25, loss_weight=0.25, add=add,
+                                          add_weight=0.75)
+        assert abs(loss.item() - (0.25 * wl + 0.75 * 0.5)) < 1e-5, (B, C)
+        np.testing.assert_allclose(joint.cpu().numpy(), wj, rtol=1e-4, atol=1e-9)
+        assert np.abs(d1.cpu().numpy() - 0.25 * wd1).max() < 1e-4 * 0.25 * m and np.abs(d2.cpu().numpy() - 0.25 * wd2).max() < 1e-4 * 0.25 * m
+        # the C ABI on its own (tiled kernel)
+        l2 = torch.empty((), device="cuda"); j2 = torch.empty((C, C), device="cuda"); e1 = torch.empty_like(z1); e2 = torch.empty_like(z2)
+        ws = _ws(z1.device, C)
+        _lib.check(lib.idl_iid_loss_scaled(_lib.ptr(z1), _lib.ptr(z2), B, C, lamb, sys.float_info.epsilon, 0.25, 0.25, _lib.ptr(add), 0.75, _lib.ptr(l2),
+                                           _lib.ptr(j2), _lib.ptr(e1), _lib.ptr(e2), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        assert abs(l2.item() - (0.25 * wl + 0.75 * 0.5)) < 1e-5, (B, C)
+        np.testing.assert_allclose(j2.cpu().numpy(), wj, rtol=1e-4, atol=1e-9)
+        assert np.abs(e1.cpu().numpy() - 0.25 * wd1).max() < 1e-4 * 0.25 * m and np.abs(e2.cpu().numpy() - 0.25 * wd2).max() < 1e-4 * 0.25 * m
+
+
 def test_first_linear_split_equals_nn_linear():
     """train._FirstLinear (inner-dimension split of the first Linear's forward GEMM, weight gradient written into its slice of a flat
     buffer) against nn.Linear + autograd on the same weights: same output, same gradients (float32 summation order aside)"""

@@ -38,6 +38,8 @@ def main():
     ws = LF._ws(dev, C)
     half = 4 * B * C
     st = lambda: _lib.stream_ptr()
+    def iid_py():
+        LF._iid_device(z[:B], z[B:], 2.8, 2.2e-16, dz1=dz[:B], dz2=dz[B:])
     def iid():
         _lib.check(lib.idl_iid_loss(_lib.ptr(z), ctypes.c_void_p(z.data_ptr() + half), B, C, 2.8, 2.2e-16, _lib.ptr(loss), None,
                                     _lib.ptr(dz), ctypes.c_void_p(dz.data_ptr() + half), _lib.ptr(ws), ws.numel(), st()))
@@ -81,7 +83,7 @@ def main():
     def empty():
         loss.add_(1.0)
     norm(); mm1()
-    for name, f in splits + [("tiny torch kernel (add_)", empty), ("idl_iid_loss (fwd + grad)", iid), ("idl_nce_normalize", norm), ("mm sim", mm1),
+    for name, f in splits + [("tiny torch kernel (add_)", empty), ("idl_iid_loss (fwd + grad)", iid), ("IIC through the Python layer", iid_py), ("idl_nce_normalize", norm), ("mm sim", mm1),
                     ("idl_nce_softmax_xent", xent), ("mm dfn", mm2), ("mm dfn as (fn^T W)", mm2_t), ("mm dfn as (fn_t contiguous) W", mm2_tc), ("mm dfn NT", mm2_nt), ("mm dfn split-K bmm", mm2_split), ("idl_nce_normalize_backward", nbwd), ("train_losses fwd + bwd", both)]:
         print("%-32s %7.2f us" % (name, graph_time(f)), flush=True)
 
