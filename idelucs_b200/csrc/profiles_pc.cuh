@@ -38,6 +38,9 @@ constexpr int PC_NBLD = 256;       // builder threads (warps 0..7)
 constexpr int PC_NFIX = 224;       // fix threads (warps 8..14); warp 15 lane 0 is the store thread
 constexpr int PC_NBUF = 4;         // 16 KB row buffers
 constexpr int PC_NOTH = 1;         // row buffers that take the "other" jobs (dense rows, minority window totals) while the rest stream the main total
+#ifndef PC_TIGHT
+#define PC_TIGHT 0
+#endif
 #ifndef PC_INFL_N
 #define PC_INFL_N (PC_NBUF - 2)
 #endif
@@ -661,6 +664,18 @@ __device__ __forceinline__ void pc_store(PcSmem& sm, const ProfParams& p) {
                 mbar_wait(&sm.row_full[buf], (gj / PC_NBUF) & 1);
                 clk.tick(1);
                 unsigned char* dst = reinterpret_cast<unsigned char*>(p.out) + (jd & ~15ull);
+#if PC_TIGHT
+                // ONE copy in flight per SM, re-issued the moment the previous one has been read (the regime in which a pure
+                // store stream reaches 7.0 instead of 6.3 TB/s, tools/ubench/tma_store.cu): the row is known to be ready before the
+                // wait, and the previous buffer's bookkeeping comes after the issue
+                if (gj >= 1) bulk_wait_read<0>();
+                bulk_store(dst, sm.rowbuf[buf], PC_F * 4);
+                bulk_commit();
+                if (gj >= 1) {
+                    st_release_smem(&sm.free_count[(gj - 1) % PC_NBUF], (gj - 1) / PC_NBUF + 1);
+                    mbar_arrive(&sm.row_free[(gj - 1) % PC_NBUF]);
+                }
+#else
                 if (IDL_DBG(p) & 4) bulk_store_hint(dst, sm.rowbuf[buf], PC_F * 4, pol_ef);
                 else bulk_store(dst, sm.rowbuf[buf], PC_F * 4);
                 bulk_commit();
@@ -670,6 +685,7 @@ __device__ __forceinline__ void pc_store(PcSmem& sm, const ProfParams& p) {
                     st_release_smem(&sm.free_count[(gj - PC_INFL) % PC_NBUF], (gj - PC_INFL) / PC_NBUF + 1);
                     mbar_arrive(&sm.row_free[(gj - PC_INFL) % PC_NBUF]);
                 }
+#endif
             }
         }
         mbar_arrive(&sm.ctx_empty[b]);
