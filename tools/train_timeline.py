@@ -7,16 +7,22 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from idelucs_b200.seqset import SeqSet
 from idelucs_b200.train import ShardedTrainer
 
-dev = torch.device("cuda")
+from idelucs_b200 import parallel
+rank, local, world = parallel.init_from_env()   # torchrun: one rank per GPU (rank 0 prints)
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
 nt, Lt = 200000, 2000
-g = torch.Generator(device="cuda").manual_seed(0)
+g = torch.Generator(device=dev).manual_seed(rank)
 codes = torch.randint(0, 4, (nt * Lt,), device=dev, dtype=torch.uint8, generator=g)
 a = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)[codes.long()]
 del codes
 ss = SeqSet.from_ascii(a, np.arange(nt + 1, dtype=np.int64) * Lt, device=dev)
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-tr = ShardedTrainer(ss, k=6, n_clusters=C, n_mimics=50, batch_sz=512, seed=7)
-print("graph:", tr.enable_cuda_graph())
+tr = ShardedTrainer(ss, k=6, n_clusters=C, n_mimics=50, batch_sz=512, seed=7, world=world, seq_id0=rank * nt,
+                    split_reduce=os.environ.get("SPLIT_REDUCE", "1") == "1")
+ok = tr.enable_cuda_graph()
+if rank == 0:
+    print("graph:", ok, "mode:", tr._mode, "split:", tr._split_reduce)
 for _ in range(20):
     tr.step()
 torch.cuda.synchronize()
@@ -25,6 +31,8 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(4):
         tr.step()
     torch.cuda.synchronize()
+if rank != 0:
+    sys.exit(0)
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 evs.sort(key=lambda e: e.time_range.start)
 # split into replays: a step starts with the featurise / zero kernels; use the gaps
