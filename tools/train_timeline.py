@@ -18,11 +18,10 @@ a = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)[codes.long()]
 del codes
 ss = SeqSet.from_ascii(a, np.arange(nt + 1, dtype=np.int64) * Lt, device=dev)
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 5
-tr = ShardedTrainer(ss, k=6, n_clusters=C, n_mimics=50, batch_sz=512, seed=7, world=world, seq_id0=rank * nt,
-                    split_reduce=os.environ.get("SPLIT_REDUCE", "1") == "1")
+tr = ShardedTrainer(ss, k=6, n_clusters=C, n_mimics=50, batch_sz=512, seed=7, world=world, seq_id0=rank * nt)
 ok = tr.enable_cuda_graph()
 if rank == 0:
-    print("graph:", ok, "mode:", tr._mode, "split:", tr._split_reduce)
+    print("graph:", ok, "mode:", tr._mode)
 for _ in range(20):
     tr.step()
 torch.cuda.synchronize()
