@@ -146,25 +146,34 @@ __global__ void __launch_bounds__(NCE_NT) nce_normalize_backward_kernel(const fl
     const int row = blockIdx.x * NCE_RB + (threadIdx.x >> 5);
     if (row >= n2) return;
     const size_t part = (size_t)n2 * D;
-    float g[4];   // D <= 128
-    float dot = 0.f;
+    const float inv = inv_norm[row];
+    if (D <= 128) {   // the parts' sum stays in registers
+        float g[4];
+        float dot = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int d = lane + 32 * q;
-        g[q] = 0.f;
-        if (d < D) {
-            for (int p = 0; p < n_parts; ++p) g[q] += dfn[p * part + (size_t)row * D + d];
-            dot = fmaf(fn[(size_t)row * D + d], g[q], dot);
+        for (int q = 0; q < 4; ++q) {
+            const int d = lane + 32 * q;
+            g[q] = 0.f;
+            if (d < D) {
+                for (int p = 0; p < n_parts; ++p) g[q] += dfn[p * part + (size_t)row * D + d];
+                dot = fmaf(fn[(size_t)row * D + d], g[q], dot);
+            }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int d = lane + 32 * q;
+            if (d < D) dh[(size_t)row * D + d] = inv * (g[q] - fn[(size_t)row * D + d] * dot);
+        }
+        return;
     }
+    auto gsum = [&](int d) { float g = 0.f; for (int p = 0; p < n_parts; ++p) g += dfn[p * part + (size_t)row * D + d]; return g; };
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32) dot = fmaf(fn[(size_t)row * D + d], gsum(d), dot);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    const float inv = inv_norm[row];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int d = lane + 32 * q;
-        if (d < D) dh[(size_t)row * D + d] = inv * (g[q] - fn[(size_t)row * D + d] * dot);
-    }
+    for (int d = lane; d < D; d += 32) dh[(size_t)row * D + d] = inv * (gsum(d) - fn[(size_t)row * D + d] * dot);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -715,7 +724,6 @@ int idl_nce_normalize_backward_parts(const float* d_dfn_parts, int n_parts, cons
                                      void* stream) {
     if (!d_dfn_parts || !d_fn || !d_inv_norm || !d_dh || n2 < 1 || D < 1 || n_parts < 1)
         return set_error(IDL_EINVAL, "idl_nce_normalize_backward: bad argument%s", "");
-    if (D > 128) return set_error(IDL_EUNSUPPORTED, "idl_nce_normalize_backward: latent width > 128 not supported%s (got %lld)", "", D);
     nce_normalize_backward_kernel<<<(n2 + NCE_RB - 1) / NCE_RB, NCE_NT, 0, (cudaStream_t)stream>>>(d_dfn_parts, n_parts, d_fn, d_inv_norm, n2, D, d_dh);
     note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());

@@ -503,7 +503,7 @@ def test_fused_info_nce_matches_reference_formulation():
     launches) against the reference's formulation and its autograd gradient, in float64 as the yardstick"""
     from idelucs_b200.LossFunctions import info_nce_loss, info_nce_loss_stacked
     torch.manual_seed(3)
-    for n, d, scale in ((512, 64, 1.0), (256, 64, 30.0), (5, 64, 1.0), (37, 32, 0.1), (100, 128, 3.0), (1, 64, 1.0)):
+    for n, d, scale in ((512, 64, 1.0), (256, 64, 30.0), (5, 64, 1.0), (37, 32, 0.1), (100, 128, 3.0), (1, 64, 1.0), (64, 256, 1.0), (33, 160, 2.0)):
         a = (torch.randn(n, d, device="cuda") * scale).requires_grad_(True)
         b = (torch.randn(n, d, device="cuda") * scale + 0.3 * a.detach()).requires_grad_(True)
         want = _ref_style_info_nce(a.double(), b.double(), 0.85)
