@@ -129,7 +129,6 @@ def train_breakdown(tr, torch):
     gz, gh = torch.ones_like(z0), torch.ones_like(h0)
 
     def mlp():            # as the step issues it: first Linear through train._FirstLinear, backward seeded with given gradients
-        tr._grad_tail.zero_()
         z, h = tr._forward(x)
         torch.autograd.backward((z, h), (gz, gh))
 

@@ -602,6 +602,34 @@ def test_iid_tiled_kernel_equals_gemm_route_and_oracle():
         assert np.abs(e1.cpu().numpy() - 0.25 * wd1).max() < 1e-4 * 0.25 * m and np.abs(e2.cpu().numpy() - 0.25 * wd2).max() < 1e-4 * 0.25 * m
 
 
+def test_trainer_forward_backward_equals_plain_module():
+    """ShardedTrainer._forward (_FirstLinear + _FlatLinear: gradients written into the flat buffer, nothing zeroed or accumulated)
+    against the plain NetLinear module + autograd with the same dropout masks: same outputs, same gradient for every parameter —
+    also on the second step, when the flat buffer still holds the previous gradients"""
+    from idelucs_b200.seqset import SeqSet
+    from idelucs_b200.train import ShardedTrainer
+    rng = np.random.default_rng(3)
+    seqs = [np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=600)].tobytes() for _ in range(700)]
+    tr = ShardedTrainer(SeqSet.from_sequences(seqs), k=6, n_clusters=5, n_mimics=3, batch_sz=256, seed=1)
+    params = [p for p in tr.net.parameters()]
+    for step in range(2):
+        x = torch.randn(512, 4096, device="cuda")
+        gz, gh = torch.randn(512, 5, device="cuda"), torch.randn(512, 64, device="cuda")
+        torch.manual_seed(100 + step)
+        z, h = tr._forward(x)
+        torch.autograd.backward((z, h), (gz, gh))
+        got = [p.grad.detach().clone() for p in params]
+        zo, ho = z.detach().clone(), h.detach().clone()
+        for p in params:
+            p.grad.zero_()
+        torch.manual_seed(100 + step)
+        z2, h2 = tr.net(x)
+        torch.autograd.backward((z2, h2), (gz, gh))
+        assert torch.allclose(zo, z2, rtol=1e-4, atol=1e-6) and torch.allclose(ho, h2, rtol=1e-4, atol=1e-4)
+        for g, p in zip(got, params):
+            assert float((g - p.grad).abs().max()) <= 2e-4 * float(p.grad.abs().max()) + 1e-7, (step, tuple(p.shape))
+
+
 def test_first_linear_split_equals_nn_linear():
     """train._FirstLinear (inner-dimension split of the first Linear's forward GEMM, weight gradient written into its slice of a flat
     buffer) against nn.Linear + autograd on the same weights: same output, same gradients (float32 summation order aside)"""
