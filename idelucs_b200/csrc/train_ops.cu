@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "common.h"
+#include "core.cuh"
 
 namespace idl {
 
@@ -298,6 +299,51 @@ __global__ void __launch_bounds__(IS_NT) iid_loss_small_kernel(const float* __re
         }
         if (dz1) dz1[q] = a1;
         if (dz2) dz2[q] = a2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ReLU + Dropout of the encoder (idelucs/PytorchUtils.py:36-44: Linear - ReLU - Dropout(0.5)) in one pass each way, behind a
+// GEMM whose output arrives as n_parts partial products (the inner-dimension split of train._FirstLinear) plus a bias:
+//   forward   v = sum_p parts[p] + bias;  out = (v > 0 and kept) ? v / (1 - p) : 0
+//   backward  dx = out > 0 ? dy / (1 - p) : 0      (out > 0 exactly where the unit was active AND kept: no mask is stored)
+// The keep decision of element e in training step t is one Philox4x32-10 word: counter (e / 4, t lo, t hi, layer tag), key = seed,
+// word e % 4 — stateless, so a CUDA graph replays it with the step counter read from device memory.  Replaces the framework's
+// reduce + add + clamp + fused_dropout launches (13 us behind the first layer) and masked_scale + threshold_backward.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) relu_dropout_fwd_kernel(const float* __restrict__ parts, int n_parts, const float* __restrict__ bias, long long n4,
+                                                               int N4, uint32_t thresh, float inv_keep, unsigned long long seed,
+                                                               const long long* __restrict__ step, uint32_t tag, float* __restrict__ out) {
+    const long long t = step ? *step : 0;
+    const size_t part4 = (size_t)n4;
+    for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < n4; q += (long long)gridDim.x * 256) {
+        float4 v = reinterpret_cast<const float4*>(parts)[q];
+        for (int p = 1; p < n_parts; ++p) {
+            const float4 w = reinterpret_cast<const float4*>(parts)[p * part4 + q];
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (int)(q % N4));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        const U4 r = philox4x32_10((uint32_t)q, (uint32_t)t, (uint32_t)((unsigned long long)t >> 32), tag ^ (uint32_t)((unsigned long long)q >> 32),
+                                   (uint32_t)seed, (uint32_t)(seed >> 32));
+        float4 o;
+        o.x = (v.x > 0.f && r.x >= thresh) ? v.x * inv_keep : 0.f;   // dropped with probability thresh / 2^32 = p
+        o.y = (v.y > 0.f && r.y >= thresh) ? v.y * inv_keep : 0.f;
+        o.z = (v.z > 0.f && r.z >= thresh) ? v.z * inv_keep : 0.f;
+        o.w = (v.w > 0.f && r.w >= thresh) ? v.w * inv_keep : 0.f;
+        reinterpret_cast<float4*>(out)[q] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) relu_dropout_bwd_kernel(const float* __restrict__ out, const float* __restrict__ dy, long long n4, float inv_keep,
+                                                               float* __restrict__ dx) {
+    for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < n4; q += (long long)gridDim.x * 256) {
+        const float4 o = reinterpret_cast<const float4*>(out)[q];
+        const float4 g = reinterpret_cast<const float4*>(dy)[q];
+        reinterpret_cast<float4*>(dx)[q] = make_float4(o.x > 0.f ? g.x * inv_keep : 0.f, o.y > 0.f ? g.y * inv_keep : 0.f,
+                                                       o.z > 0.f ? g.z * inv_keep : 0.f, o.w > 0.f ? g.w * inv_keep : 0.f);
     }
 }
 
@@ -745,6 +791,32 @@ int idl_iid_joint_algebra(const float* d_S2, int C, float lamb, float eps, float
         iid_alg_terms_kernel<<<grid, IA_NT, 0, st>>>(d_S2, C, eps, d_scratch); note_launch();
         iid_alg_grad_kernel<<<grid, IA_NT, 0, st>>>(d_S2, C, eps, grad_scale, loss_weight, d_add, add_weight, d_scratch, d_loss, d_dS); note_launch();
     }
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
+}
+
+int idl_relu_dropout_forward(const float* d_parts, int n_parts, const float* d_bias, int64_t M, int N, float p, uint64_t seed, const int64_t* d_step,
+                             uint32_t tag, float* d_out, void* stream) {
+    if (!d_parts || !d_out || n_parts < 1 || M < 1 || N < 4 || (N & 3) || !(p >= 0.f) || !(p < 1.f))
+        return set_error(IDL_EINVAL, "idl_relu_dropout_forward: bad argument%s (N must be a multiple of 4, 0 <= p < 1)", "");
+    const long long n4 = (long long)M * N / 4;
+    const double th = (double)p * 4294967296.0;
+    const uint32_t thresh = th >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)th;
+    long long grid = (n4 + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    relu_dropout_fwd_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_parts, n_parts, d_bias, n4, N / 4, thresh, 1.0f / (1.0f - p), seed,
+                                                                              reinterpret_cast<const long long*>(d_step), tag, d_out);
+    note_launch();
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
+}
+
+int idl_relu_dropout_backward(const float* d_out, const float* d_dy, int64_t n, float p, float* d_dx, void* stream) {
+    if (!d_out || !d_dy || !d_dx || n < 4 || (n & 3) || !(p >= 0.f) || !(p < 1.f)) return set_error(IDL_EINVAL, "idl_relu_dropout_backward: bad argument%s", "");
+    long long grid = (n / 4 + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    relu_dropout_bwd_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_out, d_dy, n / 4, 1.0f / (1.0f - p), d_dx);
+    note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;
 }

@@ -17,29 +17,80 @@ from .PytorchUtils import NetLinear
 from .models import weights_init
 
 
-class _FirstLinear(torch.autograd.Function):
-    """The encoder's first Linear (4^k -> 512: 97 % of the MLP's flops) as PyTorch / cuBLAS calls shaped for this batch: the forward
-    contraction [2B, 4^k] x [4^k, 512] is split over its inner dimension into ONE batched GEMM (more output tiles than SMs: 110 ->
-    84 us at 2B = 1024 in strict fp32) whose parts are summed with the bias; the backward writes the weight gradient straight into
-    its slice of the flat gradient buffer (no zero-fill and no accumulate pass over 8.4 MB) and needs no input gradient."""
+def _relu_dropout_fwd(parts, n_parts, bias, M, N, drop):
+    """idl_relu_dropout_forward on [n_parts, M, N] partial products (+ bias): the post-dropout activations [M, N]"""
+    from . import _lib
+    lib = _lib.load()
+    p, seed, step, tag = drop
+    out = torch.empty((M, N), dtype=torch.float32, device=parts.device)
+    with torch.cuda.device(parts.device):
+        _lib.check(lib.idl_relu_dropout_forward(_lib.ptr(parts), n_parts, _lib.ptr(bias), M, N, float(p), int(seed) & (2 ** 64 - 1), _lib.ptr(step),
+                                                int(tag), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def _relu_dropout_bwd(out, dy, p):
+    from . import _lib
+    lib = _lib.load()
+    dy = dy.contiguous()
+    dx = torch.empty_like(out)
+    with torch.cuda.device(out.device):
+        _lib.check(lib.idl_relu_dropout_backward(_lib.ptr(out), _lib.ptr(dy), out.numel(), float(p), _lib.ptr(dx), _lib.stream_ptr()))
+    return dx
+
+
+class _ReluDropout(torch.autograd.Function):
+    """ReLU - Dropout(p) (idelucs/PytorchUtils.py:40-44) as one kernel each way; the backward needs no stored mask (the output is
+    positive exactly where the unit was active and kept)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gw_out, gb_out, n_split, side=None):
-        M, K = x.shape
-        N = weight.shape[0]
-        if n_split > 1 and K % n_split == 0:
-            parts = torch.bmm(x.view(M, n_split, K // n_split).transpose(0, 1), weight.view(N, n_split, K // n_split).permute(1, 2, 0))
-            out = parts.sum(0)
-            out += bias
-        else:
-            out = torch.addmm(bias, x, weight.t())
-        ctx.save_for_backward(x)
-        ctx.gw_out, ctx.gb_out, ctx.side = gw_out, gb_out, side
+    def forward(ctx, x, drop):
+        x = x.contiguous()
+        out = _relu_dropout_fwd(x, 1, None, x.shape[0], x.shape[1], drop)
+        ctx.save_for_backward(out)
+        ctx.p = drop[0]
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
+        (out,) = ctx.saved_tensors
+        return _relu_dropout_bwd(out, dy, ctx.p), None
+
+
+class _FirstLinear(torch.autograd.Function):
+    """The encoder's first Linear (4^k -> 512: 97 % of the MLP's flops) as PyTorch / cuBLAS calls shaped for this batch: the forward
+    contraction [2B, 4^k] x [4^k, 512] is split over its inner dimension into ONE batched GEMM (more output tiles than SMs: 110 ->
+    84 us at 2B = 1024 in strict fp32); the backward writes the weight gradient straight into its slice of the flat gradient buffer
+    (no zero-fill and no accumulate pass over 8.4 MB) and needs no input gradient.  With ``drop`` = (p, seed, step tensor, tag) the
+    ReLU - Dropout behind the layer is part of it: the parts of the split GEMM, the bias, the activation and the dropout are ONE
+    kernel (idl_relu_dropout_forward) instead of a reduction and three elementwise launches, and the output is the activation."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gw_out, gb_out, n_split, side=None, drop=None):
+        M, K = x.shape
+        N = weight.shape[0]
+        if n_split > 1 and K % n_split == 0:
+            parts = torch.bmm(x.view(M, n_split, K // n_split).transpose(0, 1), weight.view(N, n_split, K // n_split).permute(1, 2, 0))
+        else:
+            n_split = 1
+            parts = torch.mm(x, weight.t())
+        if drop is not None:
+            out = _relu_dropout_fwd(parts, n_split, bias, M, N, drop)
+            ctx.save_for_backward(x, out)
+        else:
+            out = parts.sum(0) if n_split > 1 else parts
+            out += bias
+            ctx.save_for_backward(x)
+        ctx.gw_out, ctx.gb_out, ctx.side, ctx.drop = gw_out, gb_out, side, drop
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        if ctx.drop is not None:
+            x, out = ctx.saved_tensors
+            dy = _relu_dropout_bwd(out, dy, ctx.drop[0])
+        else:
+            (x,) = ctx.saved_tensors
         if ctx.side is not None:   # the bias gradient (a column sum) runs beside the weight-gradient GEMM; the caller joins the streams
             main = torch.cuda.current_stream(dy.device)
             ctx.side.wait_stream(main)
@@ -49,7 +100,7 @@ class _FirstLinear(torch.autograd.Function):
         else:
             torch.mm(dy.t(), x, out=ctx.gw_out)
             torch.sum(dy, 0, out=ctx.gb_out)
-        return None, None, None, None, None, None, None
+        return None, None, None, None, None, None, None, None
 
 
 class _FlatLinear(torch.autograd.Function):
@@ -134,6 +185,8 @@ class ShardedTrainer(object):
         self._grad_tail = self._flat_grad[n1:]
         self.first_layer_split = 4
         self._ones = torch.ones((1, 2 * batch_sz), dtype=torch.float32, device=self.dev)
+        self._step_no = torch.zeros((), dtype=torch.int64, device=self.dev)
+        self._drop_seed = (seed * 1000003 + 7919 * self.rank + 12345) & (2 ** 63 - 1)   # dropout masks differ between the replicas
         if world > 1:   # replicas must start identical whatever the RNG state of the rank was
             dist.broadcast(self._flat_param, src=0)
         self._shard = (n + pad) // world if self._mode == "symm" else n + pad
@@ -248,20 +301,25 @@ class ShardedTrainer(object):
             return self._loss
         return self._step_from_ids()
 
-    def _tail(self, a1):
-        """NetLinear.forward behind the first Linear (PytorchUtils.py: ReLU - Dropout - Linear -> latent; ReLU - Dropout - Linear -
-        Softmax -> cluster probabilities), the two Linears through _FlatLinear: (cluster probabilities, latent)"""
-        F = torch.nn.functional
+    def _drop(self, tag):
+        """dropout descriptor of the fused ReLU - Dropout kernels: (p, seed, step counter on the device, layer tag); p = 0 in eval mode"""
+        return (0.5 if self.net.training else 0.0, self._drop_seed, self._step_no, tag)
+
+    def _tail(self, d1):
+        """NetLinear.forward behind the first Linear - ReLU - Dropout block (PytorchUtils.py: Linear -> latent; ReLU - Dropout -
+        Linear - Softmax -> cluster probabilities), the two Linears through _FlatLinear: (cluster probabilities, latent)"""
         lin2, lin3 = self.net.layers[3], self.net.classifier[2]
-        tr = self.net.training
-        h = _FlatLinear.apply(F.dropout(F.relu(a1), 0.5, tr), lin2.weight, lin2.bias, lin2.weight.grad, lin2.bias.grad, self._ones)
-        z = torch.softmax(_FlatLinear.apply(F.dropout(F.relu(h), 0.5, tr), lin3.weight, lin3.bias, lin3.weight.grad, lin3.bias.grad, self._ones), 1)
+        h = _FlatLinear.apply(d1, lin2.weight, lin2.bias, lin2.weight.grad, lin2.bias.grad, self._ones)
+        z = torch.softmax(_FlatLinear.apply(_ReluDropout.apply(h, self._drop(2)), lin3.weight, lin3.bias, lin3.weight.grad, lin3.bias.grad,
+                                            self._ones), 1)
         return z, h
 
-    def _forward(self, x):
-        """NetLinear.forward with the Linears issued by _FirstLinear / _FlatLinear: (cluster probabilities, latent) of the stacked batch"""
+    def _forward(self, x, side=None):
+        """NetLinear.forward with the Linears issued by _FirstLinear / _FlatLinear and ReLU - Dropout by the fused kernels: (cluster
+        probabilities, latent) of the stacked batch"""
         lin1 = self.net.layers[0]
-        return self._tail(_FirstLinear.apply(x, lin1.weight, lin1.bias, lin1.weight.grad, lin1.bias.grad, self.first_layer_split))
+        d1 = _FirstLinear.apply(x, lin1.weight, lin1.bias, lin1.weight.grad, lin1.bias.grad, self.first_layer_split, side, self._drop(1))
+        return self._tail(d1)
 
     def _step_from_ids(self):
         if self._batch is None:
@@ -279,12 +337,13 @@ class ShardedTrainer(object):
         # (every parameter's gradient is WRITTEN by _FirstLinear / _FlatLinear into its slice of the flat buffer: nothing to zero)
         # one pass over the stacked [2B, F] batch: same per-row math as the reference's two forwards
         lin1 = self.net.layers[0]
-        a1 = _FirstLinear.apply(x, lin1.weight, lin1.bias, lin1.weight.grad, lin1.bias.grad, self.first_layer_split, self._side)
+        self._step_no.add_(1)   # (the fused dropout kernels read it on the device: a graph replay draws fresh masks)
+        d1 = _FirstLinear.apply(x, lin1.weight, lin1.bias, lin1.weight.grad, lin1.bias.grad, self.first_layer_split, self._side, self._drop(1))
         if not late:
             self._side.wait_stream(main)          # (after the first layer's forward GEMM)
             with torch.cuda.stream(self._side):
                 nxt = self._featurise(self._ids, cta_cap=1)
-        z, h = self._tail(a1)
+        z, h = self._tail(d1)
         # (1 - w) InfoNCE + w IIC (models.py:128) and its gradients with respect to z and h straight from the fused kernels (the
         # weights ride inside them); the MLP's backward pass is seeded with those — no framework kernel between forward and backward
         loss, dz, dh = train_losses_and_grads(z, h, self.lamb, self.weight, 0.85)

@@ -274,6 +274,16 @@ int idl_nce_normalize_backward(const float* d_dfn, const float* d_fn, const floa
 int idl_nce_normalize_backward_parts(const float* d_dfn_parts, int n_parts, const float* d_fn, const float* d_inv_norm, int n2, int D,
                                      float* d_dh, void* stream);
 
+/* ReLU + Dropout(p) of the encoder (idelucs/PytorchUtils.py:36-44) fused with the tail of the Linear before it, one pass each way.
+ * forward: v = sum over the n_parts partial products d_parts[n_parts, M, N] (n_parts = 1: a plain activation matrix) + d_bias[N]
+ * (NULL: none); d_out = (v > 0 and kept) ? v / (1 - p) : 0.  The keep decision of an element in training step *d_step (device
+ * int64, NULL = 0; read at run time, so a CUDA graph replays the call with a fresh mask) is a Philox4x32-10 word keyed by seed, the
+ * step, the element index and `tag` (one per layer).  backward: d_dx = d_out > 0 ? d_dy / (1 - p) : 0 — no mask is stored.
+ * N a multiple of 4. */
+int idl_relu_dropout_forward(const float* d_parts, int n_parts, const float* d_bias, int64_t M, int N, float p, uint64_t seed,
+                             const int64_t* d_step, uint32_t tag, float* d_out, void* stream);
+int idl_relu_dropout_backward(const float* d_out, const float* d_dy, int64_t n, float p, float* d_dx, void* stream);
+
 /* Row ids of the reference's x_train (idelucs/utils.py:321-389: row r = sequence r mod N paired with mimic r div N + 1) -> the
  * arguments of idl_profiles' selection mode for one batch: d_sidx[n] = sequence index, d_sel[n, 2] = (0, mimic slot).  Replaces the
  * index arithmetic AugmentedDataset.__getitem__ does per item. */

@@ -603,31 +603,65 @@ def test_iid_tiled_kernel_equals_gemm_route_and_oracle():
 
 
 def test_trainer_forward_backward_equals_plain_module():
-    """ShardedTrainer._forward (_FirstLinear + _FlatLinear: gradients written into the flat buffer, nothing zeroed or accumulated)
-    against the plain NetLinear module + autograd with the same dropout masks: same outputs, same gradient for every parameter —
-    also on the second step, when the flat buffer still holds the previous gradients"""
+    """ShardedTrainer._forward (_FirstLinear + _FlatLinear + fused ReLU - Dropout kernels: gradients written into the flat buffer,
+    nothing zeroed or accumulated) against the plain NetLinear module + autograd.  Dropout off (eval mode, p = 0 in the fused
+    kernels): same outputs, same gradient for every parameter — also on the second step, when the flat buffer still holds the previous
+    gradients.  Dropout on: the masks come from the kernels' own counter-based stream, so the module is re-run with exactly those masks."""
     from idelucs_b200.seqset import SeqSet
     from idelucs_b200.train import ShardedTrainer
     rng = np.random.default_rng(3)
     seqs = [np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=600)].tobytes() for _ in range(700)]
     tr = ShardedTrainer(SeqSet.from_sequences(seqs), k=6, n_clusters=5, n_mimics=3, batch_sz=256, seed=1)
     params = [p for p in tr.net.parameters()]
+    tr.net.eval()
     for step in range(2):
         x = torch.randn(512, 4096, device="cuda")
         gz, gh = torch.randn(512, 5, device="cuda"), torch.randn(512, 64, device="cuda")
-        torch.manual_seed(100 + step)
         z, h = tr._forward(x)
         torch.autograd.backward((z, h), (gz, gh))
         got = [p.grad.detach().clone() for p in params]
         zo, ho = z.detach().clone(), h.detach().clone()
         for p in params:
             p.grad.zero_()
-        torch.manual_seed(100 + step)
         z2, h2 = tr.net(x)
         torch.autograd.backward((z2, h2), (gz, gh))
         assert torch.allclose(zo, z2, rtol=1e-4, atol=1e-6) and torch.allclose(ho, h2, rtol=1e-4, atol=1e-4)
         for g, p in zip(got, params):
             assert float((g - p.grad).abs().max()) <= 2e-4 * float(p.grad.abs().max()) + 1e-7, (step, tuple(p.shape))
+    # training mode: recover the masks the fused kernels drew and replay the module's arithmetic with them
+    tr.net.train()
+    lin1, lin2, lin3 = tr.net.layers[0], tr.net.layers[3], tr.net.classifier[2]
+    x = torch.randn(512, 4096, device="cuda")
+    gz, gh = torch.randn(512, 5, device="cuda"), torch.randn(512, 64, device="cuda")
+    tr._step_no.fill_(5)
+    z, h = tr._forward(x)
+    torch.autograd.backward((z, h), (gz, gh))
+    got = [p.grad.detach().clone() for p in params]
+    with torch.no_grad():
+        a1 = torch.addmm(lin1.bias, x, lin1.weight.t())
+    from idelucs_b200.train import _relu_dropout_fwd
+    d1 = _relu_dropout_fwd(a1.unsqueeze(0).contiguous(), 1, None, 512, 512, tr._drop(1))
+    m1 = (d1 != 0) | (a1 <= 0)                       # kept (where the unit was active; irrelevant elsewhere)
+    keep1 = float(((d1 != 0) & (a1 > 0)).sum()) / float((a1 > 0).sum())
+    assert abs(keep1 - 0.5) < 0.01, keep1
+    assert torch.equal(d1, torch.where((a1 > 0) & m1, a1 * 2.0, torch.zeros_like(a1)))
+    d2k = _relu_dropout_fwd(h.detach().unsqueeze(0).contiguous(), 1, None, 512, 64, tr._drop(2))
+    m2 = (d2k != 0) | (h.detach() <= 0)
+    for p in params:
+        p.grad.zero_()
+    a1r = torch.addmm(lin1.bias, x, lin1.weight.t())
+    h2 = torch.addmm(lin2.bias, torch.relu(a1r) * m1 * 2.0, lin2.weight.t())
+    z2 = torch.softmax(torch.addmm(lin3.bias, torch.relu(h2) * m2 * 2.0, lin3.weight.t()), 1)
+    torch.autograd.backward((z2, h2), (gz, gh))
+    assert torch.allclose(z.detach(), z2, rtol=1e-4, atol=1e-6) and torch.allclose(h.detach(), h2, rtol=1e-4, atol=1e-4)
+    for g, p in zip(got, params):
+        assert float((g - p.grad).abs().max()) <= 2e-4 * float(p.grad.abs().max()) + 1e-7, tuple(p.shape)
+    # another step number: another mask; the same step number: the same mask
+    tr._step_no.fill_(6)
+    d1b = _relu_dropout_fwd(a1.unsqueeze(0).contiguous(), 1, None, 512, 512, tr._drop(1))
+    tr._step_no.fill_(5)
+    d1c = _relu_dropout_fwd(a1.unsqueeze(0).contiguous(), 1, None, 512, 512, tr._drop(1))
+    assert torch.equal(d1c, d1) and not torch.equal(d1b, d1)
 
 
 def test_first_linear_split_equals_nn_linear():
