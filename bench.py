@@ -598,7 +598,7 @@ def run_ours(args):
                                             % ("NVLS multimem.ld_reduce / multimem.st" if getattr(tr, "_mc", (0, 0))[0] else "peer loads / stores")}[tr._mode],
                  "config": "synthetic %d sequences x 2000 bp sharded over %d GPU(s), k=6, n_mimics=50, batch_sz=512 per rank, "
                            "n_clusters=5, RMSprop, (1-w) InfoNCE + w IIC (BASELINE.json configs[3]); shuffled epochs; batches regenerated "
-                           "on a side stream by the mimic kernel; fused InfoNCE / IIC / RMSprop kernels, MLP in PyTorch fp32; "
+                           "on a side stream by the mimic kernel; fused InfoNCE / IIC / ReLU-Dropout / RMSprop kernels, every contraction of the MLP a PyTorch / cuBLAS GEMM in strict fp32; "
                            "gradient mean + RMSprop + parameter broadcast as one kernel inside the step's CUDA graph" % (nt * world, world)}
         peak_gbs, _ = measured_peak()
         train["hbm_floor_fraction"] = train["pairs_per_s"] / world * 65536 / (peak_gbs * 1e9)   # 2 profiles written + 2 read per pair
