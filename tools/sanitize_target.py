@@ -55,6 +55,18 @@ def main():
         lib = _lib.load()
         p, g, v = torch.randn(1000, device="cuda"), torch.randn(1000, device="cuda"), torch.zeros(1000, device="cuda")
         _lib.check(lib.idl_rmsprop_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(v), 1000, 1e-3, 0.99, 1e-8, 0.01, 1.0, _lib.stream_ptr()))
+        # the C ABI's own tiled kernel (the Python layer takes the GEMM route above 16 clusters)
+        from idelucs_b200.LossFunctions import _ws
+        z1 = torch.softmax(torch.randn(96, 40, device="cuda"), 1); z2 = torch.softmax(torch.randn(96, 40, device="cuda"), 1)
+        lo = torch.empty((), device="cuda"); d1 = torch.empty_like(z1); d2 = torch.empty_like(z2); ws = _ws(z1.device, 40)
+        _lib.check(lib.idl_iid_loss(_lib.ptr(z1), _lib.ptr(z2), 96, 40, 2.8, 2.2e-16, _lib.ptr(lo), None, _lib.ptr(d1), _lib.ptr(d2), _lib.ptr(ws),
+                                    ws.numel(), _lib.stream_ptr()))
+        # two eager training steps: fused ReLU - Dropout kernels, pair selection, capped featurisation on the side stream, optimiser
+        from idelucs_b200.train import ShardedTrainer
+        seqs = [alph[rng.integers(0, 4, size=400)].tobytes() for _ in range(300)]
+        tr = ShardedTrainer(SeqSet.from_sequences(seqs), k=6, n_clusters=5, n_mimics=3, batch_sz=64, seed=2)
+        for _ in range(2):
+            tr.step()
         ids = torch.randint(0, 5000, (300,), device="cuda")
         sidx = torch.empty(300, dtype=torch.int32, device="cuda"); sel = torch.empty((300, 2), dtype=torch.int32, device="cuda")
         _lib.check(lib.idl_pair_selection(_lib.ptr(ids), 300, 100, _lib.ptr(sidx), _lib.ptr(sel), _lib.stream_ptr()))
