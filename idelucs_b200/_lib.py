@@ -67,6 +67,7 @@ PROTOTYPES = {
     "idl_nce_normalize_backward_parts": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "idl_relu_dropout_forward": (c_int, [c_void_p, c_int, c_void_p, c_i64, c_int, c_float, c_u64, c_void_p, ctypes.c_uint32, c_void_p, c_void_p]),
     "idl_relu_dropout_backward": (c_int, [c_void_p, c_void_p, c_i64, c_float, c_void_p, c_void_p]),
+    "idl_sum_parts_bias": (c_int, [c_void_p, c_int, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "idl_pair_selection": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p]),
     "idl_rmsprop_step": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float, c_void_p]),
     "idl_rmsprop_allreduce_step": (c_int, [c_void_p, c_void_p, c_u64, c_u64, c_void_p, c_i64, c_int, c_int, c_float, c_float, c_float, c_float, c_void_p]),

@@ -337,6 +337,24 @@ __global__ void __launch_bounds__(256) relu_dropout_fwd_kernel(const float* __re
     }
 }
 
+// out = sum_p parts[p] + bias: the tail of a Linear whose GEMM was split over its inner dimension (no activation)
+__global__ void __launch_bounds__(256) sum_parts_bias_kernel(const float* __restrict__ parts, int n_parts, const float* __restrict__ bias, long long n4, int N4,
+                                                             float* __restrict__ out) {
+    const size_t part4 = (size_t)n4;
+    for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < n4; q += (long long)gridDim.x * 256) {
+        float4 v = reinterpret_cast<const float4*>(parts)[q];
+        for (int p = 1; p < n_parts; ++p) {
+            const float4 w = reinterpret_cast<const float4*>(parts)[p * part4 + q];
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (int)(q % N4));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        reinterpret_cast<float4*>(out)[q] = v;
+    }
+}
+
 __global__ void __launch_bounds__(256) relu_dropout_bwd_kernel(const float* __restrict__ out, const float* __restrict__ dy, long long n4, float inv_keep,
                                                                float* __restrict__ dx) {
     for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < n4; q += (long long)gridDim.x * 256) {
@@ -806,6 +824,17 @@ int idl_relu_dropout_forward(const float* d_parts, int n_parts, const float* d_b
     if (grid > 148 * 8) grid = 148 * 8;
     relu_dropout_fwd_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_parts, n_parts, d_bias, n4, N / 4, thresh, 1.0f / (1.0f - p), seed,
                                                                               reinterpret_cast<const long long*>(d_step), tag, d_out);
+    note_launch();
+    IDL_CUDA_CHECK(cudaGetLastError());
+    return IDL_OK;
+}
+
+int idl_sum_parts_bias(const float* d_parts, int n_parts, const float* d_bias, int64_t M, int N, float* d_out, void* stream) {
+    if (!d_parts || !d_out || n_parts < 1 || M < 1 || N < 4 || (N & 3)) return set_error(IDL_EINVAL, "idl_sum_parts_bias: bad argument%s (N must be a multiple of 4)", "");
+    const long long n4 = (long long)M * N / 4;
+    long long grid = (n4 + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    sum_parts_bias_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d_parts, n_parts, d_bias, n4, N / 4, d_out);
     note_launch();
     IDL_CUDA_CHECK(cudaGetLastError());
     return IDL_OK;

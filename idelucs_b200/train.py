@@ -103,27 +103,52 @@ class _FirstLinear(torch.autograd.Function):
         return None, None, None, None, None, None, None, None
 
 
+def _split_mm(a, b, ns):
+    """a [M, K] @ b [K, N] as ONE batched GEMM over ns slices of K -> partial products [ns, M, N] (a GEMM with few output tiles
+    leaves most SMs idle: [1024, 512] x [512, 64] takes 11 us as one GEMM, 4.6 us split 8-fold — tools/mlp_probe.py)"""
+    M, K = a.shape
+    N = b.shape[1]
+    aa = a.reshape(M, ns, K // ns).transpose(0, 1) if a.is_contiguous() else a.t().reshape(ns, K // ns, M).transpose(1, 2)
+    bb = b.reshape(ns, K // ns, N) if b.is_contiguous() else b.t().reshape(N, ns, K // ns).permute(1, 2, 0)
+    return torch.bmm(aa, bb)
+
+
 class _FlatLinear(torch.autograd.Function):
-    """A later Linear of the encoder (same addmm as nn.Linear): its weight and bias gradients go straight into their slices of the
-    flat gradient buffer (no zero-fill, no accumulate pass per parameter), the bias gradient of a wide layer as a [1, M] x [M, N]
-    product (the framework's column reduction of a [1024, 64] matrix takes 10 us)."""
+    """A later Linear of the encoder: its weight and bias gradients go straight into their slices of the flat gradient buffer (no
+    zero-fill, no accumulate pass per parameter), the bias gradient of a wide layer as a [1, M] x [M, N] product (the framework's
+    column reduction of a [1024, 64] matrix takes 10 us).  ``split`` = (forward, weight-gradient) inner-dimension splits of the two
+    contractions with few output tiles; the parts are added by idl_sum_parts_bias / one reduction into the flat buffer."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gw_out, gb_out, ones):
+    def forward(ctx, x, weight, bias, gw_out, gb_out, ones, split=(1, 1)):
         ctx.save_for_backward(x, weight)
-        ctx.gw_out, ctx.gb_out, ctx.ones = gw_out, gb_out, ones
+        ctx.gw_out, ctx.gb_out, ctx.ones, ctx.wsplit = gw_out, gb_out, ones, split[1]
+        M, K = x.shape
+        N = weight.shape[0]
+        if split[0] > 1 and K % split[0] == 0 and N % 4 == 0 and x.is_contiguous():
+            from . import _lib
+            lib = _lib.load()
+            parts = _split_mm(x, weight.t(), split[0])
+            out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                _lib.check(lib.idl_sum_parts_bias(_lib.ptr(parts), split[0], _lib.ptr(bias), M, N, _lib.ptr(out), _lib.stream_ptr()))
+            return out
         return torch.addmm(bias, x, weight.t())
 
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
         M, N = dy.shape
-        torch.mm(dy.t(), x, out=ctx.gw_out)
+        dy = dy.contiguous()
+        if ctx.wsplit > 1 and M % ctx.wsplit == 0:
+            torch.sum(_split_mm(dy.t(), x, ctx.wsplit), 0, out=ctx.gw_out)
+        else:
+            torch.mm(dy.t(), x, out=ctx.gw_out)
         if N >= 32 and ctx.ones.shape[1] >= M:
             torch.mm(ctx.ones[:, :M], dy, out=ctx.gb_out.view(1, N))
         else:
             torch.sum(dy, 0, out=ctx.gb_out)
-        return torch.mm(dy, weight), None, None, None, None, None
+        return torch.mm(dy, weight), None, None, None, None, None, None
 
 
 class ShardedTrainer(object):
@@ -184,6 +209,7 @@ class ShardedTrainer(object):
         n1 = params[0].numel() + params[1].numel()   # layers.0.weight, layers.0.bias come first
         self._grad_tail = self._flat_grad[n1:]
         self.first_layer_split = 4
+        self.small_gemm_split = (8, 16)   # forward / weight-gradient splits of the later Linears' contractions
         self._ones = torch.ones((1, 2 * batch_sz), dtype=torch.float32, device=self.dev)
         self._step_no = torch.zeros((), dtype=torch.int64, device=self.dev)
         self._drop_seed = (seed * 1000003 + 7919 * self.rank + 12345) & (2 ** 63 - 1)   # dropout masks differ between the replicas
@@ -309,9 +335,9 @@ class ShardedTrainer(object):
         """NetLinear.forward behind the first Linear - ReLU - Dropout block (PytorchUtils.py: Linear -> latent; ReLU - Dropout -
         Linear - Softmax -> cluster probabilities), the two Linears through _FlatLinear: (cluster probabilities, latent)"""
         lin2, lin3 = self.net.layers[3], self.net.classifier[2]
-        h = _FlatLinear.apply(d1, lin2.weight, lin2.bias, lin2.weight.grad, lin2.bias.grad, self._ones)
+        h = _FlatLinear.apply(d1, lin2.weight, lin2.bias, lin2.weight.grad, lin2.bias.grad, self._ones, self.small_gemm_split)
         z = torch.softmax(_FlatLinear.apply(_ReluDropout.apply(h, self._drop(2)), lin3.weight, lin3.bias, lin3.weight.grad, lin3.bias.grad,
-                                            self._ones), 1)
+                                            self._ones, (1, self.small_gemm_split[1])), 1)
         return z, h
 
     def _forward(self, x, side=None):

@@ -283,6 +283,8 @@ int idl_nce_normalize_backward_parts(const float* d_dfn_parts, int n_parts, cons
 int idl_relu_dropout_forward(const float* d_parts, int n_parts, const float* d_bias, int64_t M, int N, float p, uint64_t seed,
                              const int64_t* d_step, uint32_t tag, float* d_out, void* stream);
 int idl_relu_dropout_backward(const float* d_out, const float* d_dy, int64_t n, float p, float* d_dx, void* stream);
+/* the same tail without activation: d_out[M, N] = sum over d_parts[n_parts, M, N] + d_bias[N] (NULL: none) */
+int idl_sum_parts_bias(const float* d_parts, int n_parts, const float* d_bias, int64_t M, int N, float* d_out, void* stream);
 
 /* Row ids of the reference's x_train (idelucs/utils.py:321-389: row r = sequence r mod N paired with mimic r div N + 1) -> the
  * arguments of idl_profiles' selection mode for one batch: d_sidx[n] = sequence index, d_sel[n, 2] = (0, mimic slot).  Replaces the
