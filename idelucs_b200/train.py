@@ -1,13 +1,19 @@
 """Sharded training loop on top of the hot path (BASELINE.json configs[3]: synthetic 1 M x 2 kb,
 k=6, n_mimics=50, batch_sz=512, sharded over 1/2/4/8 B200).
 
-Each rank owns a contiguous shard of the packed sequences, regenerates its pair batches on
-the fly with the mimic kernel (selection mode — the 1.6 TB x_train of the reference never
-exists), runs the reference's training step (idelucs/models.py:113-143: two forwards,
-(1-w) InfoNCE + w IIC loss, backward, RMSprop) with the fused IIC kernel, and all-reduces the
-gradients of the data-parallel MLP replicas over NCCL: parameters, gradients and the RMSprop state live in flat buffers;
-per step ONE kernel averages the gradient slices over NVLink (8.5 MB at k=6), applies RMSprop and broadcasts the new parameters
-(idl_rmsprop_allreduce_step), captured in the step's CUDA graph; the next pair batch is regenerated on a side stream.  batch_sz is PER RANK (weak scaling in the batch, strong in the data set)."""
+Each rank owns a contiguous shard of the packed sequences, regenerates its pair batches on the fly with the mimic kernel (selection
+mode — the 1.6 TB x_train of the reference never exists) and runs the reference's training step (idelucs/models.py:113-143: two
+forwards, (1-w) InfoNCE + w IIC loss, backward, RMSprop) as ONE CUDA graph on two streams:
+
+  * every dense contraction of the encoder stays a PyTorch / cuBLAS GEMM in strict fp32, issued in the shape that fills the GPU for
+    this batch (_FirstLinear / _FlatLinear: inner-dimension splits as batched GEMMs, gradients written straight into a flat buffer);
+  * everything between the GEMMs is a hand-written kernel behind the C ABI: ReLU - Dropout fused with the tail of the GEMM before it,
+    the two losses with their weights and gradients (LossFunctions.train_losses_and_grads seeds the backward pass), the optimiser;
+  * parameters, gradients and the RMSprop state live in flat buffers; with several ranks ONE kernel averages the gradient slices over
+    NVLink (8.5 MB at k=6), applies RMSprop and broadcasts the new parameters (idl_rmsprop_allreduce_step);
+  * the next pair batch is regenerated on the side stream under the middle of the step.
+
+batch_sz is PER RANK (weak scaling in the batch, strong in the data set)."""
 import torch
 import torch.distributed as dist
 
@@ -154,13 +160,15 @@ class _FlatLinear(torch.autograd.Function):
 class ShardedTrainer(object):
     """Data-parallel replica of the reference's training step (idelucs/models.py:113-143) fed by the mimic kernel.
 
-    Step layout (captured in ONE CUDA graph, two streams):
-      side stream  pair batch t+1 regenerated from the packed sequences (selection mode of idl_profiles) — independent of
-                   the weights, so it runs under the collectives of step t;
-      main stream  forward over the stacked [2B, F] batch t -> fused InfoNCE + fused IIC loss -> backward into ONE flat
-                   gradient buffer -> idl_rmsprop_allreduce_step: gradient mean + RMSprop + parameter broadcast as one kernel
-                   over NVLink peer memory (symmetric buffers, NVLS multimem when available; NCCL all-reduce + idl_rmsprop_step
-                   when symmetric memory cannot be set up).  At N = 1 the optimiser is one elementwise pass.
+    Step layout (captured in ONE CUDA graph, two streams; kernel timeline: profiles/train_timeline_r2.txt):
+      main stream  first Linear's forward (batched split GEMM) + its ReLU - Dropout kernel -> second / third Linear -> fused InfoNCE +
+                   IIC losses, whose gradients seed the backward -> backward, every gradient written into ONE flat buffer -> optimiser:
+                   idl_rmsprop_step at N = 1; with several ranks idl_rmsprop_allreduce_step (gradient mean + RMSprop + parameter
+                   broadcast as one kernel over NVLink peer memory: symmetric buffers, NVLS multimem when available; NCCL
+                   all-reduce + idl_rmsprop_step when symmetric memory cannot be set up);
+      side stream  pair batch t+1 regenerated from the packed sequences (selection mode of idl_profiles, one CTA per SM) under the
+                   small kernels of the middle of the step, the first layer's bias gradient beside its weight-gradient GEMM, the
+                   hand-over of the batch beside the optimiser.
     The parameters of the network are views into one flat buffer, so the optimiser and the collectives see one tensor."""
 
     def __init__(self, seqset, k=6, n_clusters=5, n_mimics=50, batch_sz=512, lamb=2.8, weight=0.25, lr=1e-3, seed=0,
@@ -206,8 +214,6 @@ class ShardedTrainer(object):
             p.data = self._flat_param[o:o + p.numel()].view_as(p)
             p.grad = self._flat_grad[o:o + p.numel()].view_as(p)
             o += p.numel()
-        n1 = params[0].numel() + params[1].numel()   # layers.0.weight, layers.0.bias come first
-        self._grad_tail = self._flat_grad[n1:]
         self.first_layer_split = 4
         self.small_gemm_split = (8, 16)   # forward / weight-gradient splits of the later Linears' contractions
         self._ones = torch.ones((1, 2 * batch_sz), dtype=torch.float32, device=self.dev)
