@@ -26,9 +26,15 @@ namespace idl {
 #define PR_PACKED 0                        // 0: int32 bins, 4 CTAs/SM (0.70 ms per 20 000 sequences); 1: uint16-pair histogram + 1024-entry edit list,
                                            //    39 KB of shared memory, 5 CTAs/SM — measured slower (0.74 ms: packed updates + the 48-register cap)
 #endif
-constexpr int PR_NT = 256;
+#ifndef PR_NT_N
+#define PR_NT_N 256
+#endif
+#ifndef PR_MINB_N
+#define PR_MINB_N (PR_PACKED ? 5 : 4)
+#endif
+constexpr int PR_NT = PR_NT_N;
 constexpr int PR_LIST = PR_PACKED ? 1024 : 2048;   // edits of all dense slots of one sequence
-constexpr int PR_MINB = PR_PACKED ? 5 : 4;
+constexpr int PR_MINB = PR_MINB_N;
 
 struct PrSmem {
 #if PR_PACKED
