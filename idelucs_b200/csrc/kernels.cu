@@ -119,6 +119,14 @@ __global__ void __launch_bounds__(PACK_NT) pack_kernel(const uint8_t* __restrict
                                                         const int64_t* __restrict__ chunk_off, long long n, int strict,
                                                         uint32_t* __restrict__ codes, uint32_t* __restrict__ nmask,
                                                         int32_t* __restrict__ len, unsigned long long* __restrict__ bad) {
+    // byte -> class table of the alphabet (core.cuh base_class: the switch itself costs ~40 divergent instructions per byte):
+    // bits 0-1 = code (0 for a non-base), bit 2 = reset flag, bits 3-5 = class when the byte is deleted / invalid (5 / 6), else 0
+    __shared__ uint8_t lut[256];
+    for (int i = threadIdx.x; i < 256; i += PACK_NT) {
+        const uint32_t cls = base_class((uint32_t)i, strict);
+        lut[i] = (uint8_t)(cls < 4 ? cls : (4u | (cls >= 5 ? cls << 3 : 0u)));
+    }
+    __syncthreads();
     for (long long s = blockIdx.x; s <= n; s += gridDim.x) {
         if (s == n) {  // slack chunk behind the last sequence: all padding
             if (blockIdx.y == 0 && threadIdx.x < 4) codes[chunk_off[n] * 4 + threadIdx.x] = 0u;
@@ -132,22 +140,49 @@ __global__ void __launch_bounds__(PACK_NT) pack_kernel(const uint8_t* __restrict
         if (blockIdx.y == 0 && threadIdx.x == 0) len[s] = (int32_t)L;
         unsigned long long first_bad = ~0ull;
         for (long long h = (long long)blockIdx.y * PACK_NT + threadIdx.x; h < nhalf; h += (long long)PACK_NT * gridDim.y) {
+            // the 32 bytes of the half chunk as 8 little-endian words (padding behind the end of the sequence reads as 'N').  A half
+            // chunk that lies completely inside the sequence is read as aligned 32-bit words (every word holds at least one byte of the
+            // sequence, so it lies inside the caller's allocation) realigned with funnel shifts: 9 loads instead of 32 byte loads
+            // (lanes are 32 bytes apart: every load instruction costs one L1 wavefront per lane)
+            uint32_t wv[8];
+            long long avail32 = L - h * 32;
+            avail32 = avail32 < 0 ? 0 : (avail32 > 32 ? 32 : avail32);
+            if (avail32 == 32) {
+                const uint8_t* a = ascii + b0 + h * 32;
+                const uint32_t sh = ((uint32_t)(uintptr_t)a & 3u) * 8u;
+                const uint32_t* a4 = reinterpret_cast<const uint32_t*>(a - ((uintptr_t)a & 3u));
+                uint32_t w9[9];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w9[i] = __ldg(a4 + i);
+                w9[8] = sh ? __ldg(a4 + 8) : 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) wv[i] = __funnelshift_r(w9[i], w9[i + 1], sh);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) w |= (uint32_t)(i * 4 + j < avail32 ? __ldg(ascii + b0 + h * 32 + i * 4 + j) : (uint8_t)'N') << (8 * j);
+                    wv[i] = w;
+                }
+            }
             uint32_t mw = 0;
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                const long long base = h * 32 + t * 16;
-                long long avail = L - base;
-                avail = avail < 0 ? 0 : (avail > 16 ? 16 : avail);
-                uint8_t buf[16];
+                uint32_t cw = 0, m16 = 0, badv = 0;
+                int bj = 16;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) buf[j] = j < avail ? __ldg(ascii + b0 + base + j) : (uint8_t)'N';
-                uint32_t cw, m16;
-                int bj, bc;
-                pack16(buf, (int)avail, strict, &cw, &m16, &bj, &bc);
+                for (int j = 0; j < 16; ++j) {
+                    uint32_t v = lut[(wv[t * 4 + (j >> 2)] >> (8 * (j & 3))) & 0xFFu];
+                    if (t * 16 + j >= avail32) v = 4u;                      // padding: reset, never "bad"
+                    if ((v >> 3) && bj == 16) { bj = j; badv = v >> 3; }   // first deleted (5) / invalid (6) byte of this word
+                    cw = (cw << 2) | (v & 3u);
+                    m16 = (m16 << 1) | ((v >> 2) & 1u);
+                }
                 codes[c0 * 4 + h * 2 + t] = cw;
                 mw = (mw << 16) | m16;
                 if (bj < 16) {
-                    const unsigned long long v = ((unsigned long long)(base + bj) << 3) | (unsigned long long)bc;
+                    const unsigned long long v = ((unsigned long long)(h * 32 + t * 16 + bj) << 3) | (unsigned long long)badv;
                     first_bad = v < first_bad ? v : first_bad;
                 }
             }
