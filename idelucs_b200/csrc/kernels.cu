@@ -1167,8 +1167,11 @@ __global__ void __launch_bounds__(SF_NT) scaler_finalize_kernel(const double* __
 
 __global__ void standardize_f32_kernel(const float* __restrict__ x, float* __restrict__ out, long long n4, int F4,
                                        const float* __restrict__ mean, const float* __restrict__ scale) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % F4);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int cstep = (int)(stride % F4);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int c = (int)(i % F4);   // column granule, advanced incrementally (a 64-bit modulo per element costs more than the element)
+    for (; i < n4; i += stride, c = c + cstep >= F4 ? c + cstep - F4 : c + cstep) {
         const float4 v = reinterpret_cast<const float4*>(x)[i];
         const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + c);
         const float4 s = __ldg(reinterpret_cast<const float4*>(scale) + c);
@@ -1180,8 +1183,11 @@ __global__ void standardize_f32_kernel(const float* __restrict__ x, float* __res
 
 __global__ void standardize_f64_kernel(const double* __restrict__ x, double* __restrict__ out64, float* __restrict__ out32,
                                        long long total, int F, const double* __restrict__ mean, const double* __restrict__ scale) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % F);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int cstep = (int)(stride % F);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int c = (int)(i % F);
+    for (; i < total; i += stride, c = c + cstep >= F ? c + cstep - F : c + cstep) {
         const double o = (x[i] - mean[c]) / scale[c];
         if (out64) out64[i] = o;
         if (out32) out32[i] = (float)o;
